@@ -1,0 +1,228 @@
+// fcpp_internal.cuh — shared device-side definitions of libfcpp (sm_100a only).
+//
+// Numerics contract: every expression that feeds an INTEGER output (point
+// counts, violation counts, coverage cells) is evaluated in FP64 in the operation order of the
+// reference's numpy code with FMA contraction disabled (this library is compiled with
+// -fmad=false); sin/cos never run on the device for geometry — the arc tables and the heading
+// rotation come from the host — so generated path points are bit-identical to numpy's.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fcpp.h"
+
+#define FCPP_PLAN_THREADS 256
+#define FCPP_COVER_THREADS 256
+
+// speed classes of a path point (initial speeds)
+enum : uint8_t { CLS_WORK = 0, CLS_TURN = 1, CLS_HEAD = 2, CLS_REVERSE = 3 };
+
+// reference constants
+#define FCPP_ZERO_LEN 1e-6        // mlp3:526, :560, :576
+#define FCPP_KAPPA_EPS 1e-6       // mlp3:496
+#define FCPP_GEOFENCE_EPS 1e-9    // D3
+#define FCPP_MIN_SPEED_MS 0.1     // mlp3:1308
+#define FCPP_REV_SPACING 0.5      // mlp3:1214
+#define FCPP_REV_MIN_PTS 10       // mlp3:1214
+#define FCPP_REV_CAP 3.0          // mlp3:1279
+#define FCPP_CORNER_GRID_H 0.1    // mlp3:1452
+
+struct TrigTables {
+    double cos20[FCPP_UTURN_POINTS], sin20[FCPP_UTURN_POINTS];
+    double cos15[FCPP_CORNER_POINTS], sin15[FCPP_CORNER_POINTS];
+};
+
+// Per-candidate geometry record written by the layout kernel (A2-A6 scalar part) and consumed
+// by the plan and coverage kernels through one bulk (TMA) copy.  Size is a multiple of 16 B.
+struct __align__(16) CandRec {
+    int32_t status, P, K, n_main;
+    int32_t n_head, n_total, flags, field;
+    int32_t n_rev[3], corner_g;
+    int32_t vn_rev[4];
+    double R;
+    double min_x, min_y, max_x, max_y;  // swath-frame bounds of the work area (mlp3:731-732)
+    double cx, cy;                      // rotation centre (work-area centroid, mlp3:690, :710)
+    double cos_a, sin_a;                // rotate-back (mlp3:709-714)
+    double pad0;
+    double main_quad[4][2];             // R-inset of the field (mlp3:594-595), D1
+    double rev[3][5];                   // loop-0 reverse fills: ex, ey, dx, dy, length (mlp3:1154-1218)
+    double vrev[4][5];                  // verification corners (mlp3:1531-1554)
+    double corners[FCPP_MAX_LOOPS][4][2];  // inset rings of the K headland loops (mlp3:964-972)
+};
+static_assert(sizeof(CandRec) % 16 == 0, "CandRec must be bulk-copyable");
+
+struct fcpp_handle {
+    int device;
+    TrigTables *d_trig;
+    CandRec *d_rec;
+    int64_t rec_cap;
+    void *d_scan_tmp;
+    int64_t scan_tmp_cap;
+    int64_t launches;
+    int max_smem_optin;
+    int sm_count;
+    bool layout_valid;
+    int64_t layout_ncand;
+    char err[512];
+};
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// D1: mitred inset of a convex CCW quad (oracle/geom.py inset_convex — same operation order).
+__device__ inline bool inset4(const double (*v)[2], double d, double (*out)[2])
+{
+    double nx[4], ny[4], c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int k1 = (k + 1) & 3;
+        const double ex = v[k1][0] - v[k][0];
+        const double ey = v[k1][1] - v[k][1];
+        const double ln = sqrt(ex * ex + ey * ey);
+        nx[k] = -ey / ln;
+        ny[k] = ex / ln;
+        c[k] = (nx[k] * v[k][0] + ny[k] * v[k][1]) + d;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int a = (i + 3) & 3, b = i;
+        const double det = nx[a] * ny[b] - ny[a] * nx[b];
+        out[i][0] = (c[a] * ny[b] - c[b] * ny[a]) / det;
+        out[i][1] = (nx[a] * c[b] - nx[b] * c[a]) / det;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int k1 = (k + 1) & 3;
+        const double ex = v[k1][0] - v[k][0], ey = v[k1][1] - v[k][1];
+        const double fx = out[k1][0] - out[k][0], fy = out[k1][1] - out[k][1];
+        ok = ok && (ex * fx + ey * fy > 0.0);
+    }
+    return ok;
+}
+
+__device__ inline double signed_area4(const double (*v)[2])
+{
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        s += v[i][0] * v[j][1] - v[j][0] * v[i][1];
+    }
+    return 0.5 * s;
+}
+
+// oracle/geom.py centroid (shifted to vertex 0)
+__device__ inline void centroid4(const double (*v)[2], double &cx, double &cy)
+{
+    const double ox = v[0][0], oy = v[0][1];
+    double a2 = 0.0, sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3;
+        const double x0 = v[i][0] - ox, y0 = v[i][1] - oy;
+        const double x1 = v[j][0] - ox, y1 = v[j][1] - oy;
+        const double cr = x0 * y1 - x1 * y0;
+        a2 += cr;
+        sx += (x0 + x1) * cr;
+        sy += (y0 + y1) * cr;
+    }
+    cx = ox + sx / (3.0 * a2);
+    cy = oy + sy / (3.0 * a2);
+}
+
+// mlp3:265-284
+__device__ __forceinline__ void rotate_pt(double px, double py, double ca, double sa, double cx, double cy,
+                                          double &ox, double &oy)
+{
+    const double x = px - cx, y = py - cy;
+    const double xn = x * ca - y * sa;
+    const double yn = x * sa + y * ca;
+    ox = xn + cx;
+    oy = yn + cy;
+}
+
+// 15-point quarter arc sample j at ring corner ci (mlp3:1049-1060, :1592-1603)
+__device__ __forceinline__ void corner_arc_pt(const TrigTables &tt, double x, double y, double R, int ci, int j,
+                                              double &ox, double &oy)
+{
+    const double c = tt.cos15[j], s = tt.sin15[j];
+    if (ci == 0) {
+        ox = x + R * (1 - c);
+        oy = y + R * s;
+    } else if (ci == 1) {
+        ox = x - R * s;
+        oy = y + R * (1 - c);
+    } else if (ci == 2) {
+        ox = x - R * (1 - c);
+        oy = y - R * s;
+    } else {
+        ox = x + R * s;
+        oy = y - R * (1 - c);
+    }
+}
+
+// 1e-4 m fixed point (D5): one FP64 multiply, round-half-even
+__device__ __forceinline__ int64_t qfix(double x) { return __double2ll_rn(x * FCPP_FIXED_UNIT); }
+
+// launchers (defined in the .cu files, called from fcpp_api.cu)
+cudaError_t fcpp_launch_layout(fcpp_handle *h, const fcpp_batch &b, int32_t *d_n_pts, int64_t *d_offsets,
+                               cudaStream_t st);
+cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
+                             int *too_large);
+cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st);
+cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, const double *d_path,
+                                     const double *d_speeds_in, const int64_t *d_offsets, int64_t n_paths,
+                                     int64_t max_len, int do_speed_plan, double *d_speeds_out, double *d_curv,
+                                     fcpp_summary *d_summary, cudaStream_t st);
+cudaError_t fcpp_launch_raster_window(fcpp_handle *h, const double *d_path, int32_t n_pts, double radius,
+                                      double ox, double oy, double hc, int32_t g, uint32_t *d_bits,
+                                      int64_t *d_count, cudaStream_t st);
+cudaError_t fcpp_launch_tours(fcpp_handle *h, const double *d_D, int32_t n, const int32_t *d_pop,
+                              int64_t pop_size, double *d_out, double *d_fit, cudaStream_t st);
+cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32_t *d_cand_field,
+                               int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
+                               double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);

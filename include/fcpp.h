@@ -1,0 +1,203 @@
+/* fcpp.h — C-ABI of libfcpp.so: the B200-native batched plan-generation-and-validation path
+ * of the two-layer field coverage planner.
+ *
+ * The reference (qwagrox/field-coverage-path-planning) is pure Python and has NO FFI boundary
+ * (SURVEY.md §8(b)); its boundary for this path is the Python class API.  This header is the
+ * boundary a maintainer would bind from Python with ctypes (INTEGRATION.md shows the stub).
+ * Each entry point cites the reference code it replaces; "mlp3" = multi_layer_planner_v3.py,
+ * "ga" = genetic_algorithm_solver.py.
+ *
+ * Conventions
+ *  - Plain C, no torch types.  Every buffer is CALLER-OWNED.  Pointers in fcpp_batch /
+ *    fcpp_outputs and all `d_*` arguments are DEVICE pointers on the handle's device,
+ *    contiguous, naturally aligned (16 B for double pairs).  The library owns only its
+ *    handle workspace.
+ *  - Every function returns 0 on success or a negative fcpp_status; it never throws, never
+ *    exits.  fcpp_last_error(handle) gives the message.  Per-candidate geometric failures
+ *    (mlp3:597 "headland too wide", mlp3:967-969 skipped loop) go to summary.status, not to
+ *    the return code.
+ *  - Work is enqueued on the cudaStream_t given (void* here so that the header needs no CUDA
+ *    include) and is asynchronous; one handle per (device, stream), not re-entrant.
+ *  - Units follow the reference: metres, km/h for speeds, m/s² for accelerations.
+ *  - There is no CPU fallback: without a CUDA device fcpp_create fails.
+ */
+#ifndef FCPP_H
+#define FCPP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCPP_ABI_VERSION 1
+
+/* hard-coded sample counts of the reference */
+#define FCPP_UTURN_POINTS 20      /* mlp3:807  */
+#define FCPP_CORNER_POINTS 15     /* mlp3:1046, :1589 */
+#define FCPP_STRAIGHT_POINTS 20   /* mlp3:990  */
+#define FCPP_MAX_LOOPS 16         /* K = ceil(R/W) (mlp3:916) supported up to this */
+#define FCPP_FIXED_UNIT 1e4       /* coverage lattice: 1e-4 m fixed point */
+
+typedef enum {
+    FCPP_OK = 0,
+    FCPP_ERR_INVALID = -1,   /* bad argument */
+    FCPP_ERR_CUDA = -2,      /* CUDA runtime error (message in fcpp_last_error) */
+    FCPP_ERR_NO_DEVICE = -3, /* no usable CUDA device: there is no CPU path */
+    FCPP_ERR_TOO_LARGE = -4  /* a plan does not fit the on-chip staging */
+} fcpp_status;
+
+/* per-candidate status bits in fcpp_summary.status */
+#define FCPP_CAND_OK 0
+#define FCPP_CAND_INSET_EMPTY 1   /* mlp3:597-598 ValueError */
+#define FCPP_CAND_LOOP_SKIPPED 2  /* mlp3:967-969 + :939 (vstack shape error) */
+#define FCPP_CAND_TOO_MANY_LOOPS 4
+#define FCPP_CAND_TOO_LARGE 8     /* N exceeds the shared-memory staging capacity */
+#define FCPP_CAND_GRID_TOO_LARGE 16
+
+typedef struct fcpp_handle fcpp_handle;
+
+/* A1 VehicleParams, mlp3:29-39 (min_turn_radius is per candidate: fcpp_batch.cand_R) */
+typedef struct {
+    double working_width;
+    double max_work_speed_kmh;
+    double max_headland_speed_kmh;
+    double headland_turn_speed_kmh;
+    double max_lateral_accel;
+    double max_longitudinal_accel;
+    double safety_factor;
+    double reverse_speed_kmh; /* literal 2.5 at mlp3:1080 */
+} fcpp_vehicle;
+
+/* Inputs of one batch.  F fields, B candidates (field x heading x turn radius x start corner). */
+typedef struct {
+    fcpp_vehicle vehicle;
+    /* ---- fields (A2 results are computed by the Python host in FP64, mlp3:109-343) ---- */
+    int32_t n_fields;
+    const double *field_verts;     /* [F][4][2] convex, CCW, vertex 0 = "lower-left" (mlp3:127-132) */
+    const double *field_extent;    /* [F][2] field_length, field_width = bbox extents (mlp3:120-122) */
+    const int32_t *field_flags;    /* [F] bit i: reverse fill allowed at corner i (angle>=60, mlp3:224-242) */
+    /* obstacles (mlp3:600-609): polygons of field f are obs_poly_start[f] .. obs_poly_start[f+1] */
+    const int32_t *obs_poly_start; /* [F+1]  (may be NULL when there are no obstacles at all) */
+    const int32_t *obs_vert_start; /* [NP+1] vertices of polygon p are obs_vert_start[p] .. [p+1] */
+    const double *obs_verts;       /* [NV][2] */
+    const double *obs_moments;     /* [NP][3] area, area*cx, area*cy of the W/2 round buffer (D2) */
+    /* ---- candidates ---- */
+    int64_t n_cand;
+    const int32_t *cand_field;     /* [B] field index */
+    const double *cand_R;          /* [B] min_turn_radius = headland width (mlp3:295-310) */
+    const double *cand_rot;        /* [B][4] cos(-a), sin(-a), cos(a), sin(a) of the swath heading a
+                                      (host libm/numpy values; replaces mlp3:244-263, used :682-716) */
+    const int32_t *cand_flags;     /* [B] bits 0-1 start corner (mlp3:397-399), bit 2 reverse_order,
+                                      bit 3 start_from_right (mlp3:631-668), bit 4 rotated
+                                      (|a| > 0.01, mlp3:686), bit 5 corner gap gate (mlp3:1070) */
+    /* ---- coverage raster ---- */
+    double grid_h;                 /* headland-band cell size in m (0.1 default, 0.05 in config 5) */
+    int32_t do_coverage;           /* 0: skip A10/A11 */
+} fcpp_batch;
+
+#define FCPP_FLAG_CORNER_MASK 3
+#define FCPP_FLAG_REVERSE_ORDER 4
+#define FCPP_FLAG_START_FROM_RIGHT 8
+#define FCPP_FLAG_ROTATED 16
+#define FCPP_FLAG_GAP_GATE 32
+
+/* One record per candidate (A8-A11, A13 + layout). 192 bytes. */
+typedef struct {
+    int32_t status;           /* FCPP_CAND_* bits */
+    int32_t n_passes;         /* P, mlp3:739 */
+    int32_t n_loops;          /* K, mlp3:916 */
+    int32_t n_main;           /* points of main_work.path */
+    int32_t n_head;           /* points of headland.path */
+    int32_t n_rev[3];         /* reverse-fill points after the three loop-0 turns, mlp3:1214 */
+    int32_t n_accel_viol;     /* mlp3:1401 */
+    int32_t n_boundary_viol;  /* D3: points outside the field by > 1e-9 m */
+    int32_t n_obstacle_viol;  /* D3: points inside an obstacle buffered by W/2 */
+    int32_t corner_g;         /* int(2R/0.1), mlp3:1457 */
+    int32_t corner_before[4]; /* covered lattice points, turn only, mlp3:1483 */
+    int32_t corner_after[4];  /* turn + reverse fill, mlp3:1500 */
+    int64_t cov_cells;        /* covered cells of the headland band (A11, D5) */
+    int64_t cov_total;        /* cells of the headland band */
+    double len_main;          /* m, mlp3:1290 on main_work.path */
+    double len_head;
+    double time_main;         /* s, mlp3:1298 with the ADJUSTED speeds (mlp3:423-431) */
+    double time_head;
+    double time_main_pre;     /* s, with the initial speeds (feeds the stale avg_speed_kmh, Q8) */
+    double time_head_pre;
+    double max_curvature;     /* mlp3:1396 */
+    double max_lateral_accel; /* mlp3:1397 */
+    double max_jump;          /* mlp3:1404-1406 */
+    double reserved;
+} fcpp_summary;
+
+typedef struct {
+    fcpp_summary *summary; /* [B] */
+    /* optional materialised paths (all NULL = summary-only search mode) */
+    const int64_t *offsets; /* [B+1] from fcpp_layout: candidate b owns points offsets[b]..offsets[b+1] */
+    double *path_xy;        /* [total][2]  main_work.path then headland.path (mlp3:411) */
+    double *speeds_kmh;     /* [total]     adjusted speeds (mlp3:415-420) */
+    double *curvature;      /* [total] or NULL: kappa per point (0 at both ends) */
+} fcpp_outputs;
+
+int fcpp_abi_version(void);
+
+/* Creates a handle on CUDA device `device`.  Fails with FCPP_ERR_NO_DEVICE when CUDA is absent. */
+int fcpp_create(int device, fcpp_handle **out);
+void fcpp_destroy(fcpp_handle *h);
+const char *fcpp_last_error(const fcpp_handle *h);
+
+/* Replaces the library's own libm tables of cos/sin(linspace(0,pi,20)) and
+ * cos/sin(linspace(0,pi/2,15)) (mlp3:807-808, :1046-1047) by the host's (numpy's) values so
+ * that device arcs are bit-identical to the host reference on the same machine.  Host pointers. */
+int fcpp_set_trig_tables(fcpp_handle *h, const double *cos20, const double *sin20,
+                         const double *cos15, const double *sin15);
+
+/* FP64 integer-layout pass (P, K, n_rev, point counts: mlp3:739, :916, :1214) for every
+ * candidate + exclusive prefix sum.  d_n_pts [B] int32 and d_offsets [B+1] int64 are device
+ * buffers; either may be NULL.  Must precede fcpp_plan_batch for the same batch. */
+int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64_t *d_offsets,
+                void *stream);
+
+/* The hot path: path sampling (mlp3:591-1288), speed planning (mlp3:467-589), kinematic and
+ * geofence validation (mlp3:1373-1424 + D3), path metrics (mlp3:1290-1311) and coverage
+ * rasterisation (mlp3:1357-1371, :1426-1578) for all candidates. */
+int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs *out, void *stream);
+
+/* Per-field argmin over candidates of cost = len_main + len_head (cost_kind 0) or
+ * time_main + time_head (cost_kind 1); candidates with status != 0 are skipped; ties go to the
+ * lowest candidate index.  d_best_cost [F] double (+inf when no valid candidate),
+ * d_best_cand [F] int64 (-1 when none).  cand_base is added to the indices (multi-GPU shards). */
+int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32_t *d_cand_field,
+                      int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
+                      double *d_best_cost, int64_t *d_best_cand, void *stream);
+
+/* Generic A7/A8/A13 on caller-supplied paths (ragged batch, path p = points offsets[p]..offsets[p+1]):
+ * speed planning mlp3:467-589 (d_speeds_out may alias d_speeds_in), curvature verification
+ * mlp3:1373-1424 and length/time mlp3:1290-1311 into d_summary (fields n_accel_viol, max_*,
+ * len_main, time_main, time_main_pre; the split point n_main = whole path).
+ * do_speed_plan = 0 verifies the given speeds without adjusting them. */
+int fcpp_speed_verify(fcpp_handle *h, const fcpp_vehicle *veh, double min_turn_radius_unused,
+                      const double *d_path_xy, const double *d_speeds_in, const int64_t *d_offsets,
+                      int64_t n_paths, int do_speed_plan, double *d_speeds_out, double *d_curvature,
+                      fcpp_summary *d_summary, void *stream);
+
+/* Generic A10 window raster (mlp3:1426-1510): ORs the W/2 round buffer of a polyline into a
+ * g x g lattice-point window (bit (j*g+i) of d_bits, row-major, 32-bit words, ceil(g*g/32) words,
+ * caller-zeroed or carrying an earlier cover) and writes the number of set bits to d_count. */
+int fcpp_raster_window(fcpp_handle *h, const double *d_path_xy, int32_t n_pts, double radius,
+                       double origin_x, double origin_y, double h_cell, int32_t g,
+                       uint32_t *d_bits, int64_t *d_count, void *stream);
+
+/* A12 closed-tour lengths: d_out[p] = sum_i D[r_i, r_(i+1) mod n] accumulated left to right in
+ * FP64 exactly as ga:174-181; d_fitness (optional) = 1/(d + 1e-6) (ga:168-172).
+ * D is n x n row-major FP64 (multi_field_planner.py:263-288), pop is pop_size x n int32. */
+int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_t *d_pop,
+                      int64_t pop_size, double *d_out, double *d_fitness, void *stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t fcpp_launch_count(const fcpp_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCPP_H */

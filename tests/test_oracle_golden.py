@@ -1,0 +1,154 @@
+"""The CPU oracle (oracle/) against the golden fixtures produced by executing the unmodified
+reference (tests/golden/make_golden.py) and against the prose known-answers of the reference
+(README.md:193-202, doc/V3.5.1 更新日志.md:108-114) — SURVEY.md §8(c)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import raster, ref_planner as rp
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    veh = rp.VehicleParams(**meta["vehicle"])
+    kw = {k: v for k, v in meta["planner"].items()}
+    for k in ("start_point", "end_point"):
+        if kw.get(k) is not None:
+            kw[k] = tuple(kw[k])
+    if kw.get("field_vertices") is not None:
+        kw["field_vertices"] = [tuple(v) for v in kw["field_vertices"]]
+    return z, meta, veh, kw
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[4:-4] for p in GOLD])
+def test_oracle_reproduces_reference(path):
+    z, meta, veh, kw = _load(path)
+    fs = rp.setup_field(veh, **kw)
+    assert fs.field_shape == meta["field_shape"]
+    assert fs.main_work_pattern == meta["pattern"]
+    np.testing.assert_allclose(fs.corner_angles, meta["corner_angles"], rtol=0, atol=1e-12)
+    o = rp.plan_complete_coverage(fs)
+    # integer layout: bit-exact
+    assert o["main_work"]["path"].shape == z["main_path"].shape
+    assert o["headland"]["path"].shape == z["head_path"].shape
+    # points: the restatement performs the same numpy operations -> <= 1e-12 m (tolerance of
+    # north_star is 1e-4 m); speeds <= 1e-12 km/h (north_star: 1e-4 m/s)
+    np.testing.assert_allclose(o["main_work"]["path"], z["main_path"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o["headland"]["path"], z["head_path"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o["main_work"]["speeds"], z["main_speeds"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o["headland"]["speeds"], z["head_speeds"], rtol=0, atol=1e-12)
+    for layer, key in (("main_work", "main_stats"), ("headland", "head_stats")):
+        got = [o[layer]["stats"][k] for k in ("path_length_km", "time_hours", "avg_speed_kmh")]
+        np.testing.assert_allclose(got, z[key], rtol=1e-13)
+    allp = np.vstack([o["main_work"]["path"], o["headland"]["path"]])
+    alls = np.concatenate([o["main_work"]["speeds"], o["headland"]["speeds"]])
+    cc = rp.verify_curvature_constraints(allp, alls, veh)
+    ref = z["curv"]
+    np.testing.assert_allclose([cc["max_curvature"], cc["max_lateral_accel"], cc["max_jump"]],
+                               [ref[0], ref[1], ref[4]], rtol=1e-12)
+    assert cc["accel_violations"] == int(ref[2])
+    assert cc["pass"] == bool(ref[5])
+    for name, key in (("approach_path", "approach"), ("departure_path", "departure")):
+        if len(z[key]):
+            np.testing.assert_allclose(o[name], z[key], rtol=0, atol=1e-12)
+        else:
+            assert o[name] is None
+    if "corner_cells_float" in z.files:
+        got, g = raster.corner_coverage(fs)
+        ref_cells = z["corner_cells_float"]
+        # the reference decides "inside" in float64; the oracle in exact 1e-4 m fixed point (D5):
+        # lattice points that sit on the buffer boundary may flip -> allow 2 cells per window
+        assert np.max(np.abs(np.array(got) - ref_cells)) <= 2
+        assert g * g == 25600 or meta["vehicle"]["min_turn_radius"] != 8.0
+
+
+def test_known_answers_readme():
+    """README.md:193-202: 1256/435 points, 0 boundary violations, 0.0 % accel violations,
+    headland coverage 100.0 %, corner gain +3.2 %."""
+    veh = rp.VehicleParams(3.2, 8.0, 9.0, 15.0)
+    fs = rp.setup_field(veh, field_length=500, field_width=200)
+    o = rp.plan_complete_coverage(fs)
+    assert len(o["main_work"]["path"]) == 1256
+    assert len(o["headland"]["path"]) == 435
+    allp = np.vstack([o["main_work"]["path"], o["headland"]["path"]])
+    alls = np.concatenate([o["main_work"]["speeds"], o["headland"]["speeds"]])
+    assert rp.boundary_violations(allp, fs.field_vertices) == 0
+    assert rp.verify_curvature_constraints(allp, alls, veh)["accel_violations"] == 0
+    cells, g = raster.corner_coverage(fs)
+    b = np.array(cells)
+    gain = (b[:, 1] - b[:, 0]).mean() / (g * g) * 100
+    assert abs(gain - 3.2) < 0.1
+    total, cov = raster.band_coverage(fs, o["headland"]["path"], 0.1)
+    assert total == 1094400                      # SURVEY.md §8(d) G_band
+    assert round(cov / total * 100, 1) == 100.0  # README "100.0 %"
+    assert (total, cov) == (1094400, 1094113)    # regression KAT of the integer raster
+
+
+def test_known_answers_changelog_v351():
+    """doc/V3.5.1 更新日志.md:109-111: start (10,10) -> corner (4,4) at 8.5 m, approach 11.9 m,
+    departure to (490,190) 515.2 m."""
+    veh = rp.VehicleParams(3.2, 8.0, 9.0, 14.0)
+    fs = rp.setup_field(veh, field_length=500, field_width=200, start_point=(10, 10), end_point=(490, 190))
+    assert rp.select_best_start_corner(fs, fs.start_point) == 0
+    assert round(float(np.hypot(10 - 4, 10 - 4)), 1) == 8.5
+    o = rp.plan_complete_coverage(fs)
+    assert round(rp.path_length(o["approach_path"]), 1) == 11.9
+    assert round(rp.path_length(o["departure_path"]), 1) == 515.2
+
+
+def test_knife_edges_q17():
+    """FP64 knife edges of the integer layout."""
+    assert int((200 - 2 * 7.2) / 3.2) == 57              # the closed form sits on a knife edge ...
+    fs = rp.setup_field(rp.VehicleParams(3.2, 7.2), field_length=500, field_width=200)
+    _, _, info = rp.plan_main_work(fs)
+    # ... but the code path goes through the inset bounds: (200-7.2) - 7.2 = 185.60000000000002,
+    # /3.2 -> 58.000000000000007 -> P = 59 (the reference run in ref_r72_knife.npz agrees: 1278 pts)
+    assert info["P"] == 59
+    assert 22 * info["P"] - 20 == 1278
+    assert int(2 * 9.6 / 0.1) == 191
+    fs = rp.setup_field(rp.VehicleParams(3.2, 9.6), field_length=300, field_width=150)
+    _, g = raster.corner_coverage(fs)
+    assert g == 191
+
+
+def test_speed_plan_is_minplus_scan():
+    """the three-pass planner == u=v² min-plus scans with chain breaks."""
+    veh = rp.VehicleParams()
+    fs = rp.setup_field(veh, field_length=500, field_width=200)
+    o = rp.plan_complete_coverage(fs)
+    path = np.vstack([o["main_work"]["path"], o["headland"]["path"]])
+    pre = o["_info"]["speeds_pre"]
+    kap = np.concatenate([[0.0], rp.curvatures(path), [0.0]])
+    lim = pre.copy()
+    m = kap > 1e-6
+    lim[m] = np.minimum(lim[m], np.sqrt(veh.max_lateral_accel / kap[m]) * veh.safety_factor * 3.6)
+    u = (lim / 3.6) ** 2
+    ds = np.sqrt((np.diff(path, axis=0) ** 2).sum(1))
+    c = np.where(ds < 1e-6, np.inf, 2 * veh.max_longitudinal_accel * ds)
+    f = u.copy()
+    for i in range(1, len(f)):
+        f[i] = min(f[i], f[i - 1] + c[i - 1])
+    for i in range(len(f) - 2, -1, -1):
+        f[i] = min(f[i], f[i + 1] + c[i])
+    got = np.concatenate([o["main_work"]["speeds"], o["headland"]["speeds"]])
+    np.testing.assert_allclose(3.6 * np.sqrt(f), got, rtol=0, atol=1e-12)
+    assert int((ds < 1e-6).sum()) == 72   # App. C: 72 zero-length segments
+
+
+def test_ga_tour_lengths_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ga_tours.npz"))
+    d = raster.tour_lengths(z["D"], z["pop"])
+    assert np.array_equal(d, z["dist"])          # sequential FP64 sum: bit-exact
+    np.testing.assert_array_equal(1.0 / (d + 1e-6), z["fitness"])
+
+
+def test_inset_error_status():
+    fs = rp.setup_field(rp.VehicleParams(3.2, 8.0), field_length=30, field_width=15)
+    with pytest.raises(ValueError):
+        rp.plan_complete_coverage(fs)
