@@ -1,0 +1,277 @@
+"""Batch entry point: evaluate many candidate plans (fields x heading x turn radius x start
+corner) at once on the GPU through libfcpp.so — SURVEY.md §8(b) "New batch entry".
+
+Host side = FP64 numpy set-up of the per-field / per-candidate scalars (A2, mlp3:109-343),
+device memory and streams through torch, everything else inside the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field as dc_field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _geometry as G
+from . import _lib
+from .vehicle import VehicleParams
+
+ROT_THRESHOLD = 0.01  # mlp3:686, :709
+
+
+def _dev(device) -> torch.device:
+    if device is None:
+        if not torch.cuda.is_available():
+            raise _lib.FcppError("no CUDA device: this package has no CPU path")
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise _lib.FcppError(f"device {d} is not a CUDA device: this package has no CPU path")
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
+def _to_dev(a: np.ndarray, dev: torch.device, pin: bool = True) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pin:
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=True)
+
+
+def make_candidates(n_fields: int, headings: Optional[Sequence[float]] = None,
+                    radii: Optional[Sequence[float]] = None,
+                    start_corners: Optional[Sequence[int]] = None) -> Dict[str, np.ndarray]:
+    """Cartesian product field x heading x radius x start corner, field-major (all candidates of
+    one field are contiguous).  ``headings`` in radians; ``None`` keeps the reference's heading
+    (direction of field edge 0, mlp3:244-263); radii ``None`` keeps the vehicle's radius."""
+    hs = [None] if headings is None else list(headings)
+    rs = [None] if radii is None else list(radii)
+    cs = [None] if start_corners is None else list(start_corners)
+    nh, nr, nc = len(hs), len(rs), len(cs)
+    per = nh * nr * nc
+    B = n_fields * per
+    fid = np.repeat(np.arange(n_fields, dtype=np.int32), per)
+    idx = np.tile(np.arange(per), n_fields)
+    out: Dict[str, np.ndarray] = {"field_id": fid}
+    if headings is not None:
+        out["heading"] = np.asarray(hs, dtype=np.float64)[idx // (nr * nc)]
+    if radii is not None:
+        out["R"] = np.asarray(rs, dtype=np.float64)[(idx // nc) % nr]
+    if start_corners is not None:
+        out["start_corner"] = np.asarray(cs, dtype=np.int32)[idx % nc]
+    assert len(fid) == B
+    return out
+
+
+@dataclass
+class PreparedBatch:
+    """Host (numpy) side of one batch, ready to be copied to a device."""
+    vehicle: VehicleParams
+    n_fields: int
+    n_cand: int
+    arrays: Dict[str, np.ndarray]
+    max_obs_verts: int
+    max_obs_polys: int
+    grid_h: float
+    coverage: bool
+
+    def h2d_bytes(self) -> int:
+        return int(sum(a.nbytes for a in self.arrays.values()))
+
+
+def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str, np.ndarray]] = None,
+                  obstacles: Optional[Sequence[Sequence[Sequence[Sequence[float]]]]] = None,
+                  start_points: Optional[np.ndarray] = None, grid_h: float = 0.1,
+                  coverage: bool = True) -> PreparedBatch:
+    """FP64 host set-up (A2).  ``fields`` [F,4,2] convex CCW quads; ``obstacles`` = per field a
+    list of polygons; ``candidates`` = dict with ``field_id`` and optional ``heading`` (rad),
+    ``R``, ``start_corner`` arrays of length B (default: one candidate per field with the
+    reference's defaults); ``start_points`` [B,2] makes the pass order follow mlp3:631-668."""
+    fv = np.ascontiguousarray(np.asarray(fields, dtype=np.float64).reshape(-1, 4, 2))
+    F = len(fv)
+    if candidates is None:
+        candidates = {"field_id": np.arange(F, dtype=np.int32)}
+    fid = np.ascontiguousarray(candidates["field_id"], dtype=np.int32)
+    B = len(fid)
+    if B and (fid.min() < 0 or fid.max() >= F):
+        raise ValueError("candidate field_id out of range")
+    W = float(vehicle.working_width)
+    # ---- per field: bbox extents (mlp3:120-122), reverse-fill permission bits (mlp3:224-242) ----
+    ext = np.stack([fv[:, :, 0].max(1) - fv[:, :, 0].min(1), fv[:, :, 1].max(1) - fv[:, :, 1].min(1)], axis=1)
+    ang = G.corner_angles_deg(fv)
+    fflags = ((ang >= 60).astype(np.int32) << np.arange(4, dtype=np.int32)).sum(axis=1).astype(np.int32)
+    # ---- per candidate ----
+    R = np.ascontiguousarray(candidates.get("R", np.full(B, vehicle.min_turn_radius)), dtype=np.float64)
+    if "heading" in candidates:
+        ang_c = np.ascontiguousarray(candidates["heading"], dtype=np.float64)
+    else:
+        e0 = fv[:, 1, :] - fv[:, 0, :]
+        ang_c = np.arctan2(e0[:, 1], e0[:, 0])[fid]  # mlp3:244-263
+    rot = np.stack([np.cos(-ang_c), np.sin(-ang_c), np.cos(ang_c), np.sin(ang_c)], axis=1)
+    flags = np.zeros(B, dtype=np.int32)
+    if "start_corner" in candidates:
+        c = np.asarray(candidates["start_corner"], dtype=np.int32)
+        if B and (c.min() < 0 or c.max() > 3):
+            raise ValueError("start_corner must be 0..3")
+        flags |= c
+        flags |= np.where((c == 2) | (c == 3), _lib.FLAG_REVERSE_ORDER, 0).astype(np.int32)
+        flags |= np.where((c == 1) | (c == 2), _lib.FLAG_START_FROM_RIGHT, 0).astype(np.int32)
+    flags |= np.where(np.abs(ang_c) > ROT_THRESHOLD, _lib.FLAG_ROTATED, 0).astype(np.int32)
+    flags |= np.where(G.gap_gate(R, W), _lib.FLAG_GAP_GATE, 0).astype(np.int32)
+    arrays = {
+        "field_verts": fv, "field_extent": np.ascontiguousarray(ext), "field_flags": fflags,
+        "cand_field": fid, "cand_R": R, "cand_rot": np.ascontiguousarray(rot), "cand_flags": flags,
+    }
+    if start_points is not None:
+        sp = np.ascontiguousarray(start_points, dtype=np.float64).reshape(B, 2)
+        use = ~np.isnan(sp[:, 0])
+        flags |= np.where(use, _lib.FLAG_START_POINT, 0).astype(np.int32)
+        arrays["cand_start"] = np.where(use[:, None], sp, 0.0)
+    # ---- obstacles (mlp3:600-609): flattened polygon tables + D2 round-buffer moments ----
+    max_v = max_p = 0
+    if obstacles is not None and any(len(o) for o in obstacles):
+        if len(obstacles) != F:
+            raise ValueError("obstacles must have one (possibly empty) polygon list per field")
+        poly_start = [0]
+        vert_start = [0]
+        verts: List[Sequence[float]] = []
+        moms = []
+        for polys in obstacles:
+            nv_field = 0
+            for poly in polys:
+                pts = [tuple(map(float, p)) for p in poly]
+                verts.extend(pts)
+                nv_field += len(pts)
+                vert_start.append(len(verts))
+                moms.append(G.round_buffer_moments(pts, W / 2))
+            poly_start.append(len(vert_start) - 1)
+            max_v = max(max_v, nv_field)
+            max_p = max(max_p, len(polys))
+        arrays["obs_poly_start"] = np.asarray(poly_start, dtype=np.int32)
+        arrays["obs_vert_start"] = np.asarray(vert_start, dtype=np.int32)
+        arrays["obs_verts"] = np.asarray(verts, dtype=np.float64).reshape(-1, 2)
+        arrays["obs_moments"] = np.asarray(moms, dtype=np.float64).reshape(-1, 3)
+    return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage))
+
+
+class DeviceBatch:
+    """A PreparedBatch resident in HBM + its ctypes descriptor."""
+
+    def __init__(self, pb: PreparedBatch, dev: torch.device, pin: bool = True):
+        self.pb = pb
+        self.dev = dev
+        self.t = {k: _to_dev(v, dev, pin) for k, v in pb.arrays.items()}
+        v = pb.vehicle
+        b = _lib.Batch()
+        b.vehicle = _lib.Vehicle(v.working_width, v.max_work_speed_kmh, v.max_headland_speed_kmh,
+                                 v.headland_turn_speed_kmh, v.max_lateral_accel, v.max_longitudinal_accel,
+                                 v.safety_factor, 2.5)
+        b.n_fields = pb.n_fields
+        b.n_cand = pb.n_cand
+        for name in ("field_verts", "field_extent", "field_flags", "obs_poly_start", "obs_vert_start",
+                     "obs_verts", "obs_moments", "cand_field", "cand_R", "cand_rot", "cand_flags", "cand_start"):
+            t = self.t.get(name)
+            setattr(b, name, t.data_ptr() if t is not None else None)
+        b.max_obs_verts = pb.max_obs_verts
+        b.max_obs_polys = pb.max_obs_polys
+        b.grid_h = pb.grid_h
+        b.do_coverage = 1 if pb.coverage else 0
+        self.c = b
+
+
+@dataclass
+class BatchResult:
+    """Per-candidate summaries (host numpy structured array, dtype _lib.SUMMARY_DTYPE), the
+    per-field argmin, and — in ``outputs='paths'`` mode — device-resident paths."""
+    summary: np.ndarray
+    best_cand: np.ndarray          # [F] int64 global candidate index (-1: no valid candidate)
+    best_cost: np.ndarray          # [F] float64
+    n_fields: int
+    offsets: Optional[np.ndarray] = None        # [B+1] int64 (paths mode)
+    d_path: Optional[torch.Tensor] = None       # [total, 2] float64 on device
+    d_speeds: Optional[torch.Tensor] = None     # [total] float64 km/h on device
+    d_curvature: Optional[torch.Tensor] = None
+    d_summary: Optional[torch.Tensor] = None
+    cand_base: int = 0
+    extras: Dict = dc_field(default_factory=dict)
+
+    def path(self, b: int):
+        """(path [n,2], speeds [n], n_main) of local candidate ``b`` copied to the host."""
+        if self.d_path is None:
+            raise ValueError("plan_batch was run with outputs='summary'")
+        o0, o1 = int(self.offsets[b]), int(self.offsets[b + 1])
+        return (self.d_path[o0:o1].cpu().numpy(), self.d_speeds[o0:o1].cpu().numpy(),
+                int(self.summary["n_main"][b]))
+
+
+def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
+                     cost: str = "length", cand_base: int = 0, copy_summary: bool = True) -> BatchResult:
+    """Enqueue one batch on torch's current stream and (optionally) fetch the summaries."""
+    if outputs not in ("summary", "paths"):
+        raise ValueError("outputs must be 'summary' or 'paths'")
+    dev = db.dev
+    h = _lib.handle(dev.index)
+    L = h.lib
+    B, F = db.pb.n_cand, db.pb.n_fields
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        d_sum = torch.empty(max(B, 1) * _lib.SUMMARY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        out = _lib.Outputs()
+        out.summary = d_sum.data_ptr()
+        d_off = d_path = d_spd = d_kap = None
+        offsets = None
+        if outputs == "paths":
+            d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+            h.check(L.fcpp_layout(h.h, C.byref(db.c), None, d_off.data_ptr(), stream))
+            offsets = d_off.cpu().numpy()
+            total = int(offsets[-1])
+            d_path = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)
+            d_spd = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+            out.offsets = d_off.data_ptr()
+            out.path_xy = d_path.data_ptr()
+            out.speeds_kmh = d_spd.data_ptr()
+            if want_curvature:
+                d_kap = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+                out.curvature = d_kap.data_ptr()
+        h.check(L.fcpp_plan_batch(h.h, C.byref(db.c), C.byref(out), stream))
+        d_cost = torch.empty(max(F, 1), dtype=torch.float64, device=dev)
+        d_best = torch.empty(max(F, 1), dtype=torch.int64, device=dev)
+        h.check(L.fcpp_field_argmin(h.h, d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
+                                    0 if cost == "length" else 1, cand_base, d_cost.data_ptr(),
+                                    d_best.data_ptr(), stream))
+        if copy_summary:
+            summary = d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE)[:B]
+        else:
+            summary = np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
+        best_cost = d_cost.cpu().numpy()[:F]
+        best_cand = d_best.cpu().numpy()[:F]
+    return BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
+                       d_path=d_path, d_speeds=d_spd, d_curvature=d_kap, d_summary=d_sum, cand_base=cand_base)
+
+
+def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,
+               obstacles=None, start_points=None, outputs: str = "summary", grid_h: float = 0.1,
+               coverage: bool = True, cost: str = "length", device=None, want_curvature: bool = False,
+               distributed: bool = False) -> BatchResult:
+    """Evaluate B candidate plans.  See ``prepare_batch`` for the inputs.
+
+    Returns a ``BatchResult``: per-candidate ``summary`` records (layout counts, path lengths and
+    times per layer, accel/boundary/obstacle violation counts, headland and corner coverage cell
+    counts, status) and the per-field argmin of ``cost`` ('length' = len_main+len_head metres,
+    'time' = time_main+time_head seconds; ties to the lowest candidate index).
+
+    ``distributed=True`` (inside a torch.distributed job): the candidates are sharded over the
+    ranks in contiguous ranges, each rank plans its shard on its own GPU and the per-field best
+    is reduced with two NCCL all-reduces (see ``dist.py``)."""
+    vehicle = vehicle or VehicleParams()
+    if distributed:
+        from . import dist
+        return dist.plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h,
+                                       coverage, cost, device, want_curvature)
+    dev = _dev(device)
+    pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage)
+    db = DeviceBatch(pb, dev)
+    return run_device_batch(db, outputs, want_curvature, cost)

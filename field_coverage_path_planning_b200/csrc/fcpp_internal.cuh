@@ -60,6 +60,9 @@ struct fcpp_handle {
     void *d_scan_tmp;
     int64_t scan_tmp_cap;
     int64_t launches;
+    int plan_ncap_hint;      // smem point capacity wanted by the next plan launch (0 = maximum)
+    int *d_maxn;             // device: max n_total of the last layout pass
+    int *h_maxn;             // pinned host mirror
     int max_smem_optin;
     int sm_count;
     bool layout_valid;
@@ -207,6 +210,105 @@ __device__ __forceinline__ void corner_arc_pt(const TrigTables &tt, double x, do
 
 // 1e-4 m fixed point (D5): one FP64 multiply, round-half-even
 __device__ __forceinline__ int64_t qfix(double x) { return __double2ll_rn(x * FCPP_FIXED_UNIT); }
+
+// ---------------------------------------------------------------------------------------------
+// point generation: index -> (x, y, speed class)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, double W, int i, double &x,
+                                          double &y, uint8_t &cls)
+{
+    if (i < r.n_main) {
+        // mlp3:744-780: visit index idx, pass index pi, 2 endpoints + 20 arc samples per pass
+        const int per = 2 + FCPP_UTURN_POINTS;
+        const int idx = i / per;
+        const int j = i - idx * per;
+        const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
+        const double yy = r.min_y + pi * W;  // mlp3:751
+        const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
+        double px, py;
+        if (j < 2) {
+            const double xs = r.min_x + r.R, xe = r.max_x - r.R;  // mlp3:736-737
+            px = (go_left == (j == 0)) ? xe : xs;                  // mlp3:761-764
+            py = yy;
+            cls = CLS_WORK;
+        } else {
+            const int a = j - 2;
+            const bool turn_right = !go_left;  // mlp3:776
+            px = turn_right ? (r.max_x - r.R * tt.cos20[a]) : (r.min_x + r.R * tt.cos20[a]);  // mlp3:815, :822
+            py = yy + r.R * tt.sin20[a];                                                       // mlp3:816, :823
+            cls = CLS_TURN;
+        }
+        if (r.flags & FCPP_FLAG_ROTATED)
+            rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
+        else {
+            x = px;
+            y = py;
+        }
+        return;
+    }
+    // ---- headland (mlp3:943-1011) ----
+    int hI = i - r.n_main;
+    const int l0 = FCPP_POINTS_PER_LOOP + r.n_rev[0] + r.n_rev[1] + r.n_rev[2];
+    int k, m;
+    if (hI < l0) {
+        k = 0;
+        m = hI;
+    } else {
+        hI -= l0;
+        k = 1 + hI / FCPP_POINTS_PER_LOOP;
+        m = hI - (k - 1) * FCPP_POINTS_PER_LOOP;
+    }
+    const int sc = r.flags & FCPP_FLAG_CORNER_MASK;
+    if (m == 0) {  // mlp3:978-980
+        x = r.corners[k][sc][0];
+        y = r.corners[k][sc][1];
+        cls = CLS_HEAD;
+        return;
+    }
+    m -= 1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int ci = (sc + t) & 3, ni = (sc + t + 1) & 3;
+        if (m < FCPP_STRAIGHT_POINTS) {  // np.linspace(cur, nxt, 20), mlp3:1013-1022
+            const double ax = r.corners[k][ci][0], ay = r.corners[k][ci][1];
+            const double bx = r.corners[k][ni][0], by = r.corners[k][ni][1];
+            if (m == FCPP_STRAIGHT_POINTS - 1) {
+                x = bx;
+                y = by;
+            } else {
+                const double sx = (bx - ax) / (FCPP_STRAIGHT_POINTS - 1);
+                const double sy = (by - ay) / (FCPP_STRAIGHT_POINTS - 1);
+                x = m * sx + ax;
+                y = m * sy + ay;
+            }
+            cls = CLS_HEAD;
+            return;
+        }
+        m -= FCPP_STRAIGHT_POINTS;
+        if (t < 3) {
+            if (m < FCPP_CORNER_POINTS) {
+                corner_arc_pt(tt, r.corners[k][ni][0], r.corners[k][ni][1], r.R, ni, m, x, y);
+                cls = CLS_TURN;
+                return;
+            }
+            m -= FCPP_CORNER_POINTS;
+            const int nr = (k == 0) ? r.n_rev[t] : 0;
+            if (m < nr) {  // mlp3:1214-1216
+                const double len = r.rev[t][4];
+                const double tt_ = (m == nr - 1) ? len : m * (len / (nr - 1));
+                x = r.rev[t][0] + tt_ * r.rev[t][2];
+                y = r.rev[t][1] + tt_ * r.rev[t][3];
+                cls = CLS_REVERSE;
+                return;
+            }
+            m -= nr;
+        }
+    }
+    x = 0.0;
+    y = 0.0;
+    cls = CLS_HEAD;  // unreachable
+}
+
 
 // launchers (defined in the .cu files, called from fcpp_api.cu)
 cudaError_t fcpp_launch_layout(fcpp_handle *h, const fcpp_batch &b, int32_t *d_n_pts, int64_t *d_offsets,

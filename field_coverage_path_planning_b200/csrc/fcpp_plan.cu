@@ -1,0 +1,661 @@
+// fcpp_plan.cu — the fused per-plan kernel: path sampling -> geofence tests -> curvature limit ->
+// forward/backward min-plus scans -> kinematic validation -> path metrics.  One CTA per plan;
+// the whole plan (x, y, u, class) lives in shared memory, only results go to HBM.
+//
+// Reference code replaced ("mlp3" = multi_layer_planner_v3.py):
+//   A4  swaths + 20-pt half-circle turns            mlp3:720-830, rotate-back :709-714
+//   A5  headland loops (straights, corner arcs)      mlp3:943-1011, :1013-1022, :1580-1608
+//   A6  reverse fills                                mlp3:1066-1080, :1213-1216
+//   A7  curvature limit + accel passes               mlp3:467-589
+//   A8  lateral-acceleration validation              mlp3:1373-1424
+//   A9  geofence / obstacle point tests              D3 (no reference code; README.md:24,200)
+//   A13 path length / work time                      mlp3:1290-1311
+//
+// The same kernel, instantiated with GEN=false, runs A7/A8/A13 on caller-supplied paths
+// (verify_curvature_constraints(path, speeds) of the drop-in API).
+#include "fcpp_internal.cuh"
+
+namespace {
+
+constexpr int T = FCPP_PLAN_THREADS;
+constexpr int NWARP = T / 32;
+
+struct PlanArgs {
+    // GEN
+    fcpp_batch b;
+    const CandRec *recs;
+    const TrigTables *trig;
+    fcpp_outputs out;
+    // generic (GEN = false)
+    fcpp_vehicle veh;
+    const double *in_path;
+    const double *in_speeds;
+    const int64_t *in_offsets;
+    int do_speed_plan;
+    // both
+    int ncap;          // smem capacity in points
+    int obs_cap_verts; // smem capacity for obstacle vertices
+    int obs_cap_polys;
+};
+
+struct Smem {
+    double *X, *Y, *U;
+    uint8_t *CLS;
+    CandRec *rec;
+    TrigTables *tt;
+    double *obs_xy;    // [obs_cap_verts][2]
+    int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
+    double *scratch;   // [128]
+    uint64_t *bar;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int obs_polys)
+{
+    size_t s = 0;
+    s += align16(sizeof(double) * ncap) * 3;
+    s += align16(ncap);
+    s += align16(sizeof(CandRec));
+    s += align16(sizeof(TrigTables));
+    s += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
+    s += align16(sizeof(int32_t) * (obs_polys + 1));
+    s += align16(sizeof(double) * 128);
+    s += 16;
+    return s;
+}
+
+__device__ inline Smem carve(unsigned char *base, int ncap, int obs_verts, int obs_polys)
+{
+    Smem s;
+    size_t o = 0;
+    s.X = (double *)(base + o);
+    o += align16(sizeof(double) * ncap);
+    s.Y = (double *)(base + o);
+    o += align16(sizeof(double) * ncap);
+    s.U = (double *)(base + o);
+    o += align16(sizeof(double) * ncap);
+    s.CLS = (uint8_t *)(base + o);
+    o += align16(ncap);
+    s.rec = (CandRec *)(base + o);
+    o += align16(sizeof(CandRec));
+    s.tt = (TrigTables *)(base + o);
+    o += align16(sizeof(TrigTables));
+    s.obs_xy = (double *)(base + o);
+    o += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
+    s.obs_vs = (int32_t *)(base + o);
+    o += align16(sizeof(int32_t) * (obs_polys + 1));
+    s.scratch = (double *)(base + o);
+    o += align16(sizeof(double) * 128);
+    s.bar = (uint64_t *)(base + o);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// min-plus scan element: the map u -> min(M, u + C)
+// ---------------------------------------------------------------------------------------------
+struct MP {
+    double C, M;
+};
+__device__ __forceinline__ MP mp_combine(const MP &a, const MP &b)  // a first, then b
+{
+    MP r;
+    r.C = a.C + b.C;
+    r.M = fmin(b.M, a.M + b.C);
+    return r;
+}
+__device__ __forceinline__ MP mp_shfl_up(const MP &v, int d)
+{
+    MP r;
+    r.C = __shfl_up_sync(0xffffffffu, v.C, d);
+    r.M = __shfl_up_sync(0xffffffffu, v.M, d);
+    return r;
+}
+
+// exclusive block scan of per-thread aggregates in thread order; returns the carry-in value
+// (the M of the composition of all earlier threads; +inf for thread 0)
+__device__ __forceinline__ double mp_block_exclusive(MP agg, double *sh /*>= 2*NWARP*/)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MP inc = agg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const MP o = mp_shfl_up(inc, d);
+        if (lane >= d) inc = mp_combine(o, inc);
+    }
+    if (lane == 31) {
+        sh[2 * warp] = inc.C;
+        sh[2 * warp + 1] = inc.M;
+    }
+    __syncthreads();
+    // composition of all earlier warps (serial over <= 8 warps)
+    MP pre;
+    pre.C = 0.0;
+    pre.M = INFINITY;
+    for (int w = 0; w < warp; ++w) {
+        MP o;
+        o.C = sh[2 * w];
+        o.M = sh[2 * w + 1];
+        pre = mp_combine(pre, o);
+    }
+    // exclusive within the warp
+    MP ex = mp_shfl_up(inc, 1);
+    if (lane == 0) {
+        ex.C = 0.0;
+        ex.M = INFINITY;
+    }
+    const MP tot = mp_combine(pre, ex);
+    __syncthreads();
+    return tot.M;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// reduce NV sums / maxes across the block (deterministic order); result valid in thread 0
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *sh)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = IS_MAX ? warp_max(v[k]) : warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sh[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double a = sh[k];
+            for (int w = 1; w < NWARP; ++w) a = IS_MAX ? fmax(a, sh[w * NV + k]) : a + sh[w * NV + k];
+            v[k] = a;
+        }
+    }
+}
+
+__device__ __forceinline__ double cls_speed(const fcpp_vehicle &v, uint8_t c)
+{
+    return c == CLS_WORK ? v.max_work_speed_kmh
+                         : (c == CLS_TURN ? v.headland_turn_speed_kmh
+                                          : (c == CLS_HEAD ? v.max_headland_speed_kmh : v.reverse_speed_kmh));
+}
+
+// mlp3:513-536 with the three atan2 folded into one: dtheta = atan2(d1 x d2, d1 . d2)
+__device__ __forceinline__ double curvature3(double dx1, double dy1, double ds1, double dx2, double dy2,
+                                             double ds2)
+{
+    if (ds1 < FCPP_ZERO_LEN || ds2 < FCPP_ZERO_LEN) return 0.0;
+    const double cr = dx1 * dy2 - dy1 * dx2;
+    const double dt = dx1 * dx2 + dy1 * dy2;
+    const double dth = atan2(cr, dt);
+    return fabs(2 * dth / (ds1 + ds2));
+}
+
+// curvature speed limit in km/h (mlp3:496-503)
+__device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_vehicle &v)
+{
+    if (kappa > FCPP_KAPPA_EPS) {
+        const double vmax = sqrt(v.max_lateral_accel / kappa) * v.safety_factor * 3.6;
+        if (v0 > vmax) return vmax;
+    }
+    return v0;
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(T) plan_kernel(const PlanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    const int tid = threadIdx.x;
+    const int64_t cand = blockIdx.x;
+    const fcpp_vehicle &veh = GEN ? a.b.vehicle : a.veh;
+    fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
+
+    int N, n_main;
+    int64_t off = 0;
+    int n_obs_poly = 0;
+    if (GEN) {
+        // stage the candidate record (and the field's obstacle vertices) with TMA bulk copies
+        int f = 0, v0 = 0, nv = 0;
+        if (tid == 0) {
+            mbar_init(s.bar, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            f = a.recs[cand].field;
+            uint32_t bytes = sizeof(CandRec);
+            if (a.b.obs_poly_start) {
+                const int p0 = a.b.obs_poly_start[f], p1 = a.b.obs_poly_start[f + 1];
+                v0 = a.b.obs_vert_start[p0];
+                nv = a.b.obs_vert_start[p1] - v0;
+                if (nv > a.obs_cap_verts) nv = a.obs_cap_verts;
+                bytes += nv * 16;
+            }
+            mbar_expect_tx(s.bar, bytes);
+            bulk_g2s(s.rec, a.recs + cand, sizeof(CandRec), s.bar);
+            if (nv > 0) bulk_g2s(s.obs_xy, a.b.obs_verts + 2 * (int64_t)v0, nv * 16, s.bar);
+        }
+        // trig tables + polygon starts through the ordinary path meanwhile
+        for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
+            ((double *)s.tt)[k] = ((const double *)a.trig)[k];
+        mbar_wait(s.bar, 0);
+        const CandRec &r = *s.rec;
+        if (a.b.obs_poly_start) {
+            const int p0 = a.b.obs_poly_start[r.field], p1 = a.b.obs_poly_start[r.field + 1];
+            n_obs_poly = min(p1 - p0, a.obs_cap_polys);
+            const int base = a.b.obs_vert_start[p0];
+            for (int k = tid; k <= n_obs_poly; k += T) s.obs_vs[k] = a.b.obs_vert_start[p0 + k] - base;
+        }
+        N = r.n_total;
+        n_main = r.n_main;
+        if (a.out.offsets) off = a.out.offsets[cand];
+        if (sum && tid == 0) {
+            sum->n_passes = r.P;
+            sum->n_loops = r.K;
+            sum->n_main = r.n_main;
+            sum->n_head = r.n_head;
+            sum->n_rev[0] = r.n_rev[0];
+            sum->n_rev[1] = r.n_rev[1];
+            sum->n_rev[2] = r.n_rev[2];
+            sum->corner_g = r.corner_g;
+        }
+        int st = r.status;
+        if (N > a.ncap) st |= FCPP_CAND_TOO_LARGE;
+        if (st != 0 || N == 0) {
+            if (sum && tid == 0) {
+                sum->status = st;
+                sum->n_accel_viol = sum->n_boundary_viol = sum->n_obstacle_viol = 0;
+                sum->len_main = sum->len_head = sum->time_main = sum->time_head = 0.0;
+                sum->time_main_pre = sum->time_head_pre = 0.0;
+                sum->max_curvature = sum->max_lateral_accel = sum->max_jump = 0.0;
+                sum->reserved = 0.0;
+                if (!a.b.do_coverage) {
+                    sum->cov_cells = sum->cov_total = 0;
+                    for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
+                }
+            }
+            return;
+        }
+        __syncthreads();
+    } else {
+        off = a.in_offsets[cand];
+        N = (int)(a.in_offsets[cand + 1] - off);
+        n_main = N;
+        if (N > a.ncap || N == 0) {
+            if (sum && tid == 0) {
+                sum->status = N ? FCPP_CAND_TOO_LARGE : 0;
+                sum->n_main = N;
+                sum->n_head = 0;
+                sum->n_accel_viol = 0;
+                sum->len_main = sum->time_main = sum->time_main_pre = 0.0;
+                sum->max_curvature = sum->max_lateral_accel = sum->max_jump = 0.0;
+            }
+            return;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------
+    // phase 1: points -> shared memory (+ HBM when paths are materialised) + geofence tests
+    // ------------------------------------------------------------------------------------
+    int n_bviol = 0, n_oviol = 0;
+    if (GEN) {
+        const CandRec &r = *s.rec;
+        const double W = veh.working_width;
+        // field edges for the D3 test: cross(e, p - v) < -eps*|e|
+        double fax[4], fay[4], fex[4], fey[4], fth[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int k1 = (k + 1) & 3;
+            fax[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k];
+            fay[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k + 1];
+            fex[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1] - fax[k];
+            fey[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1 + 1] - fay[k];
+            fth[k] = -FCPP_GEOFENCE_EPS * sqrt(fex[k] * fex[k] + fey[k] * fey[k]);
+        }
+        const double rr = W / 2;
+        const double r2 = rr * rr;
+        double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
+        for (int i = tid; i < N; i += T) {
+            double x, y;
+            uint8_t c;
+            gen_point(r, *s.tt, W, i, x, y, c);
+            s.X[i] = x;
+            s.Y[i] = y;
+            s.CLS[i] = c;
+            if (gp) gp[i] = make_double2(x, y);
+            bool outb = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) outb = outb || (fex[k] * (y - fay[k]) - fey[k] * (x - fax[k]) < fth[k]);
+            n_bviol += outb;
+            bool hit = false;
+            for (int p = 0; p < n_obs_poly && !hit; ++p) {
+                const int vs = s.obs_vs[p], ve = s.obs_vs[p + 1];
+                bool inside = false;
+                for (int q = vs; q < ve; ++q) {
+                    const int q1 = (q + 1 < ve) ? q + 1 : vs;
+                    const double ax = s.obs_xy[2 * q], ay = s.obs_xy[2 * q + 1];
+                    const double bx = s.obs_xy[2 * q1], by = s.obs_xy[2 * q1 + 1];
+                    // even-odd crossing (oracle/geom.py point_in_polygon_crossing)
+                    if ((ay > y) != (by > y)) {
+                        const double xi = ax + (y - ay) * (bx - ax) / (by - ay);
+                        if (x < xi) inside = !inside;
+                    }
+                    // D2 distance test (oracle/geom.py dist2_point_segment)
+                    const double dx = bx - ax, dy = by - ay, wx = x - ax, wy = y - ay;
+                    const double dd = dx * dx + dy * dy;
+                    const double tt_ = wx * dx + wy * dy;
+                    double u = dd > 0.0 ? tt_ / dd : 0.0;
+                    u = fmin(fmax(u, 0.0), 1.0);
+                    const double qx = wx - u * dx, qy = wy - u * dy;
+                    hit = hit || (qx * qx + qy * qy < r2);
+                }
+                hit = hit || inside;
+            }
+            n_oviol += hit;
+        }
+    } else {
+        const double2 *gp = reinterpret_cast<const double2 *>(a.in_path) + off;
+        for (int i = tid; i < N; i += T) {
+            const double2 p = gp[i];
+            s.X[i] = p.x;
+            s.Y[i] = p.y;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------
+    // phase 2: per-thread contiguous chunk: ds_i -> X[i], kappa_i -> Y[i], U_i=(vlim/3.6)^2
+    // ------------------------------------------------------------------------------------
+    const int chunk = (N + T - 1) / T;
+    const int cs = min(N, tid * chunk);
+    const int ce = min(N, cs + chunk);
+    double hpx = 0.0, hpy = 0.0, hnx = 0.0, hny = 0.0;
+    if (cs < ce) {
+        if (cs > 0) {
+            hpx = s.X[cs - 1];
+            hpy = s.Y[cs - 1];
+        }
+        if (ce < N) {
+            hnx = s.X[ce];
+            hny = s.Y[ce];
+        }
+    }
+    __syncthreads();
+    double acc_len_m = 0.0, acc_len_h = 0.0, acc_tpre_m = 0.0, acc_tpre_h = 0.0;
+    if (cs < ce) {
+        double px = hpx, py = hpy;
+        double cx = s.X[cs], cy = s.Y[cs];
+        double dx1 = cx - px, dy1 = cy - py;
+        double ds1 = (cs > 0) ? sqrt(dx1 * dx1 + dy1 * dy1) : 0.0;
+        for (int i = cs; i < ce; ++i) {
+            double nx, ny;
+            if (i + 1 < ce) {
+                nx = s.X[i + 1];
+                ny = s.Y[i + 1];
+            } else {
+                nx = hnx;
+                ny = hny;
+            }
+            double dx2 = 0.0, dy2 = 0.0, ds2 = 0.0;
+            if (i + 1 < N) {
+                dx2 = nx - cx;
+                dy2 = ny - cy;
+                ds2 = sqrt(dx2 * dx2 + dy2 * dy2);
+            }
+            double kap = 0.0;
+            if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
+            double v0, v1 = 0.0;
+            if (GEN) {
+                v0 = cls_speed(veh, s.CLS[i]);
+                if (i + 1 < N) v1 = cls_speed(veh, s.CLS[i + 1]);
+            } else {
+                v0 = a.in_speeds[off + i];
+                if (i + 1 < N) v1 = a.in_speeds[off + i + 1];
+            }
+            const double vl = (GEN || a.do_speed_plan) ? vlimit(v0, kap, veh) : v0;
+            const double vms = vl / 3.6;
+            s.X[i] = ds2;
+            s.Y[i] = kap;
+            s.U[i] = vms * vms;
+            // per-layer length and pre-adjustment time (mlp3:616-617, :882-883)
+            if (i + 1 < N && i != n_main - 1) {
+                const double t = ds2 / fmax((v0 + v1) / 2 / 3.6, FCPP_MIN_SPEED_MS);
+                if (i < n_main) {
+                    acc_len_m += ds2;
+                    acc_tpre_m += t;
+                } else {
+                    acc_len_h += ds2;
+                    acc_tpre_h += t;
+                }
+            }
+            dx1 = dx2;
+            dy1 = dy2;
+            ds1 = ds2;
+            cx = nx;
+            cy = ny;
+        }
+    }
+    __syncthreads();
+
+    const bool do_scan = GEN || a.do_speed_plan;
+    const double two_a = 2 * veh.max_longitudinal_accel;
+    if (do_scan && N >= 3) {
+        // --------------------------------------------------------------------------------
+        // phase 3: forward pass  f_i = min(U_i, f_{i-1} + 2a*ds_{i-1})   (mlp3:558-571)
+        // --------------------------------------------------------------------------------
+        {
+            MP agg;
+            agg.C = 0.0;
+            agg.M = INFINITY;
+            for (int i = cs; i < ce; ++i) {
+                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
+                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                agg.M = fmin(s.U[i], agg.M + c);
+                agg.C = agg.C + c;
+            }
+            double carry = mp_block_exclusive(agg, s.scratch);
+            for (int i = cs; i < ce; ++i) {
+                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
+                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                carry = fmin(s.U[i], carry + c);
+                s.U[i] = carry;
+            }
+        }
+        __syncthreads();
+        // --------------------------------------------------------------------------------
+        // phase 4: backward pass  b_i = min(f_i, b_{i+1} + 2a*ds_i)      (mlp3:574-587)
+        // run as a forward scan over the reversed sequence: thread order is reversed by
+        // giving thread tid the chunk of thread T-1-tid
+        // --------------------------------------------------------------------------------
+        {
+            const int rt = T - 1 - tid;
+            const int rs = min(N, rt * chunk);
+            const int re = min(N, rs + chunk);
+            MP agg;
+            agg.C = 0.0;
+            agg.M = INFINITY;
+            for (int i = re - 1; i >= rs; --i) {
+                const double dsn = s.X[i];  // ds_i (0 for the last point)
+                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                agg.M = fmin(s.U[i], agg.M + c);
+                agg.C = agg.C + c;
+            }
+            double carry = mp_block_exclusive(agg, s.scratch);
+            for (int i = re - 1; i >= rs; --i) {
+                const double dsn = s.X[i];
+                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                carry = fmin(s.U[i], carry + c);
+                s.U[i] = carry;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ------------------------------------------------------------------------------------
+    // phase 5a: final speeds (km/h) -> U[i] and HBM; lateral-acceleration validation
+    // ------------------------------------------------------------------------------------
+    int n_aviol = 0;
+    double mx[3] = {0.0, 0.0, 0.0};  // max kappa, max a_lat, max |kappa jump|
+    {
+        double *gs = nullptr, *gk = nullptr;
+        if (GEN) {
+            gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
+            gk = a.out.curvature ? a.out.curvature + off : nullptr;
+        } else {
+            gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
+            gk = a.out.curvature ? a.out.curvature + off : nullptr;
+        }
+        for (int i = tid; i < N; i += T) {
+            const double kap = s.Y[i];
+            double v0;
+            if (GEN)
+                v0 = cls_speed(veh, s.CLS[i]);
+            else
+                v0 = a.in_speeds[off + i];
+            double v;
+            if (do_scan && N >= 3) {
+                const double vl = vlimit(v0, kap, veh);
+                const double vms = vl / 3.6;
+                const double u = s.U[i];
+                v = (u == vms * vms) ? vl : 3.6 * sqrt(u);
+            } else {
+                v = v0;
+            }
+            if (gs) gs[i] = v;
+            if (gk) gk[i] = kap;
+            if (i >= 1 && i + 1 < N) {
+                const double vm = v / 3.6;
+                const double alat = vm * vm * kap;  // mlp3:1389-1390
+                n_aviol += (alat > veh.max_lateral_accel);
+                mx[0] = fmax(mx[0], kap);
+                mx[1] = fmax(mx[1], alat);
+                if (i + 2 < N) mx[2] = fmax(mx[2], fabs(s.Y[i + 1] - kap));
+            }
+            s.U[i] = v;  // safe: U[i] is read only by its owner in this loop
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------------------------
+    // phase 5b: work time with the adjusted speeds (mlp3:423-431, :1298-1311)
+    // ------------------------------------------------------------------------------------
+    double acc_t_m = 0.0, acc_t_h = 0.0;
+    for (int i = tid; i + 1 < N; i += T) {
+        if (i == n_main - 1) continue;
+        const double t = s.X[i] / fmax((s.U[i] + s.U[i + 1]) / 2 / 3.6, FCPP_MIN_SPEED_MS);
+        if (i < n_main)
+            acc_t_m += t;
+        else
+            acc_t_h += t;
+    }
+    double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
+                      acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
+    block_reduce<9, false>(sums, s.scratch);
+    block_reduce<3, true>(mx, s.scratch);
+    if (tid == 0 && sum) {
+        sum->status = 0;
+        if (!GEN) {
+            sum->n_passes = 0;
+            sum->n_loops = 0;
+            sum->n_main = N;
+            sum->n_head = 0;
+        }
+        sum->len_main = sums[0];
+        sum->len_head = sums[1];
+        sum->time_main_pre = sums[2];
+        sum->time_head_pre = sums[3];
+        sum->time_main = sums[4];
+        sum->time_head = sums[5];
+        sum->n_accel_viol = (int)sums[6];
+        sum->n_boundary_viol = (int)sums[7];
+        sum->n_obstacle_viol = (int)sums[8];
+        sum->max_curvature = mx[0];
+        sum->max_lateral_accel = mx[1];
+        sum->max_jump = mx[2];
+        sum->reserved = 0.0;
+        if (!GEN || !a.b.do_coverage) {
+            sum->cov_cells = sum->cov_total = 0;
+            for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
+        }
+    }
+}
+
+template <bool GEN>
+cudaError_t configure(fcpp_handle *h, size_t bytes)
+{
+    if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(plan_kernel<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int capacity_for(fcpp_handle *h, int obs_verts, int obs_polys, int want)
+{
+    // largest point capacity that fits the opt-in shared memory; `want` caps it so that small
+    // plans leave room for more resident CTAs per SM
+    int lo = 0, hi = 1 << 20;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (plan_smem_bytes(mid, obs_verts, obs_polys) <= (size_t)h->max_smem_optin)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return want > 0 && want < lo ? want : lo;
+}
+
+}  // namespace
+
+cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
+                             int *ncap_out)
+{
+    if (b.n_cand == 0) return cudaSuccess;
+    PlanArgs a{};
+    a.b = b;
+    a.recs = h->d_rec;
+    a.trig = h->d_trig;
+    a.out = o;
+    a.obs_cap_verts = b.obs_poly_start ? b.max_obs_verts : 0;
+    a.obs_cap_polys = b.obs_poly_start ? b.max_obs_polys : 0;
+    a.ncap = capacity_for(h, a.obs_cap_verts, a.obs_cap_polys, h->plan_ncap_hint);
+    if (ncap_out) *ncap_out = a.ncap;
+    const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    cudaError_t e = configure<true>(h, bytes);
+    if (e != cudaSuccess) return e;
+    plan_kernel<true><<<(unsigned)b.n_cand, T, bytes, st>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, const double *d_path,
+                                     const double *d_speeds_in, const int64_t *d_offsets, int64_t n_paths,
+                                     int64_t max_len, int do_speed_plan, double *d_speeds_out, double *d_curv,
+                                     fcpp_summary *d_summary, cudaStream_t st)
+{
+    if (n_paths == 0) return cudaSuccess;
+    PlanArgs a{};
+    a.veh = veh;
+    a.in_path = d_path;
+    a.in_speeds = d_speeds_in;
+    a.in_offsets = d_offsets;
+    a.do_speed_plan = do_speed_plan;
+    a.out.summary = d_summary;
+    a.out.speeds_kmh = d_speeds_out;
+    a.out.curvature = d_curv;
+    a.ncap = capacity_for(h, 0, 0, max_len > 0 ? (int)((max_len + 255) / 256 * 256) : 0);
+    const size_t bytes = plan_smem_bytes(a.ncap, 0, 0);
+    cudaError_t e = configure<false>(h, bytes);
+    if (e != cudaSuccess) return e;
+    plan_kernel<false><<<(unsigned)n_paths, T, bytes, st>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}

@@ -1,0 +1,217 @@
+"""Batched GA tour-length fitness (A12) and a drop-in ``GeneticAlgorithmSolver``.
+
+``tour_lengths`` is the hot path named by north_star: the whole population's closed-tour
+lengths in one kernel launch (genetic_algorithm_solver.py:168-181, "ga").  The FP64 sum runs
+left to right per tour exactly like the reference loop, so lengths are bit-identical.
+
+``GeneticAlgorithmSolver`` keeps the reference's interface (``GAConfig``, ``solve(distance_matrix,
+verbose) -> (route, stats)``, ``best_fitness_history`` / ``avg_fitness_history``) with the fitness
+of every generation evaluated on the GPU.  The evolution operators stay on the host (SURVEY.md
+§8(f) N1: they are RNG-driven list operations and the reference uses an unseeded global
+``random``, so parity for them is statistical, not bitwise): tournament selection (ga:183-196),
+OX crossover (ga:198-242), swap mutation (ga:244-252), elitism that overwrites the LAST
+``elite_size`` children (ga:254-268), stop after ``convergence_threshold`` stagnant generations
+(ga:113-116), final rotation so that node 0 (the depot) comes first (ga:119-120).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .batch import _dev
+
+
+def tour_lengths(distance_matrix, population, device=None, return_fitness: bool = False,
+                 distributed: bool = False):
+    """Closed-tour lengths of ``population`` [pop, n] (permutations of 0..n-1) under
+    ``distance_matrix`` [n, n] (FP64; layout of multi_field_planner.py:263-288, node 0 = depot).
+
+    Accepts numpy arrays (copied to the device and back) or CUDA tensors (results stay on the
+    device).  ``return_fitness`` adds 1/(d + 1e-6) (ga:172).  ``distributed=True`` shards the
+    population over the ranks of the torch.distributed job and all-gathers the lengths."""
+    dev = _dev(device if device is not None else (population.device if torch.is_tensor(population) else None))
+    h = _lib.handle(dev.index)
+    on_dev = torch.is_tensor(population)
+    D = distance_matrix if torch.is_tensor(distance_matrix) else torch.from_numpy(
+        np.ascontiguousarray(distance_matrix, dtype=np.float64))
+    P = population if on_dev else torch.from_numpy(np.ascontiguousarray(population, dtype=np.int32))
+    D = D.to(dev, dtype=torch.float64).contiguous()
+    P = P.to(dev, dtype=torch.int32).contiguous()
+    n = D.shape[0]
+    if D.shape != (n, n) or P.ndim != 2 or P.shape[1] != n:
+        raise ValueError("distance_matrix must be [n, n] and population [pop, n]")
+    pop = P.shape[0]
+    lo, hi = 0, pop
+    if distributed:
+        import torch.distributed as dist
+        ws, rk = dist.get_world_size(), dist.get_rank()
+        per = (pop + ws - 1) // ws
+        lo, hi = min(pop, rk * per), min(pop, (rk + 1) * per)
+    with torch.cuda.device(dev):
+        out = torch.empty(max(hi - lo, 1), dtype=torch.float64, device=dev)
+        fit = torch.empty(max(hi - lo, 1), dtype=torch.float64, device=dev) if return_fitness else None
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        Ps = P[lo:hi]
+        h.check(h.lib.fcpp_tour_lengths(h.h, D.data_ptr(), n, Ps.data_ptr() if hi > lo else None, hi - lo,
+                                        out.data_ptr(), fit.data_ptr() if fit is not None else None, st))
+        out = out[:hi - lo]
+        if fit is not None:
+            fit = fit[:hi - lo]
+        if distributed:
+            import torch.distributed as dist
+            ws = dist.get_world_size()
+            per = (pop + ws - 1) // ws
+            pad = torch.zeros(per, dtype=torch.float64, device=dev)
+            pad[:hi - lo] = out
+            allv = torch.empty(per * ws, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allv, pad)
+            out = allv[:pop]
+            if fit is not None:
+                fit = 1.0 / (out + 1e-6)
+    if on_dev:
+        return (out, fit) if return_fitness else out
+    if return_fitness:
+        return out.cpu().numpy(), fit.cpu().numpy()
+    return out.cpu().numpy()
+
+
+@dataclass
+class GAConfig:
+    """ga:20-29."""
+    population_size: int = 200
+    max_generations: int = 500
+    crossover_rate: float = 0.85
+    mutation_rate: float = 0.02
+    elite_size: int = 20
+    tournament_size: int = 5
+    convergence_threshold: int = 50
+
+
+class GeneticAlgorithmSolver:
+    """Permutation GA for the multi-field TSP ordering (ga:32-268) with GPU fitness."""
+
+    def __init__(self, config: GAConfig = None, seed: Optional[int] = None, device=None):
+        self.config = config or GAConfig()
+        self.best_fitness_history: List[float] = []
+        self.avg_fitness_history: List[float] = []
+        self.rng = np.random.default_rng(seed)
+        self._device = device
+
+    # -- fitness on the device (the hot path) ------------------------------------------------
+    def _fitness(self, D_dev: torch.Tensor, pop: np.ndarray):
+        d, fit = tour_lengths(D_dev, torch.from_numpy(pop).to(D_dev.device), return_fitness=True)
+        self._last_lengths = d.cpu().numpy()
+        return fit.cpu().numpy()
+
+    def _calculate_distance(self, route, distance_matrix) -> float:
+        return float(tour_lengths(distance_matrix, np.asarray([route], dtype=np.int32), device=self._device)[0])
+
+    def _calculate_fitness(self, route, distance_matrix) -> float:
+        return 1.0 / (self._calculate_distance(route, distance_matrix) + 1e-6)
+
+    # -- host-side evolution operators (statistical parity) ---------------
+    def _initialize_population(self, n: int) -> np.ndarray:
+        cfg = self.config
+        half = cfg.population_size // 2
+        rows = [self.rng.permutation(n) for _ in range(half)]
+        for i in range(half):   # "greedy" init of the reference is random too (ga:155-166)
+            start = i % n
+            rest = self.rng.permutation(np.delete(np.arange(n), start))
+            rows.append(np.concatenate([[start], rest]))
+        return np.asarray(rows, dtype=np.int32)
+
+    def _selection(self, pop: np.ndarray, fit: np.ndarray) -> np.ndarray:
+        k = self.config.tournament_size
+        m = len(pop)
+        # sampling WITHOUT replacement per tournament (random.sample, ga:189); first max wins
+        idx = np.argsort(self.rng.random((m, m)), axis=1)[:, :k] if m <= 2048 else \
+            np.stack([self.rng.choice(m, size=k, replace=False) for _ in range(m)])
+        win = idx[np.arange(m), np.argmax(fit[idx], axis=1)]
+        return pop[win].copy()
+
+    def _ox(self, p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
+        n = len(p1)
+        a, b = sorted(self.rng.choice(n, size=2, replace=False).tolist())
+        child = np.full(n, -1, dtype=np.int32)
+        child[a:b] = p1[a:b]
+        used = np.zeros(n, dtype=bool)
+        used[p1[a:b]] = True
+        order = np.concatenate([p2[b:], p2[:b]])          # fill starts at cx_point2, wrapping (ga:229-240)
+        fill = order[~used[order]]
+        pos = np.concatenate([np.arange(b, n), np.arange(0, a)])
+        child[pos] = fill
+        return child
+
+    def _crossover(self, pop: np.ndarray) -> np.ndarray:
+        out = []
+        m = len(pop)
+        for i in range(0, m, 2):
+            p1 = pop[i]
+            p2 = pop[i + 1] if i + 1 < m else pop[0]      # odd population pairs with individual 0 (ga:205)
+            if self.rng.random() < self.config.crossover_rate:
+                out.append(self._ox(p1, p2))
+                out.append(self._ox(p2, p1))
+            else:
+                out.append(p1.copy())
+                out.append(p2.copy())
+        return np.asarray(out, dtype=np.int32)
+
+    def _mutation(self, pop: np.ndarray) -> np.ndarray:
+        n = pop.shape[1]
+        hit = np.nonzero(self.rng.random(len(pop)) < self.config.mutation_rate)[0]
+        for r in hit:
+            i, j = self.rng.choice(n, size=2, replace=False)
+            pop[r, i], pop[r, j] = pop[r, j], pop[r, i]
+        return pop
+
+    def _elitism(self, old: np.ndarray, fit: np.ndarray, new: np.ndarray) -> np.ndarray:
+        e = self.config.elite_size
+        elite = old[np.argsort(-fit, kind="stable")[:e]]
+        return np.concatenate([new[:-e], elite]) if e > 0 else new   # drops the LAST children (ga:266)
+
+    def solve(self, distance_matrix: np.ndarray, verbose: bool = True) -> Tuple[List[int], dict]:
+        """ga:44-135."""
+        cfg = self.config
+        t0 = time.time()
+        n = len(distance_matrix)
+        dev = _dev(self._device)
+        D_dev = torch.from_numpy(np.ascontiguousarray(distance_matrix, dtype=np.float64)).to(dev)
+        pop = self._initialize_population(n)
+        fit = self._fitness(D_dev, pop)
+        best_i = int(np.argmax(fit))
+        best_route, best_fit = pop[best_i].copy(), float(fit[best_i])
+        best_distance = float(self._last_lengths[best_i])
+        stagnant, gens, gen = 0, 0, -1
+        self.best_fitness_history, self.avg_fitness_history = [], []
+        for gen in range(cfg.max_generations):
+            gens = gen + 1
+            sel = self._selection(pop, fit)
+            chi = self._mutation(self._crossover(sel))
+            pop = self._elitism(pop, fit, chi)
+            fit = self._fitness(D_dev, pop)
+            gi = int(np.argmax(fit))
+            if fit[gi] > best_fit:
+                best_fit, best_route = float(fit[gi]), pop[gi].copy()
+                best_distance = float(self._last_lengths[gi])
+                stagnant = 0
+            else:
+                stagnant += 1
+            self.best_fitness_history.append(best_fit)
+            self.avg_fitness_history.append(float(np.mean(fit)))
+            if stagnant >= cfg.convergence_threshold:
+                break
+        route = best_route.tolist()
+        z = route.index(0)
+        route = route[z:] + route[:z]                      # depot first (ga:119-120)
+        stats = {'generations': gens, 'best_distance': best_distance, 'best_fitness': best_fit,
+                 'convergence_gen': gen - stagnant,      # ga:125-130
+                 'time': time.time() - t0}
+        if verbose:
+            print(f"[fcpp GA] nodes={n} generations={gens} best={best_distance:.1f} m time={stats['time']:.2f} s")
+        return route, stats

@@ -36,7 +36,8 @@ extern "C" {
 #define FCPP_UTURN_POINTS 20      /* mlp3:807  */
 #define FCPP_CORNER_POINTS 15     /* mlp3:1046, :1589 */
 #define FCPP_STRAIGHT_POINTS 20   /* mlp3:990  */
-#define FCPP_MAX_LOOPS 16         /* K = ceil(R/W) (mlp3:916) supported up to this */
+#define FCPP_MAX_LOOPS 8          /* K = ceil(R/W) (mlp3:916) supported up to this */
+#define FCPP_POINTS_PER_LOOP 126   /* 1 + 4*20 + 3*15, mlp3:979-1007 */
 #define FCPP_FIXED_UNIT 1e4       /* coverage lattice: 1e-4 m fixed point */
 
 typedef enum {
@@ -82,6 +83,8 @@ typedef struct {
     const int32_t *obs_vert_start; /* [NP+1] vertices of polygon p are obs_vert_start[p] .. [p+1] */
     const double *obs_verts;       /* [NV][2] */
     const double *obs_moments;     /* [NP][3] area, area*cx, area*cy of the W/2 round buffer (D2) */
+    int32_t max_obs_verts;         /* max over fields of the obstacle vertices of one field */
+    int32_t max_obs_polys;         /* max over fields of the obstacle polygons of one field */
     /* ---- candidates ---- */
     int64_t n_cand;
     const int32_t *cand_field;     /* [B] field index */
@@ -90,7 +93,9 @@ typedef struct {
                                       (host libm/numpy values; replaces mlp3:244-263, used :682-716) */
     const int32_t *cand_flags;     /* [B] bits 0-1 start corner (mlp3:397-399), bit 2 reverse_order,
                                       bit 3 start_from_right (mlp3:631-668), bit 4 rotated
-                                      (|a| > 0.01, mlp3:686), bit 5 corner gap gate (mlp3:1070) */
+                                      (|a| > 0.01, mlp3:686), bit 5 corner gap gate (mlp3:1070),
+                                      bit 6: derive bits 2-3 from cand_start (mlp3:649-658) */
+    const double *cand_start;      /* [B][2] start_point (mlp3:689-696) or NULL; read when bit 6 is set */
     /* ---- coverage raster ---- */
     double grid_h;                 /* headland-band cell size in m (0.1 default, 0.05 in config 5) */
     int32_t do_coverage;           /* 0: skip A10/A11 */
@@ -101,8 +106,9 @@ typedef struct {
 #define FCPP_FLAG_START_FROM_RIGHT 8
 #define FCPP_FLAG_ROTATED 16
 #define FCPP_FLAG_GAP_GATE 32
+#define FCPP_FLAG_START_POINT 64
 
-/* One record per candidate (A8-A11, A13 + layout). 192 bytes. */
+/* One record per candidate (A8-A11, A13 + layout). 176 bytes. */
 typedef struct {
     int32_t status;           /* FCPP_CAND_* bits */
     int32_t n_passes;         /* P, mlp3:739 */
@@ -176,10 +182,10 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
  * mlp3:1373-1424 and length/time mlp3:1290-1311 into d_summary (fields n_accel_viol, max_*,
  * len_main, time_main, time_main_pre; the split point n_main = whole path).
  * do_speed_plan = 0 verifies the given speeds without adjusting them. */
-int fcpp_speed_verify(fcpp_handle *h, const fcpp_vehicle *veh, double min_turn_radius_unused,
-                      const double *d_path_xy, const double *d_speeds_in, const int64_t *d_offsets,
-                      int64_t n_paths, int do_speed_plan, double *d_speeds_out, double *d_curvature,
-                      fcpp_summary *d_summary, void *stream);
+int fcpp_speed_verify(fcpp_handle *h, const fcpp_vehicle *veh, const double *d_path_xy,
+                      const double *d_speeds_in, const int64_t *d_offsets, int64_t n_paths,
+                      int64_t max_path_len, int do_speed_plan, double *d_speeds_out,
+                      double *d_curvature, fcpp_summary *d_summary, void *stream);
 
 /* Generic A10 window raster (mlp3:1426-1510): ORs the W/2 round buffer of a polyline into a
  * g x g lattice-point window (bit (j*g+i) of d_bits, row-major, 32-bit words, ceil(g*g/32) words,

@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the Python host) against the CPU
+oracle on the same inputs, against the committed golden fixtures of the reference, and —
+at BASELINE.json's full sizes — through size-independent properties.
+
+Tolerances (north_star): counts bit-exact; points <= 1e-4 m; speeds <= 1e-4 m/s = 3.6e-4 km/h.
+The generated points are expected to be BIT-IDENTICAL to numpy's (host-supplied trig tables,
+-fmad=false), so the tests assert a much tighter 1e-9 and record the observed maximum.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PT_TOL = 1e-4          # m       (north_star)
+SPEED_TOL = 3.6e-4     # km/h    (north_star: 1e-4 m/s)
+TIGHT = 1e-9           # what the design actually delivers
+
+
+@pytest.fixture(scope="module")
+def fc():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import field_coverage_path_planning_b200 as pkg
+    return pkg
+
+
+def _golden_cases():
+    d = os.path.join(os.path.dirname(__file__), "golden")
+    return sorted(glob.glob(os.path.join(d, "ref_*.npz")))
+
+
+def _meta(z):
+    meta = json.loads(str(z["meta"]))
+    kw = dict(meta["planner"])
+    for k in ("start_point", "end_point"):
+        if kw.get(k) is not None:
+            kw[k] = tuple(kw[k])
+    if kw.get("field_vertices") is not None:
+        kw["field_vertices"] = [tuple(v) for v in kw["field_vertices"]]
+    return meta, kw
+
+
+@pytest.mark.parametrize("path", _golden_cases(), ids=lambda p: os.path.basename(p)[4:-4])
+def test_single_plan_vs_reference_golden(fc, path):
+    """Drop-in API vs outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    z = np.load(path)
+    meta, kw = _meta(z)
+    veh = fc.VehicleParams(**meta["vehicle"])
+    planner = fc.TwoLayerPathPlannerV37(veh, **kw)
+    assert planner.field_shape == meta["field_shape"]
+    assert planner.main_work_pattern == meta["pattern"]
+    r = planner.plan_complete_coverage()
+    assert r["version"] == "V3.5.1"
+    assert r["main_work"]["path"].shape == z["main_path"].shape        # integer layout: exact
+    assert r["headland"]["path"].shape == z["head_path"].shape
+    dm = np.abs(r["main_work"]["path"] - z["main_path"]).max()
+    dh = np.abs(r["headland"]["path"] - z["head_path"]).max()
+    ds = max(np.abs(r["main_work"]["speeds"] - z["main_speeds"]).max(),
+             np.abs(r["headland"]["speeds"] - z["head_speeds"]).max())
+    assert dm <= TIGHT and dh <= TIGHT, (dm, dh)
+    assert ds <= TIGHT, ds
+    assert dm <= PT_TOL and dh <= PT_TOL and ds <= SPEED_TOL
+    for layer, key in (("main_work", "main_stats"), ("headland", "head_stats")):
+        got = [r[layer]["stats"][k] for k in ("path_length_km", "time_hours", "avg_speed_kmh")]
+        np.testing.assert_allclose(got, z[key], rtol=1e-11)
+    allp = np.vstack([r["main_work"]["path"], r["headland"]["path"]])
+    alls = np.concatenate([r["main_work"]["speeds"], r["headland"]["speeds"]])
+    cc = planner.verify_curvature_constraints(allp, alls)
+    ref = z["curv"]
+    np.testing.assert_allclose([cc["max_curvature"], cc["max_lateral_accel"], cc["max_jump"]],
+                               [ref[0], ref[1], ref[4]], rtol=1e-9)
+    assert cc["accel_violations"] == int(ref[2])
+    assert cc["pass"] == bool(ref[5])
+    for name, key in (("approach_path", "approach"), ("departure_path", "departure")):
+        if len(z[key]):
+            np.testing.assert_allclose(r[name], z[key], rtol=0, atol=TIGHT)
+        else:
+            assert r[name] is None
+    if "corner_cells_float" in z.files:
+        cov = planner.verify_all_corners_coverage(r["headland"])
+        got = np.array([[c["cells_before"], c["cells_after"]] for c in cov["corners"]])
+        assert np.max(np.abs(got - z["corner_cells_float"])) <= 2      # float64 vs exact fixed point (D5)
+    # README.md:199: "100.0 %" headland coverage for the rectangles
+    assert 0.99 < r["headland"]["stats"]["coverage_rate"] <= 1.0
+
+
+def _summary_vs_oracle(s, o, coverage=True):
+    assert int(s["status"]) == o["status"]
+    if o["status"]:
+        return
+    for k in ("n_passes", "n_loops", "n_main", "n_head", "n_accel_viol", "n_boundary_viol", "n_obstacle_viol"):
+        assert int(s[k]) == int(o[k]), (k, int(s[k]), o[k])
+    for k in ("len_main", "len_head", "time_main", "time_head", "time_main_pre", "time_head_pre",
+              "max_curvature", "max_lateral_accel", "max_jump"):
+        np.testing.assert_allclose(float(s[k]), o[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    if coverage:
+        assert int(s["corner_g"]) == o["corner_g"]
+        assert list(map(int, s["corner_before"])) == o["corner_before"]
+        assert list(map(int, s["corner_after"])) == o["corner_after"]
+        assert (int(s["cov_total"]), int(s["cov_cells"])) == (o["cov_total"], o["cov_cells"])
+
+
+OBST2 = [[(200, 80), (250, 80), (250, 120), (200, 120)], [(350, 140), (380, 140), (380, 170), (350, 170)]]
+RECT = [(0, 0), (500, 0), (500, 200), (0, 200)]
+
+
+def test_batch_config2_subset_vs_oracle(fc):
+    """BASELINE config 2 (500x200 + two obstacles, start corner x radius), a 44-candidate subset
+    including the FP64 knife-edge radii of SURVEY.md App. A Q17 — every summary field against
+    the oracle, paths and speeds of every candidate too."""
+    from oracle import batch as ob, ref_planner as rp
+    veh = fc.VehicleParams()
+    radii = np.concatenate([np.linspace(5.0, 12.0, 8), [7.2, 9.6, 6.4]])
+    cand = fc.make_candidates(1, radii=radii, start_corners=[0, 1, 2, 3])
+    res = fc.plan_batch([RECT], veh, cand, obstacles=[OBST2], outputs="paths")
+    oveh = rp.VehicleParams()
+    assert len(res.summary) == len(radii) * 4
+    worst_p = worst_s = 0.0
+    for b in range(len(res.summary)):
+        o = ob.evaluate_candidate(RECT, oveh, R=cand["R"][b], start_corner=int(cand["start_corner"][b]),
+                                  obstacles=OBST2, keep_paths=True)
+        _summary_vs_oracle(res.summary[b], o)
+        p, s, nm = res.path(b)
+        assert p.shape == o["path"].shape
+        worst_p = max(worst_p, np.abs(p - o["path"]).max())
+        worst_s = max(worst_s, np.abs(s - o["speeds"]).max())
+    assert worst_p <= TIGHT and worst_s <= TIGHT, (worst_p, worst_s)
+    assert res.summary["n_obstacle_viol"].max() > 0        # swaths run through the obstacles (Q2)
+    # argmin: len_main + len_head, ties to the lowest index
+    cost = res.summary["len_main"] + res.summary["len_head"]
+    assert int(res.best_cand[0]) == int(np.argmin(cost))
+    assert res.best_cost[0] == cost.min()
+
+
+def test_batch_config3_parallelograms_headings_vs_oracle(fc):
+    """BASELINE config 3 in miniature: seeded tilted parallelograms x headings; counts exact."""
+    from oracle import batch as ob, ref_planner as rp
+    rng = np.random.default_rng(1234)
+    F = 6
+    fields = []
+    for _ in range(F):
+        L, Wd = rng.uniform(200, 800), rng.uniform(100, 400)
+        sx, phi = rng.uniform(-0.4, 0.4) * Wd, rng.uniform(0, np.pi)
+        o = rng.uniform(0, 5000, 2)
+        q = np.array([(0, 0), (L, 0), (L + sx, Wd), (sx, Wd)])
+        rot = np.array([[np.cos(phi), -np.sin(phi)], [np.sin(phi), np.cos(phi)]])
+        fields.append(q @ rot.T + o)
+    fields = np.array(fields)
+    heads = np.deg2rad([0.0, 17.0, 45.0, 90.0, 133.0, 179.0])
+    cand = fc.make_candidates(F, headings=heads)
+    veh = fc.VehicleParams()
+    res = fc.plan_batch(fields, veh, cand, outputs="paths", grid_h=0.1)
+    oveh = rp.VehicleParams()
+    for b in range(len(res.summary)):
+        f = int(cand["field_id"][b])
+        o = ob.evaluate_candidate(fields[f], oveh, heading=float(cand["heading"][b]), keep_paths=True,
+                                  coverage=(b % 6 == 0))
+        _summary_vs_oracle(res.summary[b], o, coverage=(b % 6 == 0))
+        if not o["status"]:
+            p, s, _ = res.path(b)
+            assert np.abs(p - o["path"]).max() <= TIGHT
+            assert np.abs(s - o["speeds"]).max() <= TIGHT
+    # per-field argmin is local to each field's 6 headings
+    cost = res.summary["len_main"] + res.summary["len_head"]
+    for f in range(F):
+        assert int(res.best_cand[f]) == f * 6 + int(np.argmin(cost[f * 6:(f + 1) * 6]))
+
+
+def test_degenerate_candidates_status(fc):
+    """mlp3:597-598 (headland too wide) and mlp3:967-969 (loop skipped) become status bits."""
+    from oracle import batch as ob, ref_planner as rp
+    fields = [[(0, 0), (30, 0), (30, 15), (0, 15)], RECT]
+    cand = fc.make_candidates(2, radii=[8.0, 40.0])
+    res = fc.plan_batch(fields, fc.VehicleParams(), cand)
+    for b in range(4):
+        o = ob.evaluate_candidate(fields[int(cand["field_id"][b])], rp.VehicleParams(), R=cand["R"][b],
+                                  coverage=False)
+        assert int(res.summary["status"][b]) == o["status"]
+    assert res.summary["status"][0] != 0 and res.summary["status"][2] == 0
+    with pytest.raises(ValueError):
+        fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=30, field_width=15).plan()
+
+
+def test_full_config2_properties(fc):
+    """BASELINE config 2 at full size (4096 candidates): summary-only and paths mode agree bit for
+    bit, the run is idempotent, counts obey their closed forms and the path
+    buffers are consistent with the summaries."""
+    import torch
+    veh = fc.VehicleParams()
+    radii = np.linspace(5.0, 12.0, 1024)
+    cand = fc.make_candidates(1, radii=radii, start_corners=[0, 1, 2, 3])
+    a = fc.plan_batch([RECT], veh, cand, obstacles=[OBST2], outputs="summary")
+    b = fc.plan_batch([RECT], veh, cand, obstacles=[OBST2], outputs="paths")
+    assert a.summary.tobytes() == b.summary.tobytes()
+    c = fc.plan_batch([RECT], veh, cand, obstacles=[OBST2], outputs="summary")
+    assert a.summary.tobytes() == c.summary.tobytes()
+    s = a.summary
+    assert (s["status"] == 0).all()
+    P = s["n_passes"]
+    assert (s["n_main"] == 2 * P + 20 * (P - 1)).all()
+    K = np.ceil(cand["R"] / 3.2).astype(int)
+    assert (s["n_loops"] == K).all()
+    assert (s["n_head"] == 126 * K + s["n_rev"].sum(1)).all()
+    assert (s["corner_g"] == (2 * cand["R"] / 0.1).astype(int)).all()
+    assert (s["n_accel_viol"] == 0).all()                      # safety_factor < 1 (Q16)
+    assert (s["cov_total"] > 0).all() and (s["cov_cells"] <= s["cov_total"]).all()
+    assert (s["corner_after"] >= s["corner_before"]).all()
+    # start corner only permutes the visiting order: total band cells depend on R alone
+    tot = s["cov_total"].reshape(1024, 4)
+    assert (tot == tot[:, :1]).all()
+    # offsets are the prefix sum of the counts
+    n = s["n_main"] + s["n_head"]
+    assert (np.diff(b.offsets) == n).all()
+    # path length recomputed from the materialised points equals the summary (checksum of checksums)
+    d = b.d_path[1:] - b.d_path[:-1]
+    seg = torch.sqrt((d * d).sum(1)).cpu().numpy()
+    for k in (0, 1234, 4095):
+        o0, nm, nt = int(b.offsets[k]), int(s["n_main"][k]), int(n[k])
+        np.testing.assert_allclose(seg[o0:o0 + nm - 1].sum(), s["len_main"][k], rtol=1e-12)
+        np.testing.assert_allclose(seg[o0 + nm:o0 + nt - 1].sum(), s["len_head"][k], rtol=1e-12)
+    assert torch.isfinite(b.d_speeds).all()
+    assert float(b.d_speeds.min()) > 0 and float(b.d_speeds.max()) <= 15.0
+
+
+def test_speed_planner_random_paths_vs_oracle(fc):
+    """A7 on caller-supplied paths: random walks with duplicates, sharp turns and long jumps."""
+    from oracle import ref_planner as rp
+    rng = np.random.default_rng(5)
+    veh = fc.VehicleParams()
+    oveh = rp.VehicleParams()
+    pl = fc.TwoLayerPathPlannerV37(veh, field_length=500, field_width=200)
+    for n in (3, 17, 256, 257, 1000, 5000):
+        step = rng.normal(0, 1.0, size=(n, 2)) * rng.choice([0.0, 0.3, 1.0, 25.0], size=(n, 1), p=[0.1, 0.3, 0.5, 0.1])
+        path = np.cumsum(step, axis=0) + 1000.0
+        speeds = rng.choice([2.5, 4.0, 9.0, 15.0], size=n)
+        got = pl._apply_curvature_based_speed_limit(path, speeds)
+        want = rp.speed_plan(path, speeds, oveh)
+        assert np.abs(got - want).max() <= 1e-9, n
+        cc = pl.verify_curvature_constraints(path, got)
+        oc = rp.verify_curvature_constraints(path, want, oveh)
+        assert cc["accel_violations"] == oc["accel_violations"]
+        np.testing.assert_allclose(cc["max_curvature"], oc["max_curvature"], rtol=1e-9)
+        np.testing.assert_allclose(pl._calculate_path_length(path), rp.path_length(path), rtol=1e-12)
+        np.testing.assert_allclose(pl._calculate_work_time(path, got), rp.work_time(path, want), rtol=1e-9)
+    # ragged edge cases of the reference: fewer than 3 points are returned untouched (mlp3:480-481)
+    p2 = np.array([[0.0, 0.0], [1.0, 0.0]])
+    s2 = np.array([9.0, 9.0])
+    assert pl._apply_curvature_based_speed_limit(p2, s2) is s2
+    assert pl.verify_curvature_constraints(p2, s2) == {'max_curvature': 0, 'violations': 0, 'pass': True}
+    assert pl._calculate_path_length(p2[:1]) == 0.0
+
+
+def test_raster_window_random_polylines_vs_oracle(fc):
+    """A10 on caller-supplied polylines vs the brute-force integer oracle (bit-exact grids)."""
+    from oracle import raster
+    rng = np.random.default_rng(11)
+    pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=500, field_width=200)
+    R, W = 8.0, 3.2
+    g = int(2 * R / 0.1)
+    for trial in range(6):
+        corner = (float(rng.uniform(0, 400)), float(rng.uniform(0, 150)))
+        ci = trial % 4
+        n1, n2 = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+        base = np.array(corner) + rng.uniform(-4, 12, 2)
+        turn = base + np.cumsum(rng.normal(0, 1.5, size=(n1, 2)), axis=0)
+        rev = turn[-1] + np.cumsum(rng.normal(0, 1.0, size=(n2, 2)), axis=0)
+        if trial == 3:
+            rev[5] = rev[4]                                   # zero-length segment
+        got = pl.verify_corner_coverage_grid_based(corner, ci, turn, rev)
+        ox = corner[0] if ci in (0, 3) else corner[0] - 2 * R
+        oy = corner[1] if ci in (0, 1) else corner[1] - 2 * R
+        c1, bits = raster.raster_window(turn, W / 2, (ox, oy), 0.1, g, g)
+        c2, bits = raster.raster_window(rev, W / 2, (ox, oy), 0.1, g, g, bits)
+        assert (got["cells_before"], got["cells_after"]) == (c1, c2)
+        want = np.unpackbits(bits, bitorder="little")[:g * g].reshape(g, g).astype(bool)
+        assert np.array_equal(got["grid"], want)
+
+
+def test_tour_lengths_vs_reference_golden_and_oracle(fc, golden_dir):
+    from oracle import raster
+    z = np.load(os.path.join(golden_dir, "ga_tours.npz"))
+    d, f = fc.tour_lengths(z["D"], z["pop"], return_fitness=True)
+    assert np.array_equal(d, z["dist"])                       # sequential FP64 sum: bit-exact
+    assert np.array_equal(f, z["fitness"])
+    # BASELINE config 4: 200 fields + depot, population 8192
+    rng = np.random.default_rng(42)
+    pos = np.vstack([[100.0, 100.0], rng.uniform(0, 5000, size=(200, 2))])
+    D = np.sqrt(((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1))
+    prng = np.random.default_rng(7)
+    pop = np.array([prng.permutation(201) for _ in range(8192)], dtype=np.int32)
+    got = fc.tour_lengths(D, pop)
+    assert np.array_equal(got, raster.tour_lengths(D, pop))
+    # invariances: rotating or reversing a closed tour keeps its length up to summation order
+    np.testing.assert_allclose(fc.tour_lengths(D, np.roll(pop[:64], 5, axis=1)), got[:64], rtol=1e-12)
+    np.testing.assert_allclose(fc.tour_lengths(D, pop[:64, ::-1].copy()), got[:64], rtol=1e-12)
+    # ragged sizes
+    for n, m in ((2, 1), (3, 5), (33, 129), (64, 128)):
+        Dn = D[:n, :n].copy()
+        pn = np.array([prng.permutation(n) for _ in range(m)], dtype=np.int32)
+        assert np.array_equal(fc.tour_lengths(Dn, pn), raster.tour_lengths(Dn, pn))
+
+
+def test_ga_solver_improves(fc):
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(0, 1000, size=(30, 2))
+    D = np.sqrt(((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1))
+    solver = fc.GeneticAlgorithmSolver(fc.GAConfig(population_size=120, max_generations=150), seed=1)
+    route, stats = solver.solve(D, verbose=False)
+    assert sorted(route) == list(range(30)) and route[0] == 0
+    rand = fc.tour_lengths(D, np.array([rng.permutation(30) for _ in range(200)], dtype=np.int32)).mean()
+    assert stats["best_distance"] < 0.6 * rand
+    assert abs(stats["best_distance"] - fc.tour_lengths(D, np.array([route], dtype=np.int32))[0]) < 1e-6
+
+
+def test_config5_large_field_fine_grid(fc):
+    """BASELINE config 5 geometry (2 km x 1 km, h = 0.05 m): one candidate against the oracle,
+    and a closed form for the number of band cells."""
+    from oracle import batch as ob, ref_planner as rp
+    big = [(0, 0), (2000, 0), (2000, 1000), (0, 1000)]
+    cand = fc.make_candidates(1, radii=[8.0, 5.0], start_corners=[0, 2])
+    res = fc.plan_batch([big], fc.VehicleParams(), cand, grid_h=0.05)
+    s = res.summary
+    assert (s["status"] == 0).all()
+    assert int(s["n_main"][0]) == 6756 and int(s["n_head"][0]) == 435
+    assert int(s["cov_total"][0]) == 19097600
+    o = ob.evaluate_candidate(big, rp.VehicleParams(), R=8.0, start_corner=0, grid_h=0.05)
+    _summary_vs_oracle(s[0], o)
