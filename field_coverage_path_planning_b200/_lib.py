@@ -60,6 +60,7 @@ class Batch(C.Structure):
         ("cand_start", C.c_void_p),
         ("grid_h", C.c_double),
         ("do_coverage", C.c_int32),
+        ("max_points_hint", C.c_int32),
     ]
 
 
@@ -88,7 +89,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
     "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_speed_verify", "fcpp_raster_window",
-    "fcpp_tour_lengths", "fcpp_launch_count",
+    "fcpp_tour_lengths", "fcpp_launch_count", "fcpp_last_max_points", "fcpp_set_profiling", "fcpp_kernel_times",
 ]
 
 _lib = None
@@ -133,6 +134,12 @@ def load():
         L.fcpp_raster_window.argtypes = [vp, vp, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
         L.fcpp_tour_lengths.restype = C.c_int
         L.fcpp_tour_lengths.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
+        L.fcpp_last_max_points.restype = i32
+        L.fcpp_last_max_points.argtypes = [vp]
+        L.fcpp_set_profiling.restype = C.c_int
+        L.fcpp_set_profiling.argtypes = [vp, C.c_int]
+        L.fcpp_kernel_times.restype = C.c_int
+        L.fcpp_kernel_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
         if L.fcpp_abi_version() != ABI_VERSION:
             raise FcppError(f"libfcpp.so ABI {L.fcpp_abi_version()} != expected {ABI_VERSION}: rebuild")
         _lib = L

@@ -207,9 +207,33 @@ class BatchResult:
                 int(self.summary["n_main"][b]))
 
 
+class BatchBuffers:
+    """Device output buffers of one batch shape, reusable across calls (steady-state serving:
+    no allocation, no readback, no synchronisation inside the step)."""
+
+    def __init__(self, dev: torch.device, n_cand: int, n_fields: int, total_points: int = 0,
+                 want_curvature: bool = False):
+        self.dev = dev
+        self.n_cand, self.n_fields, self.total_points = n_cand, n_fields, total_points
+        self.d_sum = torch.empty(max(n_cand, 1) * _lib.SUMMARY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.d_cost = torch.empty(max(n_fields, 1), dtype=torch.float64, device=dev)
+        self.d_best = torch.empty(max(n_fields, 1), dtype=torch.int64, device=dev)
+        self.d_off = self.d_path = self.d_spd = self.d_kap = None
+        if total_points > 0:
+            self.d_off = torch.empty(n_cand + 1, dtype=torch.int64, device=dev)
+            self.d_path = torch.empty((total_points, 2), dtype=torch.float64, device=dev)
+            self.d_spd = torch.empty(total_points, dtype=torch.float64, device=dev)
+            if want_curvature:
+                self.d_kap = torch.empty(total_points, dtype=torch.float64, device=dev)
+
+
 def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
-                     cost: str = "length", cand_base: int = 0, copy_summary: bool = True) -> BatchResult:
-    """Enqueue one batch on torch's current stream and (optionally) fetch the summaries."""
+                     cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
+                     buffers: Optional[BatchBuffers] = None, fetch: bool = True) -> Optional[BatchResult]:
+    """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
+
+    With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
+    whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only."""
     if outputs not in ("summary", "paths"):
         raise ValueError("outputs must be 'summary' or 'paths'")
     dev = db.dev
@@ -218,38 +242,53 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
     B, F = db.pb.n_cand, db.pb.n_fields
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
-        d_sum = torch.empty(max(B, 1) * _lib.SUMMARY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         out = _lib.Outputs()
-        out.summary = d_sum.data_ptr()
-        d_off = d_path = d_spd = d_kap = None
         offsets = None
+        if buffers is None:
+            db.c.max_points_hint = 0
+            total = 0
+            if outputs == "paths":
+                d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+                h.check(L.fcpp_layout(h.h, C.byref(db.c), None, d_off.data_ptr(), stream))
+                offsets = d_off.cpu().numpy()
+                total = max(int(offsets[-1]), 1)
+            buffers = BatchBuffers(dev, B, F, total, want_curvature)
+            if outputs == "paths":
+                buffers.d_off = d_off
+        else:
+            db.c.max_points_hint = int(getattr(db, "max_points", 0))
+            if outputs == "paths":
+                if buffers.d_off is None:
+                    raise ValueError("buffers were allocated without path storage")
+                h.check(L.fcpp_layout(h.h, C.byref(db.c), None, buffers.d_off.data_ptr(), stream))
+        out.summary = buffers.d_sum.data_ptr()
         if outputs == "paths":
-            d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
-            h.check(L.fcpp_layout(h.h, C.byref(db.c), None, d_off.data_ptr(), stream))
-            offsets = d_off.cpu().numpy()
-            total = int(offsets[-1])
-            d_path = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)
-            d_spd = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
-            out.offsets = d_off.data_ptr()
-            out.path_xy = d_path.data_ptr()
-            out.speeds_kmh = d_spd.data_ptr()
-            if want_curvature:
-                d_kap = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
-                out.curvature = d_kap.data_ptr()
+            out.offsets = buffers.d_off.data_ptr()
+            out.path_xy = buffers.d_path.data_ptr()
+            out.speeds_kmh = buffers.d_spd.data_ptr()
+            if buffers.d_kap is not None:
+                out.curvature = buffers.d_kap.data_ptr()
         h.check(L.fcpp_plan_batch(h.h, C.byref(db.c), C.byref(out), stream))
-        d_cost = torch.empty(max(F, 1), dtype=torch.float64, device=dev)
-        d_best = torch.empty(max(F, 1), dtype=torch.int64, device=dev)
-        h.check(L.fcpp_field_argmin(h.h, d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
-                                    0 if cost == "length" else 1, cand_base, d_cost.data_ptr(),
-                                    d_best.data_ptr(), stream))
+        if db.c.max_points_hint == 0:
+            db.max_points = int(L.fcpp_last_max_points(h.h))
+        h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
+                                    0 if cost == "length" else 1, cand_base, buffers.d_cost.data_ptr(),
+                                    buffers.d_best.data_ptr(), stream))
+        if not fetch:
+            return None
         if copy_summary:
-            summary = d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE)[:B]
+            summary = buffers.d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE)[:B]
         else:
             summary = np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
-        best_cost = d_cost.cpu().numpy()[:F]
-        best_cand = d_best.cpu().numpy()[:F]
-    return BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
-                       d_path=d_path, d_speeds=d_spd, d_curvature=d_kap, d_summary=d_sum, cand_base=cand_base)
+        best_cost = buffers.d_cost.cpu().numpy()[:F]
+        best_cand = buffers.d_best.cpu().numpy()[:F]
+        if outputs == "paths" and offsets is None:
+            offsets = buffers.d_off.cpu().numpy()
+    res = BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
+                      d_path=buffers.d_path, d_speeds=buffers.d_spd, d_curvature=buffers.d_kap,
+                      d_summary=buffers.d_sum, cand_base=cand_base)
+    res.extras["buffers"] = buffers
+    return res
 
 
 def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,

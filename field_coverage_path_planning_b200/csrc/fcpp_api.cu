@@ -130,12 +130,38 @@ void fcpp_destroy(fcpp_handle *h)
     if (h->d_scan_tmp) cudaFree(h->d_scan_tmp);
     if (h->d_maxn) cudaFree(h->d_maxn);
     if (h->h_maxn) cudaFreeHost(h->h_maxn);
+    for (int k = 0; k < 4; ++k)
+        if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     free(h);
 }
 
 const char *fcpp_last_error(const fcpp_handle *h) { return h ? h->err : "invalid handle"; }
 
 int64_t fcpp_launch_count(const fcpp_handle *h) { return h ? h->launches : 0; }
+
+int32_t fcpp_last_max_points(const fcpp_handle *h) { return h ? h->last_maxn : 0; }
+
+int fcpp_set_profiling(fcpp_handle *h, int on)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (on && !h->ev[0]) {
+        for (int k = 0; k < 4; ++k)
+            if (cudaEventCreate(&h->ev[k]) != cudaSuccess) return cuda_fail(h, cudaGetLastError(), "cudaEventCreate");
+    }
+    h->profiling = on != 0;
+    return FCPP_OK;
+}
+
+int fcpp_kernel_times(fcpp_handle *h, float *ms3)
+{
+    if (!h || !ms3 || !h->ev[0]) return fail(h, FCPP_ERR_INVALID, "profiling is off");
+    for (int k = 0; k < 3; ++k) {
+        cudaError_t e = cudaEventElapsedTime(&ms3[k], h->ev[k], h->ev[k + 1]);
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaEventElapsedTime");
+    }
+    return FCPP_OK;
+}
 
 int fcpp_set_trig_tables(fcpp_handle *h, const double *cos20, const double *sin20, const double *cos15,
                          const double *sin15)
@@ -163,13 +189,18 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
     cudaError_t e = fcpp_launch_layout(h, *batch, d_n_pts, d_offsets, st);
     if (e != cudaSuccess) return cuda_fail(h, e, "layout kernel");
     // the plan kernel sizes its shared-memory staging by the longest plan of the batch
-    *h->h_maxn = 0;
-    if (batch->n_cand > 0) {
-        e = cudaMemcpyAsync(h->h_maxn, h->d_maxn, sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return cuda_fail(h, e, "layout readback");
+    int maxn = batch->max_points_hint;
+    if (maxn <= 0) {
+        *h->h_maxn = 0;
+        if (batch->n_cand > 0) {
+            e = cudaMemcpyAsync(h->h_maxn, h->d_maxn, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return cuda_fail(h, e, "layout readback");
+        }
+        maxn = *h->h_maxn;
+        h->last_maxn = maxn;
     }
-    int want = (*h->h_maxn + 63) / 64 * 64;
+    int want = (maxn + 63) / 64 * 64;
     if (want < 256) want = 256;
     h->plan_ncap_hint = want;
     h->layout_valid = true;
@@ -187,6 +218,8 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
         return fail(h, FCPP_ERR_INVALID, "materialised paths need outputs.offsets from fcpp_layout");
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool prof = h->profiling;
+    if (prof) cudaEventRecord(h->ev[0], st);
     if (out->offsets) {
         if (!h->layout_valid || h->layout_ncand != batch->n_cand)
             return fail(h, FCPP_ERR_INVALID, "fcpp_layout must be called for this batch before fcpp_plan_batch");
@@ -194,13 +227,16 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
         rc = fcpp_layout(h, batch, nullptr, nullptr, stream);
         if (rc) return rc;
     }
+    if (prof) cudaEventRecord(h->ev[1], st);
     int ncap = 0;
     cudaError_t e = fcpp_launch_plan(h, *batch, *out, st, &ncap);
     if (e != cudaSuccess) return cuda_fail(h, e, "plan kernel");
+    if (prof) cudaEventRecord(h->ev[2], st);
     if (batch->do_coverage) {
         e = fcpp_launch_cover(h, *batch, *out, st);
         if (e != cudaSuccess) return cuda_fail(h, e, "coverage kernel");
     }
+    if (prof) cudaEventRecord(h->ev[3], st);
     h->layout_valid = false;  // one layout per plan call
     return FCPP_OK;
 }

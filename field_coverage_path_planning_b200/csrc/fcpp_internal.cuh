@@ -66,6 +66,9 @@ struct fcpp_handle {
     int max_smem_optin;
     int sm_count;
     bool layout_valid;
+    bool profiling;
+    cudaEvent_t ev[4];       // layout start, plan start, cover start, end
+    int last_maxn;
     int64_t layout_ncand;
     char err[512];
 };

@@ -1,0 +1,91 @@
+"""Multi-GPU: one process per GPU (torch.distributed), candidates sharded in contiguous ranges,
+NO data-path collective — the only exchange is the final per-field argmin.
+
+The reduction is exact and deterministic (ties go to the lowest global candidate index):
+    1. all_reduce(MIN) of the per-field best cost (float64);
+    2. all_reduce(MIN) of the candidate index where the local best equals the global minimum
+       (int64, "no candidate" = INT64_MAX);
+    3. the winner's 176-byte summary record is contributed by its owner and summed as int32
+       words (every other rank contributes zeros), i.e. an all-gather of one record per field.
+Works on NCCL (CUDA tensors) and gloo (CPU tensors — used by the world_size-2 CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+I64_MAX = torch.iinfo(torch.int64).max
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced shard [lo, hi) of n candidates for `rank` (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_candidates(cands: Dict[str, np.ndarray], world: int, rank: int) -> Tuple[Dict[str, np.ndarray], int]:
+    n = len(cands["field_id"])
+    lo, hi = shard_range(n, world, rank)
+    return {k: v[lo:hi] for k, v in cands.items()}, lo
+
+
+def reduce_best(best_cost: torch.Tensor, best_cand: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global per-field (cost, candidate) from the local ones.  ``best_cand`` holds GLOBAL
+    candidate indices (-1 = this rank has no valid candidate for the field).  In place."""
+    local_cost = best_cost.clone()
+    dist.all_reduce(best_cost, op=dist.ReduceOp.MIN, group=group)
+    mine = (local_cost == best_cost) & (best_cand >= 0)
+    key = torch.where(mine, best_cand, torch.full_like(best_cand, I64_MAX))
+    dist.all_reduce(key, op=dist.ReduceOp.MIN, group=group)
+    best_cand.copy_(torch.where(key == I64_MAX, torch.full_like(key, -1), key))
+    return best_cost, best_cand
+
+
+def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, lo: int, hi: int,
+                          group=None) -> torch.Tensor:
+    """[F, 176] uint8: the summary record of every field's global winner.
+    ``summary_bytes`` = this rank's records as a flat uint8 tensor ((hi-lo)*176 bytes)."""
+    rec = _lib.SUMMARY_DTYPE.itemsize
+    F = best_cand.numel()
+    own = (best_cand >= lo) & (best_cand < hi)
+    idx = torch.where(own, best_cand - lo, torch.zeros_like(best_cand))
+    rows = summary_bytes.view(-1, rec)[idx] if hi > lo else torch.zeros((F, rec), dtype=torch.uint8,
+                                                                        device=best_cand.device)
+    rows = torch.where(own[:, None], rows, torch.zeros_like(rows)).contiguous()
+    words = rows.view(torch.int32)
+    dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
+    return words.view(torch.uint8).view(F, rec)
+
+
+def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h, coverage, cost,
+                       device, want_curvature):
+    """plan_batch over all ranks of the default process group (see batch.plan_batch)."""
+    from .batch import DeviceBatch, _dev, prepare_batch, run_device_batch
+    if not dist.is_initialized():
+        raise RuntimeError("distributed=True needs torch.distributed.init_process_group (backend 'nccl')")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    fv = np.asarray(fields, dtype=np.float64).reshape(-1, 4, 2)
+    if candidates is None:
+        candidates = {"field_id": np.arange(len(fv), dtype=np.int32)}
+    n = len(candidates["field_id"])
+    local, lo = shard_candidates(candidates, world, rank)
+    hi = lo + len(local["field_id"])
+    sp = None if start_points is None else np.asarray(start_points, dtype=np.float64).reshape(n, 2)[lo:hi]
+    dev = _dev(device)
+    pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage)
+    db = DeviceBatch(pb, dev)
+    res = run_device_batch(db, outputs, want_curvature, cost, cand_base=lo)
+    bufs = res.extras["buffers"]
+    reduce_best(bufs.d_cost, bufs.d_best)
+    win = gather_winner_records(bufs.d_sum, bufs.d_best, lo, hi)
+    res.best_cost = bufs.d_cost.cpu().numpy()[:pb.n_fields]
+    res.best_cand = bufs.d_best.cpu().numpy()[:pb.n_fields]
+    res.extras["winner_summary"] = win.cpu().numpy().view(_lib.SUMMARY_DTYPE).reshape(-1)[:pb.n_fields]
+    res.extras["shard"] = (lo, hi)
+    return res

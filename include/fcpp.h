@@ -99,6 +99,9 @@ typedef struct {
     /* ---- coverage raster ---- */
     double grid_h;                 /* headland-band cell size in m (0.1 default, 0.05 in config 5) */
     int32_t do_coverage;           /* 0: skip A10/A11 */
+    int32_t max_points_hint;       /* >0: upper bound of points per plan known to the caller (e.g. from a
+                                      previous fcpp_layout of the same batch): fcpp_layout then skips its
+                                      4-byte readback + stream synchronisation and stays fully asynchronous */
 } fcpp_batch;
 
 #define FCPP_FLAG_CORNER_MASK 3
@@ -202,6 +205,15 @@ int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t fcpp_launch_count(const fcpp_handle *h);
+
+/* Longest plan (points) seen by the last synchronous fcpp_layout (feeds max_points_hint). */
+int32_t fcpp_last_max_points(const fcpp_handle *h);
+
+/* Per-kernel device times.  With profiling on, every fcpp_plan_batch brackets its kernels with
+ * CUDA events on the launching stream; fcpp_kernel_times (call after synchronising the stream)
+ * returns the milliseconds of the last call: [0] layout (+scan), [1] plan, [2] coverage. */
+int fcpp_set_profiling(fcpp_handle *h, int on);
+int fcpp_kernel_times(fcpp_handle *h, float *ms3);
 
 #ifdef __cplusplus
 }
