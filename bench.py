@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if self.nv is None:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.sm.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
                 try:
@@ -123,10 +123,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": int(statistics.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}

@@ -184,6 +184,8 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
         r.vn_rev[ci] = n;
     }
     r.corner_g = (int)(2 * R / FCPP_CORNER_GRID_H);  // mlp3:1457
+    // the reference raises at the first failure: layer 1 (mlp3:597) comes before layer 2 (mlp3:967)
+    if (status & FCPP_CAND_INSET_EMPTY) status = FCPP_CAND_INSET_EMPTY;
     if (status & (FCPP_CAND_INSET_EMPTY | FCPP_CAND_LOOP_SKIPPED | FCPP_CAND_TOO_MANY_LOOPS)) {
         // the reference raises here; no points are produced
         r.n_main = 0;
