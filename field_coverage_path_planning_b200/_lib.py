@@ -61,6 +61,7 @@ class Batch(C.Structure):
         ("grid_h", C.c_double),
         ("do_coverage", C.c_int32),
         ("max_points_hint", C.c_int32),
+        ("max_head_points_hint", C.c_int32),
     ]
 
 
@@ -89,7 +90,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
     "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_speed_verify", "fcpp_raster_window",
-    "fcpp_tour_lengths", "fcpp_launch_count", "fcpp_last_max_points", "fcpp_set_profiling", "fcpp_kernel_times",
+    "fcpp_tour_lengths", "fcpp_launch_count", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_set_profiling", "fcpp_kernel_times",
 ]
 
 _lib = None
@@ -136,6 +137,8 @@ def load():
         L.fcpp_tour_lengths.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
         L.fcpp_last_max_points.restype = i32
         L.fcpp_last_max_points.argtypes = [vp]
+        L.fcpp_last_max_head_points.restype = i32
+        L.fcpp_last_max_head_points.argtypes = [vp]
         L.fcpp_set_profiling.restype = C.c_int
         L.fcpp_set_profiling.argtypes = [vp, C.c_int]
         L.fcpp_kernel_times.restype = C.c_int

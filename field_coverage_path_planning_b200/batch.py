@@ -246,6 +246,7 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
         offsets = None
         if buffers is None:
             db.c.max_points_hint = 0
+            db.c.max_head_points_hint = 0
             total = 0
             if outputs == "paths":
                 d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
@@ -257,6 +258,7 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
                 buffers.d_off = d_off
         else:
             db.c.max_points_hint = int(getattr(db, "max_points", 0))
+            db.c.max_head_points_hint = int(getattr(db, "max_head_points", 0))
             if outputs == "paths":
                 if buffers.d_off is None:
                     raise ValueError("buffers were allocated without path storage")
@@ -271,6 +273,7 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
         h.check(L.fcpp_plan_batch(h.h, C.byref(db.c), C.byref(out), stream))
         if db.c.max_points_hint == 0:
             db.max_points = int(L.fcpp_last_max_points(h.h))
+            db.max_head_points = int(L.fcpp_last_max_head_points(h.h))
         h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
                                     0 if cost == "length" else 1, cand_base, buffers.d_cost.data_ptr(),
                                     buffers.d_best.data_ptr(), stream))

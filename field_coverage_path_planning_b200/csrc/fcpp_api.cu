@@ -111,8 +111,8 @@ int fcpp_create(int device, fcpp_handle **out)
     host_tables(t);
     cudaError_t e = cudaMalloc((void **)&h->d_trig, sizeof(TrigTables));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_trig, &t, sizeof(t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_maxn, sizeof(int));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_maxn, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_maxn, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_maxn, 2 * sizeof(int));
     if (e != cudaSuccess) {
         fcpp_destroy(h);
         return FCPP_ERR_CUDA;
@@ -140,6 +140,7 @@ const char *fcpp_last_error(const fcpp_handle *h) { return h ? h->err : "invalid
 int64_t fcpp_launch_count(const fcpp_handle *h) { return h ? h->launches : 0; }
 
 int32_t fcpp_last_max_points(const fcpp_handle *h) { return h ? h->last_maxn : 0; }
+int32_t fcpp_last_max_head_points(const fcpp_handle *h) { return h ? h->last_maxhead : 0; }
 
 int fcpp_set_profiling(fcpp_handle *h, int on)
 {
@@ -189,17 +190,20 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
     cudaError_t e = fcpp_launch_layout(h, *batch, d_n_pts, d_offsets, st);
     if (e != cudaSuccess) return cuda_fail(h, e, "layout kernel");
     // the plan kernel sizes its shared-memory staging by the longest plan of the batch
-    int maxn = batch->max_points_hint;
-    if (maxn <= 0) {
-        *h->h_maxn = 0;
+    int maxn = batch->max_points_hint, maxhead = batch->max_head_points_hint;
+    if (maxn <= 0 || maxhead <= 0) {
+        h->h_maxn[0] = h->h_maxn[1] = 0;
         if (batch->n_cand > 0) {
-            e = cudaMemcpyAsync(h->h_maxn, h->d_maxn, sizeof(int), cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(h->h_maxn, h->d_maxn, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return cuda_fail(h, e, "layout readback");
         }
-        maxn = *h->h_maxn;
+        maxn = h->h_maxn[0];
+        maxhead = h->h_maxn[1];
         h->last_maxn = maxn;
+        h->last_maxhead = maxhead;
     }
+    h->cover_pcap = maxhead;
     int want = (maxn + 63) / 64 * 64;
     if (want < 256) want = 256;
     h->plan_ncap_hint = want;

@@ -7,10 +7,18 @@
 //   A11 headland coverage rate     mlp3:1357-1371, recast as integer cell counts (north_star)
 //
 // Decision D5: all coordinates are snapped to the 1e-4 m lattice and a lattice point
-// is covered iff dist²(point, segment) < r² EXACTLY (128-bit integers).  The rasteriser is
-// span-based: for every (segment, grid row) pair one lane computes an FP64 estimate of the covered
-// x-interval and then repairs both ends with the exact integer predicate, so the result equals
-// the per-cell brute force of oracle/raster_oracle.c bit for bit while doing O(rows) work.
+// is covered iff dist²(point, segment) < r² EXACTLY (128-bit integers).
+//
+// Rasteriser (v3):
+//  * per segment ("entry") the offset vector of the capsule's tangent lines (r*n) and the slope
+//    dx/dy are computed once per plan and kept in shared memory;
+//  * work items are (entry, 32-row chunk) pairs; a prefix sum over the entries and an
+//    item -> entry table distribute them evenly over the 8 warps; a lane owns one grid row;
+//  * the capsule's left and right boundaries are piecewise (arc of end A | offset line | arc of
+//    end B): per row ONE sqrt or ONE multiply-add per side in FP64;
+//  * the FP64 boundary is certified: only when it falls within 1e-5 cell of a lattice point is
+//    that point decided by the exact integer predicate, so the result equals the per-cell brute
+//    force of oracle/raster_oracle.c bit for bit.
 #include "fcpp_internal.cuh"
 
 namespace {
@@ -19,27 +27,89 @@ constexpr int T = FCPP_COVER_THREADS;
 constexpr int NWARP = T / 32;
 constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
 constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
-constexpr int HEAD_CAP = 2048;  // headland polyline points staged on chip
-constexpr int VPOLY_CAP = 512;  // verification polyline (15-pt arc + reverse fill)
+constexpr int VPOLY_CAP = 256;  // verification polyline (15-pt arc + reverse fill), per corner
+constexpr int ICAP = 4096;      // item -> entry table
+constexpr double AMBIG = 1e-5;  // in lattice-index units (= 1e-6 m at h = 0.1 m)
 
 struct Lattice {
     int64_t X0, Y0, H;  // lattice point (i, j) = (X0 + i*H, Y0 + j*H)
     int nx, ny;
+    double X0d, Y0d, Hd, invH;
 };
 
-struct CoverSmem {
+__device__ __forceinline__ void lattice_finish(Lattice &L)
+{
+    L.X0d = (double)L.X0;
+    L.Y0d = (double)L.Y0;
+    L.Hd = (double)L.H;
+    L.invH = 1.0 / L.Hd;
+}
+
+// one raster target: a lattice, the window of its rows held in the tile, and where they sit
+struct Target {
+    Lattice L;
+    int j0, nrows;  // lattice rows [j0, j0 + nrows) are resident
+    int koff;       // tile-row index of lattice row j0
+};
+
+struct CoverFixed {
     CandRec rec;
     TrigTables tt;
-    int2 hpts[HEAD_CAP];
-    int2 vpts[VPOLY_CAP];
     uint32_t tile[TW];
     int rbase[ROWCAP], rfa[ROWCAP], rfb[ROWCAP], rma[ROWCAP], rmb[ROWCAP];
     int scan[T];
-    int nrows, total_words, err;
+    double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey  (k unused when ey == 0)
+    Target tg[4];
+    int nrows, total_words;
+    int cnt[8];
     unsigned long long acc[2];
     uint64_t bar;
 };
 
+// dynamic part, sized by the point capacity pc (>= longest polyline staged)
+struct CoverDyn {
+    int2 *pts;          // [pc]
+    double *egeo;       // [pc][3]  ox, oy, k of entry e = segment pts[e] -> pts[e+1]
+    int *estart, *eend, *epre;  // [pc] first / last resident row, exclusive item prefix
+    uint8_t *ekind;     // [pc]
+    uint16_t *item_entry;  // [ICAP]
+};
+
+__host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
+__host__ __device__ inline size_t cover_smem_bytes(int pc)
+{
+    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double) * 3 * pc) + 3 * a16(sizeof(int) * pc) +
+           a16(pc) + a16(sizeof(uint16_t) * ICAP);
+}
+__device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
+{
+    CoverDyn d;
+    size_t o = a16(sizeof(CoverFixed));
+    d.pts = (int2 *)(base + o);
+    o += a16(sizeof(int2) * pc);
+    d.egeo = (double *)(base + o);
+    o += a16(sizeof(double) * 3 * pc);
+    d.estart = (int *)(base + o);
+    o += a16(sizeof(int) * pc);
+    d.eend = (int *)(base + o);
+    o += a16(sizeof(int) * pc);
+    d.epre = (int *)(base + o);
+    o += a16(sizeof(int) * pc);
+    d.ekind = (uint8_t *)(base + o);
+    o += a16(pc);
+    d.item_entry = (uint16_t *)(base + o);
+    return d;
+}
+
+// exact floor(a / H) for |a| < 2^40, 0 < H <= 2^20 through FP64 + integer correction
+__device__ __forceinline__ int64_t floor_div_fast(int64_t a, const Lattice &L)
+{
+    int64_t q = __double2ll_rd((double)a * L.invH);
+    const int64_t rem = a - q * L.H;
+    if (rem < 0) --q;
+    if (rem >= L.H) ++q;
+    return q;
+}
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b)  // b > 0
 {
     int64_t q = a / b;
@@ -49,8 +119,8 @@ __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b)  // b > 0
 __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return -floor_div(-a, b); }
 
 // exact: dist²((px,py), segment a-b) < r2 (oracle/raster_oracle.c near_segment)
-__device__ __forceinline__ bool near_seg(int64_t px, int64_t py, int64_t ax, int64_t ay, int64_t bx, int64_t by,
-                                         int64_t r2)
+__device__ __noinline__ bool near_seg(int64_t px, int64_t py, int64_t ax, int64_t ay, int64_t bx, int64_t by,
+                                      int64_t r2)
 {
     const int64_t dx = bx - ax, dy = by - ay;
     const int64_t wx = px - ax, wy = py - ay;
@@ -69,7 +139,7 @@ __device__ __forceinline__ bool near_seg(int64_t px, int64_t py, int64_t ax, int
 }
 
 // closed containment in a convex CCW quad with integer vertices
-__device__ __forceinline__ bool in_quad(const int64_t (*q)[2], int64_t px, int64_t py)
+__device__ __noinline__ bool in_quad(const int64_t (*q)[2], int64_t px, int64_t py)
 {
     bool in = true;
 #pragma unroll
@@ -81,21 +151,34 @@ __device__ __forceinline__ bool in_quad(const int64_t (*q)[2], int64_t px, int64
     return in;
 }
 
-// inclusive lattice-index interval of row cy inside the convex quad (empty: a > b)
-__device__ void quad_row_interval(const int64_t (*q)[2], int64_t cy, const Lattice &L, int &a, int &b)
+// per-edge constants of a convex quad for the row-interval evaluation
+__device__ void quad_edges_setup(const int64_t (*q)[2], double (*e)[3], int k)
+{
+    const int k1 = (k + 1) & 3;
+    const double ex = (double)(q[k1][0] - q[k][0]), ey = (double)(q[k1][1] - q[k][1]);
+    e[k][0] = (double)q[k][0];
+    e[k][1] = (double)q[k][1];
+    e[k][2] = (ey != 0.0) ? ex / ey : 0.0;
+}
+
+// inclusive lattice-index interval [a, b] of row cy inside the CLOSED convex quad (empty: a > b).
+// FP64 boundary + exact test of a lattice point only when the boundary is within AMBIG of it.
+__device__ void quad_row_interval(const int64_t (*q)[2], const double (*e)[3], int64_t cy, const Lattice &L,
+                                  int &a, int &b)
 {
     double lo = -1e300, hi = 1e300;
     bool empty = false;
+    const double y = (double)cy;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int k1 = (k + 1) & 3;
-        const double ex = (double)(q[k1][0] - q[k][0]), ey = (double)(q[k1][1] - q[k][1]);
-        const double wy = (double)(cy - q[k][1]);
-        if (ey > 0)
-            hi = fmin(hi, (double)q[k][0] + ex * wy / ey);
-        else if (ey < 0)
-            lo = fmax(lo, (double)q[k][0] + ex * wy / ey);
-        else if (ex * wy < 0)
+        const int64_t eyi = q[k1][1] - q[k][1];
+        const double x = e[k][0] + e[k][2] * (y - e[k][1]);
+        if (eyi > 0)
+            hi = fmin(hi, x);
+        else if (eyi < 0)
+            lo = fmax(lo, x);
+        else if ((q[k1][0] - q[k][0]) * (cy - q[k][1]) < 0)
             empty = true;
     }
     if (empty || !(lo <= hi + 2.0)) {
@@ -103,76 +186,42 @@ __device__ void quad_row_interval(const int64_t (*q)[2], int64_t cy, const Latti
         b = -1;
         return;
     }
-    double fa = floor((lo - (double)L.X0) / (double)L.H) - 1.0;
-    double fb = ceil((hi - (double)L.X0) / (double)L.H) + 1.0;
-    fa = fmax(fa, 0.0);
-    fb = fmin(fb, (double)(L.nx - 1));
-    int ia = (int)fa, ib = (int)fb;
-    while (ia <= ib && !in_quad(q, L.X0 + (int64_t)ia * L.H, cy)) ++ia;
-    while (ib >= ia && !in_quad(q, L.X0 + (int64_t)ib * L.H, cy)) --ib;
-    a = ia;
-    b = ib;
+    const double tl = (lo - L.X0d) * L.invH, th = (hi - L.X0d) * L.invH;
+    double fl = ceil(tl), fh = floor(th);  // closed interval: i >= tl, i <= th
+    const double rl = rint(tl), rh = rint(th);
+    if (fabs(tl - rl) < AMBIG) fl = in_quad(q, L.X0 + (int64_t)rl * L.H, cy) ? rl : rl + 1.0;
+    if (fabs(th - rh) < AMBIG) fh = in_quad(q, L.X0 + (int64_t)rh * L.H, cy) ? rh : rh - 1.0;
+    fl = fmax(fl, 0.0);
+    fh = fmin(fh, (double)(L.nx - 1));
+    if (!(fl <= fh)) {
+        a = 0;
+        b = -1;
+        return;
+    }
+    a = (int)fl;
+    b = (int)fh;
 }
 
-// covered lattice-index interval [ia, ib] of row cy for the capsule (a-b, r), clipped to [clo, chi]
-__device__ bool span_row(int64_t ax, int64_t ay, int64_t bx, int64_t by, int64_t r, int64_t r2, int64_t cy,
-                         const Lattice &L, int clo, int chi, int &ia, int &ib)
+// Offset vector r*n (n = (dy,-dx)/len pointing to +x) and slope dx/dy of segment p->q, with the
+// ends ordered so that the lower one comes first.  kind 0: general, 1: horizontal, 2: point.
+__device__ __forceinline__ void entry_setup(int2 p, int2 q, double r, double *geo, uint8_t &kind)
 {
-    const double rd = (double)r;
-    double lo = 1e300, hi = -1e300;
-    const double wyA = (double)(cy - ay), wyB = (double)(cy - by);
-    if (fabs(wyA) < rd) {
-        const double h = sqrt(rd * rd - wyA * wyA);
-        lo = fmin(lo, (double)ax - h);
-        hi = fmax(hi, (double)ax + h);
+    if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
+        const int2 t = p;
+        p = q;
+        q = t;
     }
-    if (fabs(wyB) < rd) {
-        const double h = sqrt(rd * rd - wyB * wyB);
-        lo = fmin(lo, (double)bx - h);
-        hi = fmax(hi, (double)bx + h);
+    const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
+    if (dy == 0.0) {
+        kind = (dx == 0.0) ? 2 : 1;
+        geo[0] = geo[1] = geo[2] = 0.0;
+        return;
     }
-    const double dx = (double)(bx - ax), dy = (double)(by - ay);
-    const double dd = dx * dx + dy * dy;
-    if (dd > 0.0) {
-        const double len = sqrt(dd);
-        double clo_ = -1e300, chi_ = 1e300, tlo = -1e300, thi = 1e300;
-        bool ok = true;
-        if (dy != 0.0) {  // |(x-ax)*dy - wy*dx| < r*len
-            const double p = (wyA * dx - rd * len) / dy, q = (wyA * dx + rd * len) / dy;
-            clo_ = fmin(p, q);
-            chi_ = fmax(p, q);
-        } else {
-            ok = fabs(wyA) < rd;
-        }
-        if (dx != 0.0) {  // 0 <= (x-ax)*dx + wy*dy <= dd
-            const double p = (0.0 - wyA * dy) / dx, q = (dd - wyA * dy) / dx;
-            tlo = fmin(p, q);
-            thi = fmax(p, q);
-        } else {
-            const double tt_ = wyA * dy;
-            ok = ok && (tt_ >= 0.0) && (tt_ <= dd);
-        }
-        if (ok) {
-            const double slo = fmax(clo_, tlo), shi = fmin(chi_, thi);
-            if (slo <= shi + 2.0) {  // 2e-4 m slack: the estimate must be a superset
-                lo = fmin(lo, (double)ax + slo - 1.0);
-                hi = fmax(hi, (double)ax + shi + 1.0);
-            }
-        }
-    }
-    if (!(lo <= hi)) return false;
-    double fa = floor((lo - (double)L.X0) / (double)L.H) - 1.0;
-    double fb = ceil((hi - (double)L.X0) / (double)L.H) + 1.0;
-    fa = fmax(fa, (double)clo);
-    fb = fmin(fb, (double)chi);
-    if (!(fa <= fb)) return false;
-    int a = (int)fa, b = (int)fb;
-    while (a <= b && !near_seg(L.X0 + (int64_t)a * L.H, cy, ax, ay, bx, by, r2)) ++a;
-    if (a > b) return false;
-    while (!near_seg(L.X0 + (int64_t)b * L.H, cy, ax, ay, bx, by, r2)) --b;
-    ia = a;
-    ib = b;
-    return true;
+    kind = 0;
+    const double len = sqrt(dx * dx + dy * dy);
+    geo[0] = r * dy / len;
+    geo[1] = r * dx / len;
+    geo[2] = dx / dy;
 }
 
 __device__ __forceinline__ void or_span(uint32_t *win, int w_first, int ia, int ib)
@@ -205,25 +254,162 @@ __device__ __forceinline__ int row_words(int fa, int fb, int ma, int mb, int &nl
     return n;
 }
 
-// rasterise polyline pts[0..n) into the current tile rows [j0, j0+nrows)
-__device__ void raster_polyline(CoverSmem &s, const int2 *pts, int n, int64_t r, const Lattice &L, int j0,
-                                int nrows)
+// block-wide inclusive scan of 4 ints per thread (entries 4*tid .. 4*tid+3); returns the total
+__device__ int block_scan4(int (&v)[4], int *sh /*[T]*/)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v[1] += v[0];
+    v[2] += v[1];
+    v[3] += v[2];
+    int inc = v[3];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+        const int x = sh[w];
+        if (w < warp) woff += x;
+        total += x;
+    }
+    const int off = woff + inc - v[3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] += off;
+    return total;
+}
+
+// geometry of entries [e0, e0 + n): once per polyline
+__device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
+{
+    for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
+        uint8_t kind;
+        entry_setup(d.pts[e], d.pts[e + 1], rd, d.egeo + 3 * e, kind);
+        d.ekind[e] = kind;
+    }
+}
+
+// Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entry e = pts[e] -> pts[e+1]; entries that
+// join two different polylines must be masked by `tgt(e) < 0`) into the resident tile rows.
+template <class TgFn>
+__device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int64_t r)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double rd = (double)r;
     const int64_t r2 = r * r;
-    for (int sgm = warp; sgm + 1 < n; sgm += NWARP) {
-        const int64_t ax = pts[sgm].x, ay = pts[sgm].y, bx = pts[sgm + 1].x, by = pts[sgm + 1].y;
-        const int64_t ylo = (ay < by ? ay : by) - r, yhi = (ay > by ? ay : by) + r;
-        int64_t jlo = floor_div(ylo - L.Y0, L.H) + 1;  // cy > ylo
-        int64_t jhi = ceil_div(yhi - L.Y0, L.H) - 1;   // cy < yhi
-        if (jlo < j0) jlo = j0;
-        if (jhi > j0 + nrows - 1) jhi = j0 + nrows - 1;
-        for (int64_t j = jlo + lane; j <= jhi; j += 32) {
-            const int k = (int)(j - j0);
-            const int fa = s.rfa[k], fb = s.rfb[k], ma = s.rma[k], mb = s.rmb[k];
+    for (int eb = 0; eb < n_ent; eb += 4 * T) {  // batches of 1024 entries
+        const int nb = min(4 * T, n_ent - eb);
+        // ---- items per entry: 32-row chunks of the resident rows the capsule can touch ----
+        int cnt[4], inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int le = tid * 4 + q;
+            cnt[q] = 0;
+            if (le < nb) {
+                const int e = e0 + eb + le;
+                const int ti = tgt(e);
+                if (ti >= 0) {
+                    const int2 a = d.pts[e], b = d.pts[e + 1];
+                    const Target &t = s.tg[ti];
+                    const int64_t ylo = (int64_t)min(a.y, b.y) - r, yhi = (int64_t)max(a.y, b.y) + r;
+                    int64_t jlo = floor_div_fast(ylo - t.L.Y0, t.L) + 1;      // cy > ylo
+                    int64_t jhi = -floor_div_fast(-(yhi - t.L.Y0), t.L) - 1;  // cy < yhi
+                    if (jlo < t.j0) jlo = t.j0;
+                    if (jhi > t.j0 + t.nrows - 1) jhi = t.j0 + t.nrows - 1;
+                    if (jhi >= jlo) cnt[q] = (int)((jhi - jlo + 32) >> 5);
+                    d.estart[e] = (int)jlo;
+                    d.eend[e] = (int)jhi;
+                }
+            }
+            inc[q] = cnt[q];
+        }
+        const int total = block_scan4(inc, s.scan);
+        const bool table = total <= ICAP;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int le = tid * 4 + q;
+            if (le < nb) {
+                const int e = e0 + eb + le;
+                const int ex = inc[q] - cnt[q];
+                d.epre[e] = ex;
+                if (table)
+                    for (int c = 0; c < cnt[q]; ++c) d.item_entry[ex + c] = (uint16_t)le;
+            }
+        }
+        __syncthreads();
+        for (int item = warp; item < total; item += NWARP) {
+            int le;
+            if (table) {
+                le = d.item_entry[item];
+            } else {  // upper_bound over the exclusive prefix (uniform across the warp)
+                int lo = 0, hi = nb - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (d.epre[e0 + eb + mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                // skip entries without items that share the same prefix value
+                while (lo + 1 < nb && d.epre[e0 + eb + lo + 1] <= item) ++lo;
+                le = lo;
+            }
+            const int e = e0 + eb + le;
+            const int j = d.estart[e] + 32 * (item - d.epre[e]) + lane;
+            if (j > d.eend[e]) continue;
+            const Target &t = s.tg[tgt(e)];
+            const int k = (j - t.j0) + t.koff;
+            const int fa = s.rfa[k], fb = s.rfb[k];
             if (fa > fb) continue;
-            int ia, ib;
-            if (!span_row(ax, ay, bx, by, r, r2, L.Y0 + j * L.H, L, fa, fb, ia, ib)) continue;
+            int2 a = d.pts[e], b = d.pts[e + 1];
+            if (b.y < a.y || (b.y == a.y && b.x < a.x)) {
+                const int2 tmp = a;
+                a = b;
+                b = tmp;
+            }
+            const double ax = (double)a.x, ay = (double)a.y, bx = (double)b.x, by = (double)b.y;
+            const int64_t cy = t.L.Y0 + (int64_t)j * t.L.H;
+            const double y = (double)cy;
+            const double wa = y - ay, wb = y - by;
+            const double r2d = rd * rd;
+            double xl, xr;
+            if (d.ekind[e] == 0) {
+                const double ox = d.egeo[3 * e], oy = d.egeo[3 * e + 1], kk = d.egeo[3 * e + 2];
+                const double yL0 = ay + oy, yL1 = by + oy, yR0 = ay - oy, yR1 = by - oy;
+                if (y < yL0)
+                    xl = ax - sqrt(fmax(r2d - wa * wa, 0.0));
+                else if (y <= yL1)
+                    xl = (ax - ox) + (y - yL0) * kk;
+                else
+                    xl = bx - sqrt(fmax(r2d - wb * wb, 0.0));
+                if (y < yR0)
+                    xr = ax + sqrt(fmax(r2d - wa * wa, 0.0));
+                else if (y <= yR1)
+                    xr = (ax + ox) + (y - yR0) * kk;
+                else
+                    xr = bx + sqrt(fmax(r2d - wb * wb, 0.0));
+            } else {
+                const double h = sqrt(fmax(r2d - wa * wa, 0.0));
+                xl = ax - h;
+                xr = bx + h;
+            }
+            // lattice indices strictly inside (xl, xr); ambiguous ends decided exactly
+            const double tl = (xl - t.L.X0d) * t.L.invH, th = (xr - t.L.X0d) * t.L.invH;
+            double fl = floor(tl) + 1.0, fh = ceil(th) - 1.0;
+            const double rl = rint(tl), rh = rint(th);
+            if (fabs(tl - rl) < AMBIG)
+                fl = near_seg(t.L.X0 + (int64_t)rl * t.L.H, cy, a.x, a.y, b.x, b.y, r2) ? rl : rl + 1.0;
+            if (fabs(th - rh) < AMBIG)
+                fh = near_seg(t.L.X0 + (int64_t)rh * t.L.H, cy, a.x, a.y, b.x, b.y, r2) ? rh : rh - 1.0;
+            fl = fmax(fl, (double)fa);
+            fh = fmin(fh, (double)fb);
+            if (!(fl <= fh)) continue;
+            const int ia = (int)fl, ib = (int)fh;
+            const int ma = s.rma[k], mb = s.rmb[k];
             uint32_t *base = s.tile + s.rbase[k];
             if (ma > mb) {
                 or_span(base, fa >> 5, ia, ib);
@@ -232,26 +418,28 @@ __device__ void raster_polyline(CoverSmem &s, const int2 *pts, int n, int64_t r,
                 row_words(fa, fb, ma, mb, nl);
                 const int lh = ib < ma - 1 ? ib : ma - 1;
                 if (ia <= lh) or_span(base, fa >> 5, ia, lh);
-                const int rl = ia > mb + 1 ? ia : mb + 1;
-                if (rl <= ib) or_span(base + nl, (mb + 1) >> 5, rl, ib);
+                const int rlo = ia > mb + 1 ? ia : mb + 1;
+                if (rlo <= ib) or_span(base + nl, (mb + 1) >> 5, rlo, ib);
             }
         }
+        __syncthreads();
     }
 }
 
-__device__ __forceinline__ int block_count_tile(CoverSmem &s, int nwords)
+__device__ __forceinline__ int count_words(const uint32_t *w, int n)
 {
     int c = 0;
-    for (int w = threadIdx.x; w < nwords; w += T) c += __popc(s.tile[w]);
+    for (int i = threadIdx.x; i < n; i += T) c += __popc(w[i]);
     return c;
 }
 
-__global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
-                                                  const TrigTables *__restrict__ trig,
-                                                  fcpp_summary *__restrict__ summary)
+__global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
+                                                     const TrigTables *__restrict__ trig,
+                                                     fcpp_summary *__restrict__ summary, int pc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoverSmem &s = *reinterpret_cast<CoverSmem *>(smem_raw);
+    CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
+    const CoverDyn d = carve_dyn(smem_raw, pc);
     const int tid = threadIdx.x;
     const int64_t cand = blockIdx.x;
     fcpp_summary *sum = summary + cand;
@@ -262,8 +450,8 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
         mbar_expect_tx(&s.bar, sizeof(CandRec));
         bulk_g2s(&s.rec, recs + cand, sizeof(CandRec), &s.bar);
         s.acc[0] = s.acc[1] = 0ull;
-        s.err = 0;
     }
+    if (tid < 8) s.cnt[tid] = 0;
     for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
         ((double *)&s.tt)[k] = ((const double *)trig)[k];
     mbar_wait(&s.bar, 0);
@@ -278,6 +466,7 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
     }
     const double W = b.vehicle.working_width;
     const int64_t rq = qfix(W / 2);
+    const double rd = (double)rq;
     int grid_err = 0;
 
     // =====================================================================================
@@ -287,72 +476,110 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
         const double fl = b.field_extent[2 * r.field], fw = b.field_extent[2 * r.field + 1];
         const int g = r.corner_g;
         const int rw = (g + 31) >> 5;
-        const bool fits = (g >= 1) && (g <= ROWCAP) && (g * rw <= TW);
-        if (!fits) grid_err = 1;
+        const bool okc = (g >= 1) && (rw <= TW) && (4 * VPOLY_CAP <= pc);
+        if (!okc) grid_err = 1;
+        const int rpt = okc ? min(ROWCAP, TW / rw) : 1;   // rows per tile
+        const int group = (okc && 4 * g <= rpt) ? 4 : 1;  // corners per pass
+        // snapped polylines of the four corners: 15-pt arc + reverse fill (mlp3:1531-1554);
+        // corner ci occupies pts[ci*VPOLY_CAP ...]
+        int nv[4];
+#pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-            int before = 0, after = 0;
-            if (fits) {
-                const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;  // mlp3:1531-1536
-                const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
-                const double ox = (ci == 0 || ci == 3) ? qx : qx - 2 * r.R;  // mlp3:1461-1468
-                const double oy = (ci == 0 || ci == 1) ? qy : qy - 2 * r.R;
-                Lattice L;
-                L.X0 = qfix(ox);
-                L.Y0 = qfix(oy);
-                L.H = qfix(FCPP_CORNER_GRID_H);
-                L.nx = g;
-                L.ny = g;
-                const int nv = min(r.vn_rev[ci], VPOLY_CAP - FCPP_CORNER_POINTS);
-                for (int k = tid; k < FCPP_CORNER_POINTS + nv; k += T) {
-                    double x, y;
-                    if (k < FCPP_CORNER_POINTS) {
-                        corner_arc_pt(s.tt, qx, qy, r.R, ci, k, x, y);
-                    } else {
-                        const int m = k - FCPP_CORNER_POINTS;
-                        const double len = r.vrev[ci][4];
-                        const double tt_ = (m == r.vn_rev[ci] - 1) ? len : m * (len / (r.vn_rev[ci] - 1));
-                        x = r.vrev[ci][0] + tt_ * r.vrev[ci][2];
-                        y = r.vrev[ci][1] + tt_ * r.vrev[ci][3];
-                    }
-                    s.vpts[k] = make_int2((int)qfix(x), (int)qfix(y));
+            nv[ci] = min(r.vn_rev[ci], VPOLY_CAP - FCPP_CORNER_POINTS);
+            if (r.vn_rev[ci] > VPOLY_CAP - FCPP_CORNER_POINTS) grid_err = 1;
+            if (!okc) continue;
+            const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;  // mlp3:1531-1536
+            const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
+            for (int k = tid; k < FCPP_CORNER_POINTS + nv[ci]; k += T) {
+                double x, y;
+                if (k < FCPP_CORNER_POINTS) {
+                    corner_arc_pt(s.tt, qx, qy, r.R, ci, k, x, y);
+                } else {
+                    const int m = k - FCPP_CORNER_POINTS;
+                    const double len = r.vrev[ci][4];
+                    const double tt_ = (m == r.vn_rev[ci] - 1) ? len : m * (len / (r.vn_rev[ci] - 1));
+                    x = r.vrev[ci][0] + tt_ * r.vrev[ci][2];
+                    y = r.vrev[ci][1] + tt_ * r.vrev[ci][3];
                 }
-                for (int k = tid; k < g; k += T) {
+                d.pts[ci * VPOLY_CAP + k] = make_int2((int)qfix(x), (int)qfix(y));
+            }
+        }
+        __syncthreads();
+        if (okc) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) setup_entries(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
+        }
+        int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
+        for (int c0 = 0; c0 < 4 && okc; c0 += group) {
+            for (int j0 = 0; j0 < g; j0 += rpt) {
+                const int nrows = (group == 4) ? g : min(rpt, g - j0);
+                if (tid < group) {
+                    const int ci = c0 + tid;
+                    const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;
+                    const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
+                    const double ox = (ci == 0 || ci == 3) ? qx : qx - 2 * r.R;  // mlp3:1461-1468
+                    const double oy = (ci == 0 || ci == 1) ? qy : qy - 2 * r.R;
+                    Target &t = s.tg[tid];
+                    t.L.X0 = qfix(ox);
+                    t.L.Y0 = qfix(oy);
+                    t.L.H = qfix(FCPP_CORNER_GRID_H);
+                    t.L.nx = g;
+                    t.L.ny = g;
+                    lattice_finish(t.L);
+                    t.j0 = j0;
+                    t.nrows = nrows;
+                    t.koff = tid * nrows;
+                }
+                for (int k = tid; k < group * nrows; k += T) {
                     s.rbase[k] = k * rw;
                     s.rfa[k] = 0;
                     s.rfb[k] = g - 1;
                     s.rma[k] = 1;
                     s.rmb[k] = 0;
                 }
-                for (int w = tid; w < g * rw; w += T) s.tile[w] = 0u;
+                for (int w = tid; w < group * nrows * rw; w += T) s.tile[w] = 0u;
+                if (tid < 8) s.cnt[tid] = 0;
                 __syncthreads();
-                raster_polyline(s, s.vpts, FCPP_CORNER_POINTS, rq, L, 0, g);
-                __syncthreads();
-                int c = block_count_tile(s, g * rw);
-                // block sum via shared atomics
-                if (tid == 0) s.scan[0] = 0;
-                __syncthreads();
-                if (c) atomicAdd(&s.scan[0], c);
-                __syncthreads();
-                before = s.scan[0];
-                after = before;
-                __syncthreads();
-                if (nv > 0) {
-                    raster_polyline(s, s.vpts + FCPP_CORNER_POINTS, nv, rq, L, 0, g);
-                    __syncthreads();
-                    c = block_count_tile(s, g * rw);
-                    if (tid == 0) s.scan[0] = 0;
-                    __syncthreads();
-                    if (c) atomicAdd(&s.scan[0], c);
-                    __syncthreads();
-                    after = s.scan[0];
-                    __syncthreads();
+                // pass 1: the turn arcs (entries 0..13 of every corner of the group)
+                {
+                    auto tgt = [&](int e) {
+                        const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
+                        return (k < FCPP_CORNER_POINTS - 1) ? c - c0 : -1;
+                    };
+                    raster_entries(s, d, c0 * VPOLY_CAP, (group - 1) * VPOLY_CAP + FCPP_CORNER_POINTS - 1, tgt, rq);
                 }
-            }
-            if (tid == 0) {
-                sum->corner_before[ci] = before;
-                sum->corner_after[ci] = after;
+                for (int c = 0; c < group; ++c) {
+                    const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
+                    if (n) atomicAdd(&s.cnt[c], n);
+                }
+                __syncthreads();
+                // pass 2: the reverse fills (entries 15 .. 15+nv-2; entry 14 joins arc and fill and
+                // is NOT part of either LineString, mlp3:1471 / :1487)
+                {
+                    auto tgt = [&](int e) {
+                        const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
+                        return (k >= FCPP_CORNER_POINTS && k < FCPP_CORNER_POINTS + nv[c] - 1) ? c - c0 : -1;
+                    };
+                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq);
+                }
+                for (int c = 0; c < group; ++c) {
+                    const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
+                    if (n) atomicAdd(&s.cnt[4 + c], n);
+                }
+                __syncthreads();
+                for (int c = 0; c < group; ++c) {
+                    before[c0 + c] += s.cnt[c];
+                    after[c0 + c] += s.cnt[4 + c];
+                }
+                __syncthreads();
+                if (group == 4) break;
             }
         }
+        if (tid == 0)
+            for (int k = 0; k < 4; ++k) {
+                sum->corner_before[k] = okc ? before[k] : 0;
+                sum->corner_after[k] = okc ? after[k] : 0;
+            }
     }
 
     // =====================================================================================
@@ -374,6 +601,9 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
             bx1 = fmax(bx1, x);
             by1 = fmax(by1, y);
         }
+        __syncthreads();
+        if (tid < 4) quad_edges_setup(fq, s.qedge[0], tid);
+        if (tid >= 4 && tid < 8) quad_edges_setup(mq, s.qedge[1], tid - 4);
         Lattice L;
         L.H = qfix(b.grid_h);
         const int64_t X0 = qfix(bx0), Y0 = qfix(by0);
@@ -382,30 +612,33 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
         L.Y0 = Y0 + L.H / 2;
         L.nx = (int)nx64;
         L.ny = (int)ny64;
+        lattice_finish(L);
         const int nh = r.n_head;
-        bool ok = (nh <= HEAD_CAP) && nx64 > 0 && ny64 > 0 && nx64 < (1ll << 30) && ny64 < (1ll << 30);
+        const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 < (1ll << 30) && ny64 < (1ll << 30);
         if (!ok) grid_err = 1;
         if (ok) {
             for (int k = tid; k < nh; k += T) {
                 double x, y;
                 uint8_t c;
                 gen_point(r, s.tt, W, r.n_main + k, x, y, c);
-                s.hpts[k] = make_int2((int)qfix(x), (int)qfix(y));
+                d.pts[k] = make_int2((int)qfix(x), (int)qfix(y));
             }
+            __syncthreads();
+            setup_entries(d, 0, nh - 1, rd);
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
             while (j0 < L.ny) {
                 // --- how many rows to try: from the word count of the first row (uniform) ---
                 int a0, b0, a1, b1, nl0;
-                quad_row_interval(fq, L.Y0 + (int64_t)j0 * L.H, L, a0, b0);
-                quad_row_interval(mq, L.Y0 + (int64_t)j0 * L.H, L, a1, b1);
+                quad_row_interval(fq, s.qedge[0], L.Y0 + (int64_t)j0 * L.H, L, a0, b0);
+                quad_row_interval(mq, s.qedge[1], L.Y0 + (int64_t)j0 * L.H, L, a1, b1);
                 const int w0 = row_words(a0, b0, a1, b1, nl0);
                 int rows_try = 2 * TW / (w0 > 0 ? w0 : 1);
                 if (rows_try < 8) rows_try = 8;
                 if (rows_try > ROWCAP) rows_try = ROWCAP;
                 if (rows_try > L.ny - j0) rows_try = L.ny - j0;
                 // --- row intervals + word counts: thread t owns rows 4t .. 4t+3 ---
-                int wcnt[4], loc = 0;
+                int wcnt[4], wsum[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
@@ -413,8 +646,8 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
                     if (k < rows_try) {
                         int fa, fb, ma, mb, nl;
                         const int64_t cy = L.Y0 + (int64_t)(j0 + k) * L.H;
-                        quad_row_interval(fq, cy, L, fa, fb);
-                        quad_row_interval(mq, cy, L, ma, mb);
+                        quad_row_interval(fq, s.qedge[0], cy, L, fa, fb);
+                        quad_row_interval(mq, s.qedge[1], cy, L, ma, mb);
                         if (ma <= mb) {  // the inset lies inside the field: clamp defensively
                             if (ma < fa) ma = fa;
                             if (mb > fb) mb = fb;
@@ -425,33 +658,22 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
                         s.rmb[k] = mb;
                         wcnt[q] = row_words(fa, fb, ma, mb, nl);
                     }
-                    loc += wcnt[q];
+                    wsum[q] = wcnt[q];
                 }
-                // block exclusive scan of `loc`
-                s.scan[tid] = loc;
-                __syncthreads();
-                for (int d = 1; d < T; d <<= 1) {
-                    const int v = (tid >= d) ? s.scan[tid - d] : 0;
-                    __syncthreads();
-                    s.scan[tid] += v;
-                    __syncthreads();
-                }
-                int run = s.scan[tid] - loc;
                 if (tid == 0) {
                     s.nrows = 0;
                     s.total_words = 0;
                 }
-                __syncthreads();
+                block_scan4(wsum, s.scan);  // inclusive prefix of the row word counts (syncs inside)
                 int fit_rows = 0, fit_words = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
                     if (k < rows_try) {
-                        s.rbase[k] = run;
-                        run += wcnt[q];
-                        if (run <= TW) {
+                        s.rbase[k] = wsum[q] - wcnt[q];
+                        if (wsum[q] <= TW) {
                             fit_rows = k + 1;
-                            fit_words = run;
+                            fit_words = wsum[q];
                         }
                     }
                 }
@@ -466,7 +688,6 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
                     break;
                 }
                 for (int w = tid; w < nwords; w += T) s.tile[w] = 0u;
-                // band cells of my rows
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
@@ -475,10 +696,19 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
                         if (fa <= fb) my_total += (unsigned long long)((fb - fa + 1) - (ma <= mb ? (mb - ma + 1) : 0));
                     }
                 }
+                if (tid == 0) {
+                    Target &t = s.tg[0];
+                    t.L = L;
+                    t.j0 = j0;
+                    t.nrows = nrows;
+                    t.koff = 0;
+                }
                 __syncthreads();
-                raster_polyline(s, s.hpts, nh, rq, L, j0, nrows);
-                __syncthreads();
-                my_cov += (unsigned long long)block_count_tile(s, nwords);
+                {
+                    auto tgt = [&](int) { return 0; };
+                    raster_entries(s, d, 0, nh - 1, tgt, rq);
+                }
+                my_cov += (unsigned long long)count_words(s.tile, nwords);
                 __syncthreads();
                 j0 += nrows;
             }
@@ -494,15 +724,23 @@ __global__ void __launch_bounds__(T) cover_kernel(const fcpp_batch b, const Cand
     }
 }
 
+int cover_point_capacity(int max_head)
+{
+    int pc = max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP;
+    return (pc + 255) / 256 * 256 + 16;
+}
+
 }  // namespace
 
 cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st)
 {
     if (b.n_cand == 0) return cudaSuccess;
-    const size_t bytes = sizeof(CoverSmem);
+    int pc = cover_point_capacity(h->cover_pcap);
+    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + 16) pc -= 256;
+    const size_t bytes = cover_smem_bytes(pc);
     cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary);
+    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc);
     h->launches++;
     return cudaGetLastError();
 }
@@ -512,6 +750,8 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int WIN_PC = 1024 + 16;
+
 __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ path, int n_pts, double radius,
                                                    double ox, double oy, double hc, int g,
                                                    uint32_t *__restrict__ bits, int64_t *__restrict__ count)
@@ -519,7 +759,8 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
     // one CTA; rows are processed in tiles of the shared occupancy buffer, then merged into the
     // caller's row-major g x g bit grid (bit j*g+i)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoverSmem &s = *reinterpret_cast<CoverSmem *>(smem_raw);
+    CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
+    const CoverDyn d = carve_dyn(smem_raw, WIN_PC);
     const int tid = threadIdx.x;
     Lattice L;
     L.X0 = qfix(ox);
@@ -527,6 +768,7 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
     L.H = qfix(hc);
     L.nx = g;
     L.ny = g;
+    lattice_finish(L);
     const int64_t rq = qfix(radius);
     const int rw = (g + 31) >> 5;
     const int rows_per_tile = min(ROWCAP, TW / rw);
@@ -540,15 +782,23 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
             s.rmb[k] = 0;
         }
         for (int w = tid; w < nrows * rw; w += T) s.tile[w] = 0u;
+        if (tid == 0) {
+            Target &t = s.tg[0];
+            t.L = L;
+            t.j0 = j0;
+            t.nrows = nrows;
+            t.koff = 0;
+        }
         __syncthreads();
-        // polyline in chunks of VPOLY_CAP points (chunks overlap by one point)
-        for (int p0 = 0; p0 + 1 < n_pts; p0 += VPOLY_CAP - 1) {
-            const int np = min(VPOLY_CAP, n_pts - p0);
+        // polyline in chunks of 1024 points (chunks overlap by one point)
+        for (int p0 = 0; p0 + 1 < n_pts; p0 += 1023) {
+            const int np = min(1024, n_pts - p0);
             for (int k = tid; k < np; k += T)
-                s.vpts[k] = make_int2((int)qfix(path[2 * (p0 + k)]), (int)qfix(path[2 * (p0 + k) + 1]));
+                d.pts[k] = make_int2((int)qfix(path[2 * (p0 + k)]), (int)qfix(path[2 * (p0 + k) + 1]));
             __syncthreads();
-            raster_polyline(s, s.vpts, np, rq, L, j0, nrows);
-            __syncthreads();
+            setup_entries(d, 0, np - 1, (double)rq);
+            auto tgt = [&](int) { return 0; };
+            raster_entries(s, d, 0, np - 1, tgt, rq);
         }
         // merge into the global bit grid
         for (int c = tid; c < nrows * g; c += T) {
@@ -579,7 +829,7 @@ cudaError_t fcpp_launch_raster_window(fcpp_handle *h, const double *d_path, int3
                                       double ox, double oy, double hc, int32_t g, uint32_t *d_bits,
                                       int64_t *d_count, cudaStream_t st)
 {
-    const size_t bytes = sizeof(CoverSmem);
+    const size_t bytes = cover_smem_bytes(WIN_PC);
     cudaError_t e = cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     window_kernel<<<1, T, bytes, st>>>(d_path, n_pts, radius, ox, oy, hc, g, d_bits, d_count);

@@ -61,7 +61,7 @@ struct fcpp_handle {
     int64_t scan_tmp_cap;
     int64_t launches;
     int plan_ncap_hint;      // smem point capacity wanted by the next plan launch (0 = maximum)
-    int *d_maxn;             // device: max n_total of the last layout pass
+    int *d_maxn;             // device: [max n_total, max n_head] of the last layout pass
     int *h_maxn;             // pinned host mirror
     int max_smem_optin;
     int sm_count;
@@ -69,6 +69,8 @@ struct fcpp_handle {
     bool profiling;
     cudaEvent_t ev[4];       // layout start, plan start, cover start, end
     int last_maxn;
+    int last_maxhead;
+    int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
     int64_t layout_ncand;
     char err[512];
 };

@@ -225,10 +225,17 @@ __global__ void __launch_bounds__(128) layout_kernel(fcpp_batch b, const TrigTab
                                                      int *__restrict__ maxn)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int nt = 0;
-    if (c < b.n_cand) nt = layout_one(b, trig, recs, n_pts, c);
+    int nt = 0, nh = 0;
+    if (c < b.n_cand) {
+        nt = layout_one(b, trig, recs, n_pts, c);
+        nh = recs[c].n_head;
+    }
     const int wmax = __reduce_max_sync(0xffffffffu, nt);
-    if ((threadIdx.x & 31) == 0) atomicMax(maxn, wmax);
+    const int hmax = __reduce_max_sync(0xffffffffu, nh);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(maxn, wmax);
+        atomicMax(maxn + 1, hmax);
+    }
 }
 
 // ---- exclusive prefix sum int32 -> int64 (three small kernels; B is at most a few million) ----
@@ -327,7 +334,7 @@ cudaError_t fcpp_launch_layout(fcpp_handle *h, const fcpp_batch &b, int32_t *d_n
     }
     const int threads = 128;
     const unsigned blocks = (unsigned)((B + threads - 1) / threads);
-    cudaError_t e = cudaMemsetAsync(h->d_maxn, 0, sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(h->d_maxn, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     layout_kernel<<<blocks, threads, 0, st>>>(b, h->d_trig, h->d_rec, d_n_pts, h->d_maxn);
     h->launches++;

@@ -36,7 +36,7 @@ extern "C" {
 #define FCPP_UTURN_POINTS 20      /* mlp3:807  */
 #define FCPP_CORNER_POINTS 15     /* mlp3:1046, :1589 */
 #define FCPP_STRAIGHT_POINTS 20   /* mlp3:990  */
-#define FCPP_MAX_LOOPS 8          /* K = ceil(R/W) (mlp3:916) supported up to this */
+#define FCPP_MAX_LOOPS 16         /* K = ceil(R/W) (mlp3:916) supported up to this */
 #define FCPP_POINTS_PER_LOOP 126   /* 1 + 4*20 + 3*15, mlp3:979-1007 */
 #define FCPP_FIXED_UNIT 1e4       /* coverage lattice: 1e-4 m fixed point */
 
@@ -101,7 +101,8 @@ typedef struct {
     int32_t do_coverage;           /* 0: skip A10/A11 */
     int32_t max_points_hint;       /* >0: upper bound of points per plan known to the caller (e.g. from a
                                       previous fcpp_layout of the same batch): fcpp_layout then skips its
-                                      4-byte readback + stream synchronisation and stays fully asynchronous */
+                                      8-byte readback + stream synchronisation and stays fully asynchronous */
+    int32_t max_head_points_hint;  /* same for the headland part alone (n_head); used with max_points_hint */
 } fcpp_batch;
 
 #define FCPP_FLAG_CORNER_MASK 3
@@ -206,8 +207,10 @@ int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t fcpp_launch_count(const fcpp_handle *h);
 
-/* Longest plan (points) seen by the last synchronous fcpp_layout (feeds max_points_hint). */
+/* Longest plan / longest headland path (points) seen by the last synchronous fcpp_layout
+ * (feed max_points_hint / max_head_points_hint). */
 int32_t fcpp_last_max_points(const fcpp_handle *h);
+int32_t fcpp_last_max_head_points(const fcpp_handle *h);
 
 /* Per-kernel device times.  With profiling on, every fcpp_plan_batch brackets its kernels with
  * CUDA events on the launching stream; fcpp_kernel_times (call after synchronising the stream)
