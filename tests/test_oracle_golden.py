@@ -152,3 +152,25 @@ def test_inset_error_status():
     fs = rp.setup_field(rp.VehicleParams(3.2, 8.0), field_length=30, field_width=15)
     with pytest.raises(ValueError):
         rp.plan_complete_coverage(fs)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/multi_layer_planner_v3.py"),
+                    reason="the reference tree only exists in the build container")
+def test_oracle_vs_reference_executed_live():
+    """Execute the UNMODIFIED reference (through the Shapely stand-in) right now and compare:
+    proves the committed fixtures are what the reference produces and that the stub pipeline works."""
+    import contextlib
+    import io
+    from oracle import shapely_stub
+    m = shapely_stub.load_reference()
+    kw = dict(field_length=120, field_width=60, start_point=(110, 50), end_point=(5, 5))
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = m.TwoLayerPathPlannerV37(m.VehicleParams(3.2, 6.4, 9.0, 14.0), **kw)
+        r = p.plan_complete_coverage()
+    fs = rp.setup_field(rp.VehicleParams(3.2, 6.4, 9.0, 14.0), **kw)
+    o = rp.plan_complete_coverage(fs)
+    for layer in ("main_work", "headland"):
+        assert np.array_equal(o[layer]["path"], r[layer]["path"])          # 0 ulp
+        np.testing.assert_allclose(o[layer]["speeds"], r[layer]["speeds"], rtol=0, atol=1e-12)
+    assert np.array_equal(o["approach_path"], r["approach_path"])
+    assert np.array_equal(o["departure_path"], r["departure_path"])
