@@ -350,3 +350,25 @@ def test_config5_large_field_fine_grid(fc):
     assert int(s["cov_total"][0]) == 19097600
     o = ob.evaluate_candidate(big, rp.VehicleParams(), R=8.0, start_corner=0, grid_h=0.05)
     _summary_vs_oracle(s[0], o)
+
+
+def test_integration_md_ctypes_stub_runs(fc):
+    """The reference-side ctypes stub printed in INTEGRATION.md is executed verbatim (only the
+    library path is made absolute) and must reproduce the drop-in planner's result."""
+    import re
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    code = re.search(r"```python\n# fcpp_binding\.py.*?\n(.*?)```", md, re.S).group(1)
+    code = code.replace('"libfcpp.so"', repr(os.path.join(root, "field_coverage_path_planning_b200", "libfcpp.so")))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    verts = [(0, 0), (500, 0), (580, 200), (80, 200)]
+    ref = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_vertices=verts)
+    want = ref.plan_complete_coverage()
+    shim = types.SimpleNamespace(vehicle=fc.VehicleParams(), field_vertices=verts, field_length=ref.field_length,
+                                 field_width=ref.field_width, corner_angles=ref.corner_angles,
+                                 _calculate_rotation_angle=lambda: np.arctan2(0.0, 500.0))
+    (mp, ms), (hp, hs) = ns["plan_on_gpu"](shim, 0)
+    assert np.array_equal(mp, want["main_work"]["path"]) and np.array_equal(hp, want["headland"]["path"])
+    assert np.array_equal(ms, want["main_work"]["speeds"]) and np.array_equal(hs, want["headland"]["speeds"])
