@@ -46,8 +46,12 @@ WORKLOAD = "config2: 500x200 m field + 2 obstacles, 4096 candidates/GPU (4 start
 
 
 def global_candidates(n_gpus: int):
-    """(R, start_corner) of the whole job, candidate-major: radius-major, corner-minor."""
+    """(R, start_corner) of the whole job.  The 1024*N radii of linspace(5, 12) are enumerated
+    shard-major (shard r = radii[r::N]) so that every GPU's contiguous shard spans the whole radius
+    range — plan cost grows with R (more headland loops, larger corner windows), and radius-sorted
+    contiguous shards would leave the last rank ~25 % more work than the first."""
     radii = np.linspace(5.0, 12.0, RADII_PER_GPU * n_gpus)
+    radii = np.concatenate([radii[r::n_gpus] for r in range(n_gpus)])
     R = np.repeat(radii, len(CORNERS))
     c = np.tile(np.asarray(CORNERS, dtype=np.int32), len(radii))
     return R, c

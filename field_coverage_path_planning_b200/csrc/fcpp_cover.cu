@@ -70,16 +70,18 @@ struct CoverFixed {
 struct CoverDyn {
     int2 *pts;          // [pc]
     double *egeo;       // [pc][3]  ox, oy, k of entry e = segment pts[e] -> pts[e+1]
-    int *estart, *eend, *epre;  // [pc] first / last resident row, exclusive item prefix
+    int *estart;        // [pc] first resident row of the entry
+    int *apre;          // [1024 + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries of a batch
+    uint16_t *act;      // [1024] active entries (batch-local index)
     uint8_t *ekind;     // [pc]
-    uint16_t *item_entry;  // [ICAP]
+    uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
 };
 
 __host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 __host__ __device__ inline size_t cover_smem_bytes(int pc)
 {
-    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double) * 3 * pc) + 3 * a16(sizeof(int) * pc) +
-           a16(pc) + a16(sizeof(uint16_t) * ICAP);
+    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double) * 3 * pc) + a16(sizeof(int) * pc) +
+           a16(sizeof(int) * 1025) + a16(sizeof(uint16_t) * 1024) + a16(pc) + a16(sizeof(uint16_t) * ICAP);
 }
 __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
 {
@@ -91,13 +93,13 @@ __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
     o += a16(sizeof(double) * 3 * pc);
     d.estart = (int *)(base + o);
     o += a16(sizeof(int) * pc);
-    d.eend = (int *)(base + o);
-    o += a16(sizeof(int) * pc);
-    d.epre = (int *)(base + o);
-    o += a16(sizeof(int) * pc);
+    d.apre = (int *)(base + o);
+    o += a16(sizeof(int) * 1025);
+    d.act = (uint16_t *)(base + o);
+    o += a16(sizeof(uint16_t) * 1024);
     d.ekind = (uint8_t *)(base + o);
     o += a16(pc);
-    d.item_entry = (uint16_t *)(base + o);
+    d.item_first = (uint16_t *)(base + o);
     return d;
 }
 
@@ -295,6 +297,8 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
 
 // Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entry e = pts[e] -> pts[e+1]; entries that
 // join two different polylines must be masked by `tgt(e) < 0`) into the resident tile rows.
+// Work = all (entry, row) pairs of the resident rows, flattened: lane p of item i owns pair
+// 32*i + p, so no lane idles on short segments.
 template <class TgFn>
 __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int64_t r)
 {
@@ -303,12 +307,12 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
     const int64_t r2 = r * r;
     for (int eb = 0; eb < n_ent; eb += 4 * T) {  // batches of 1024 entries
         const int nb = min(4 * T, n_ent - eb);
-        // ---- items per entry: 32-row chunks of the resident rows the capsule can touch ----
-        int cnt[4], inc[4];
+        // ---- rows per entry (resident rows the capsule can touch); packed (active << 21 | rows) ----
+        int rows[4], inc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int le = tid * 4 + q;
-            cnt[q] = 0;
+            rows[q] = 0;
             if (le < nb) {
                 const int e = e0 + eb + le;
                 const int ti = tgt(e);
@@ -320,47 +324,49 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                     int64_t jhi = -floor_div_fast(-(yhi - t.L.Y0), t.L) - 1;  // cy < yhi
                     if (jlo < t.j0) jlo = t.j0;
                     if (jhi > t.j0 + t.nrows - 1) jhi = t.j0 + t.nrows - 1;
-                    if (jhi >= jlo) cnt[q] = (int)((jhi - jlo + 32) >> 5);
+                    if (jhi >= jlo) rows[q] = (int)(jhi - jlo + 1);
                     d.estart[e] = (int)jlo;
-                    d.eend[e] = (int)jhi;
                 }
             }
-            inc[q] = cnt[q];
+            inc[q] = rows[q] ? ((1 << 21) | rows[q]) : 0;
         }
-        const int total = block_scan4(inc, s.scan);
-        const bool table = total <= ICAP;
+        const unsigned tot = (unsigned)block_scan4(inc, s.scan);
+        const int n_act = (int)(tot >> 21), n_pairs = (int)(tot & 0x1fffffu);
+        const int n_items = (n_pairs + 31) >> 5;
+        const bool table = n_items <= ICAP;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int le = tid * 4 + q;
-            if (le < nb) {
-                const int e = e0 + eb + le;
-                const int ex = inc[q] - cnt[q];
-                d.epre[e] = ex;
+            if (rows[q]) {
+                const int a = (int)((unsigned)inc[q] >> 21) - 1;
+                const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
+                d.act[a] = (uint16_t)(tid * 4 + q);
+                d.apre[a] = first;
                 if (table)
-                    for (int c = 0; c < cnt[q]; ++c) d.item_entry[ex + c] = (uint16_t)le;
+                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)a;
             }
         }
+        if (tid == 0) d.apre[n_act] = n_pairs;
         __syncthreads();
-        for (int item = warp; item < total; item += NWARP) {
-            int le;
+        for (int item = warp; item < n_items; item += NWARP) {
+            const int p = 32 * item + lane;
+            if (p >= n_pairs) continue;
+            int ai;
             if (table) {
-                le = d.item_entry[item];
-            } else {  // upper_bound over the exclusive prefix (uniform across the warp)
-                int lo = 0, hi = nb - 1;
+                ai = d.item_first[item];
+                while (p >= d.apre[ai + 1]) ++ai;
+            } else {  // upper_bound over the pair prefix
+                int lo = 0, hi = n_act - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (d.epre[e0 + eb + mid] <= item)
+                    if (d.apre[mid] <= p)
                         lo = mid;
                     else
                         hi = mid - 1;
                 }
-                // skip entries without items that share the same prefix value
-                while (lo + 1 < nb && d.epre[e0 + eb + lo + 1] <= item) ++lo;
-                le = lo;
+                ai = lo;
             }
-            const int e = e0 + eb + le;
-            const int j = d.estart[e] + 32 * (item - d.epre[e]) + lane;
-            if (j > d.eend[e]) continue;
+            const int e = e0 + eb + d.act[ai];
+            const int j = d.estart[e] + (p - d.apre[ai]);
             const Target &t = s.tg[tgt(e)];
             const int k = (j - t.j0) + t.koff;
             const int fa = s.rfa[k], fb = s.rfb[k];
@@ -712,8 +718,15 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 __syncthreads();
                 j0 += nrows;
             }
-            atomicAdd(&s.acc[0], my_total);
-            atomicAdd(&s.acc[1], my_cov);
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) {
+                my_total += __shfl_xor_sync(0xffffffffu, my_total, dd);
+                my_cov += __shfl_xor_sync(0xffffffffu, my_cov, dd);
+            }
+            if ((tid & 31) == 0) {
+                atomicAdd(&s.acc[0], my_total);
+                atomicAdd(&s.acc[1], my_cov);
+            }
             __syncthreads();
         }
         if (tid == 0) {
