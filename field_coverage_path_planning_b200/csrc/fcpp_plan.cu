@@ -214,7 +214,7 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
 }
 
 template <bool GEN>
-__global__ void __launch_bounds__(T) plan_kernel(const PlanArgs a)
+__global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
