@@ -9,16 +9,19 @@
 // Decision D5: all coordinates are snapped to the 1e-4 m lattice and a lattice point
 // is covered iff dist²(point, segment) < r² EXACTLY (128-bit integers).
 //
-// Rasteriser (v3):
-//  * per segment ("entry") the offset vector of the capsule's tangent lines (r*n) and the slope
-//    dx/dy are computed once per plan and kept in shared memory;
-//  * work items are (entry, 32-row chunk) pairs; a prefix sum over the entries and an
-//    item -> entry table distribute them evenly over the 8 warps; a lane owns one grid row;
-//  * the capsule's left and right boundaries are piecewise (arc of end A | offset line | arc of
-//    end B): per row ONE sqrt or ONE multiply-add per side in FP64;
-//  * the FP64 boundary is certified: only when it falls within 1e-5 cell of a lattice point is
-//    that point decided by the exact integer predicate, so the result equals the per-cell brute
-//    force of oracle/raster_oracle.c bit for bit.
+// Rasteriser (v5):
+//  * polyline points are stored relative to their lattice origin (int32); per segment ("entry")
+//    the offset vector r*n of the capsule's tangent lines and the slope dx/dy are computed once
+//    per plan and kept in shared memory;
+//  * work = all (entry, grid row) pairs of the resident rows, flattened through a prefix sum:
+//    lane p of item i owns pair 32*i + p, so lanes never idle on short segments;
+//  * the capsule's left and right boundaries are piecewise (arc of the lower end | tangent line |
+//    arc of the upper end), selected branch-free; arcs use an FP32 sqrt of an exact integer;
+//  * the boundary is CERTIFIED: only when it falls within 5e-6 m of a lattice point is that point
+//    decided by the exact integer predicate, so the counts equal the per-cell brute force of
+//    oracle/raster_oracle.c bit for bit;
+//  * every grid row has up to two windows of band cells ([field_lo, main_lo) and (main_hi,
+//    field_hi]); only their words are stored, zeroed, written and counted.
 #include "fcpp_internal.cuh"
 
 namespace {
@@ -27,27 +30,13 @@ constexpr int T = FCPP_COVER_THREADS;
 constexpr int NWARP = T / 32;
 constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
 constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
-constexpr int VPOLY_CAP = 256;  // verification polyline (15-pt arc + reverse fill), per corner
-constexpr int ICAP = 4096;      // item -> entry table
-constexpr double AMBIG = 1e-5;  // in lattice-index units (= 1e-6 m at h = 0.1 m)
+constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fill), per corner
+constexpr int ICAP = 2048;      // item -> active-entry table
+constexpr int EBATCH = 4 * T;   // entries per scheduling batch
+constexpr double AMBIG_UNITS = 0.05;  // capsule boundaries: 5e-6 m certification margin
+constexpr double AMBIG_Q = 1e-5;      // quad row intervals: margin in cells
 
-struct Lattice {
-    int64_t X0, Y0, H;  // lattice point (i, j) = (X0 + i*H, Y0 + j*H)
-    int nx, ny;
-    double X0d, Y0d, Hd, invH;
-};
-
-__device__ __forceinline__ void lattice_finish(Lattice &L)
-{
-    L.X0d = (double)L.X0;
-    L.Y0d = (double)L.Y0;
-    L.Hd = (double)L.H;
-    L.invH = 1.0 / L.Hd;
-}
-
-// one raster target: a lattice, the window of its rows held in the tile, and where they sit
 struct Target {
-    Lattice L;
     int j0, nrows;  // lattice rows [j0, j0 + nrows) are resident
     int koff;       // tile-row index of lattice row j0
 };
@@ -56,9 +45,11 @@ struct CoverFixed {
     CandRec rec;
     TrigTables tt;
     uint32_t tile[TW];
-    int rbase[ROWCAP], rfa[ROWCAP], rfb[ROWCAP], rma[ROWCAP], rmb[ROWCAP];
+    int4 rwin[ROWCAP];   // per tile row: window 1 cells [x, y], window 2 cells [z, w] (empty: lo > hi)
+    int2 rbias[ROWCAP];  // per tile row: tile word index of cell i in window w = bias.w + (i >> 5)
     int scan[T];
-    double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey  (k unused when ey == 0)
+    double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey (relative coordinates)
+    int2 fq[4], mq[4];      // snapped field quad and R-inset, relative to the band lattice origin
     Target tg[4];
     int nrows, total_words;
     int cnt[8];
@@ -68,20 +59,22 @@ struct CoverFixed {
 
 // dynamic part, sized by the point capacity pc (>= longest polyline staged)
 struct CoverDyn {
-    int2 *pts;          // [pc]
-    double *egeo;       // [pc][3]  ox, oy, k of entry e = segment pts[e] -> pts[e+1]
-    int *estart;        // [pc] first resident row of the entry
-    int *apre;          // [1024 + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries of a batch
-    uint16_t *act;      // [1024] active entries (batch-local index)
-    uint8_t *ekind;     // [pc]
+    int2 *pts;        // [pc] snapped points relative to their lattice origin
+    double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len of entry e = pts[e] -> pts[e+1]; oy = +inf if dy == 0
+    double *kk;       // [pc] dx/dy
+    int *ejlo;        // [pc] first resident lattice row of the entry (per pass)
+    int *ek0;         // [pc] tile row of ejlo
+    int *apre;        // [EBATCH + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries
+    uint16_t *act;    // [EBATCH] active entries (batch-local index)
     uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
 };
 
 __host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 __host__ __device__ inline size_t cover_smem_bytes(int pc)
 {
-    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double) * 3 * pc) + a16(sizeof(int) * pc) +
-           a16(sizeof(int) * 1025) + a16(sizeof(uint16_t) * 1024) + a16(pc) + a16(sizeof(uint16_t) * ICAP);
+    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double2) * pc) + a16(sizeof(double) * pc) +
+           2 * a16(sizeof(int) * pc) + a16(sizeof(int) * (EBATCH + 1)) + a16(sizeof(uint16_t) * EBATCH) +
+           a16(sizeof(uint16_t) * ICAP);
 }
 __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
 {
@@ -89,38 +82,41 @@ __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
     size_t o = a16(sizeof(CoverFixed));
     d.pts = (int2 *)(base + o);
     o += a16(sizeof(int2) * pc);
-    d.egeo = (double *)(base + o);
-    o += a16(sizeof(double) * 3 * pc);
-    d.estart = (int *)(base + o);
+    d.og = (double2 *)(base + o);
+    o += a16(sizeof(double2) * pc);
+    d.kk = (double *)(base + o);
+    o += a16(sizeof(double) * pc);
+    d.ejlo = (int *)(base + o);
+    o += a16(sizeof(int) * pc);
+    d.ek0 = (int *)(base + o);
     o += a16(sizeof(int) * pc);
     d.apre = (int *)(base + o);
-    o += a16(sizeof(int) * 1025);
+    o += a16(sizeof(int) * (EBATCH + 1));
     d.act = (uint16_t *)(base + o);
-    o += a16(sizeof(uint16_t) * 1024);
-    d.ekind = (uint8_t *)(base + o);
-    o += a16(pc);
+    o += a16(sizeof(uint16_t) * EBATCH);
     d.item_first = (uint16_t *)(base + o);
     return d;
 }
 
-// exact floor(a / H) for |a| < 2^40, 0 < H <= 2^20 through FP64 + integer correction
-__device__ __forceinline__ int64_t floor_div_fast(int64_t a, const Lattice &L)
+// exact floor(a / H) for |a| < 2^31, 0 < H < 2^20 through FP64 + integer correction
+__device__ __forceinline__ int floor_div_i(int a, int H, double invH)
 {
-    int64_t q = __double2ll_rd((double)a * L.invH);
-    const int64_t rem = a - q * L.H;
+    int q = __double2int_rd((double)a * invH);
+    const int rem = a - q * H;
     if (rem < 0) --q;
-    if (rem >= L.H) ++q;
+    if (rem >= H) ++q;
     return q;
 }
-__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b)  // b > 0
+__device__ __forceinline__ int64_t floor_div64(int64_t a, int64_t b)  // b > 0
 {
     int64_t q = a / b;
     if ((a % b != 0) && (a < 0)) --q;
     return q;
 }
-__device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return -floor_div(-a, b); }
+__device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return -floor_div64(-a, b); }
 
-// exact: dist²((px,py), segment a-b) < r2 (oracle/raster_oracle.c near_segment)
+// exact: dist²((px,py), segment a-b) < r2 (oracle/raster_oracle.c near_segment); coordinates may be
+// relative to any common origin
 __device__ __noinline__ bool near_seg(int64_t px, int64_t py, int64_t ax, int64_t ay, int64_t bx, int64_t by,
                                       int64_t r2)
 {
@@ -141,32 +137,33 @@ __device__ __noinline__ bool near_seg(int64_t px, int64_t py, int64_t ax, int64_
 }
 
 // closed containment in a convex CCW quad with integer vertices
-__device__ __noinline__ bool in_quad(const int64_t (*q)[2], int64_t px, int64_t py)
+__device__ __noinline__ bool in_quad(const int2 *q, int px, int py)
 {
     bool in = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int k1 = (k + 1) & 3;
-        const int64_t cr = (q[k1][0] - q[k][0]) * (py - q[k][1]) - (q[k1][1] - q[k][1]) * (px - q[k][0]);
+        const int64_t cr = (int64_t)(q[k1].x - q[k].x) * (py - q[k].y) - (int64_t)(q[k1].y - q[k].y) * (px - q[k].x);
         in = in && (cr >= 0);
     }
     return in;
 }
 
 // per-edge constants of a convex quad for the row-interval evaluation
-__device__ void quad_edges_setup(const int64_t (*q)[2], double (*e)[3], int k)
+__device__ void quad_edges_setup(const int2 *q, double (*e)[3], int k)
 {
     const int k1 = (k + 1) & 3;
-    const double ex = (double)(q[k1][0] - q[k][0]), ey = (double)(q[k1][1] - q[k][1]);
-    e[k][0] = (double)q[k][0];
-    e[k][1] = (double)q[k][1];
+    const double ex = (double)(q[k1].x - q[k].x), ey = (double)(q[k1].y - q[k].y);
+    e[k][0] = (double)q[k].x;
+    e[k][1] = (double)q[k].y;
     e[k][2] = (ey != 0.0) ? ex / ey : 0.0;
 }
 
-// inclusive lattice-index interval [a, b] of row cy inside the CLOSED convex quad (empty: a > b).
-// FP64 boundary + exact test of a lattice point only when the boundary is within AMBIG of it.
-__device__ void quad_row_interval(const int64_t (*q)[2], const double (*e)[3], int64_t cy, const Lattice &L,
-                                  int &a, int &b)
+// inclusive lattice-index interval [a, b] of row cy (relative) inside the CLOSED convex quad
+// (empty: a > b).  FP64 boundary + exact test of a lattice point only when the boundary is within
+// AMBIG_Q of it.
+__device__ void quad_row_interval(const int2 *q, const double (*e)[3], int cy, int H, double invH, int nx, int &a,
+                                  int &b)
 {
     double lo = -1e300, hi = 1e300;
     bool empty = false;
@@ -174,13 +171,13 @@ __device__ void quad_row_interval(const int64_t (*q)[2], const double (*e)[3], i
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int k1 = (k + 1) & 3;
-        const int64_t eyi = q[k1][1] - q[k][1];
+        const int eyi = q[k1].y - q[k].y;
         const double x = e[k][0] + e[k][2] * (y - e[k][1]);
         if (eyi > 0)
             hi = fmin(hi, x);
         else if (eyi < 0)
             lo = fmax(lo, x);
-        else if ((q[k1][0] - q[k][0]) * (cy - q[k][1]) < 0)
+        else if ((int64_t)(q[k1].x - q[k].x) * (cy - q[k].y) < 0)
             empty = true;
     }
     if (empty || !(lo <= hi + 2.0)) {
@@ -188,72 +185,34 @@ __device__ void quad_row_interval(const int64_t (*q)[2], const double (*e)[3], i
         b = -1;
         return;
     }
-    const double tl = (lo - L.X0d) * L.invH, th = (hi - L.X0d) * L.invH;
-    double fl = ceil(tl), fh = floor(th);  // closed interval: i >= tl, i <= th
-    const double rl = rint(tl), rh = rint(th);
-    if (fabs(tl - rl) < AMBIG) fl = in_quad(q, L.X0 + (int64_t)rl * L.H, cy) ? rl : rl + 1.0;
-    if (fabs(th - rh) < AMBIG) fh = in_quad(q, L.X0 + (int64_t)rh * L.H, cy) ? rh : rh - 1.0;
-    fl = fmax(fl, 0.0);
-    fh = fmin(fh, (double)(L.nx - 1));
-    if (!(fl <= fh)) {
+    const double tl = fmin(fmax(lo * invH, -1.0e9), 1.0e9), th = fmin(fmax(hi * invH, -1.0e9), 1.0e9);
+    const int il = __double2int_ru(tl), ih = __double2int_rd(th);  // closed: i >= tl, i <= th
+    int ia = il, ib = ih;
+    const int rl = __double2int_rn(tl), rh = __double2int_rn(th);
+    if (fabs(tl - (double)rl) < AMBIG_Q) ia = in_quad(q, rl * H, cy) ? rl : rl + 1;
+    if (fabs(th - (double)rh) < AMBIG_Q) ib = in_quad(q, rh * H, cy) ? rh : rh - 1;
+    ia = max(ia, 0);
+    ib = min(ib, nx - 1);
+    if (ia > ib) {
         a = 0;
         b = -1;
         return;
     }
-    a = (int)fl;
-    b = (int)fh;
+    a = ia;
+    b = ib;
 }
 
-// Offset vector r*n (n = (dy,-dx)/len pointing to +x) and slope dx/dy of segment p->q, with the
-// ends ordered so that the lower one comes first.  kind 0: general, 1: horizontal, 2: point.
-__device__ __forceinline__ void entry_setup(int2 p, int2 q, double r, double *geo, uint8_t &kind)
-{
-    if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
-        const int2 t = p;
-        p = q;
-        q = t;
-    }
-    const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
-    if (dy == 0.0) {
-        kind = (dx == 0.0) ? 2 : 1;
-        geo[0] = geo[1] = geo[2] = 0.0;
-        return;
-    }
-    kind = 0;
-    const double len = sqrt(dx * dx + dy * dy);
-    geo[0] = r * dy / len;
-    geo[1] = r * dx / len;
-    geo[2] = dx / dy;
-}
-
-__device__ __forceinline__ void or_span(uint32_t *win, int w_first, int ia, int ib)
+__device__ __forceinline__ void or_span(uint32_t *base, int ia, int ib)
 {
     const int w0 = ia >> 5, w1 = ib >> 5;
-    for (int w = w0; w <= w1; ++w) {
-        uint32_t m = 0xffffffffu;
-        if (w == w0) m &= 0xffffffffu << (ia & 31);
-        if (w == w1) m &= 0xffffffffu >> (31 - (ib & 31));
-        atomicOr(&win[w - w_first], m);
+    const uint32_t m0 = 0xffffffffu << (ia & 31), m1 = 0xffffffffu >> (31 - (ib & 31));
+    if (w0 == w1) {
+        atomicOr(base + w0, m0 & m1);
+    } else {
+        atomicOr(base + w0, m0);
+        for (int w = w0 + 1; w < w1; ++w) atomicOr(base + w, 0xffffffffu);
+        atomicOr(base + w1, m1);
     }
-}
-
-// words a row needs: left window [fa, ma-1] + right window [mb+1, fb] (or one window when the
-// main interval is empty)
-__device__ __forceinline__ int row_words(int fa, int fb, int ma, int mb, int &nl)
-{
-    nl = 0;
-    if (fa > fb) return 0;
-    if (ma > mb) {
-        nl = (fb >> 5) - (fa >> 5) + 1;
-        return nl;
-    }
-    int n = 0;
-    if (fa <= ma - 1) {
-        nl = ((ma - 1) >> 5) - (fa >> 5) + 1;
-        n += nl;
-    }
-    if (mb + 1 <= fb) n += (fb >> 5) - ((mb + 1) >> 5) + 1;
-    return n;
 }
 
 // block-wide inclusive scan of 4 ints per thread (entries 4*tid .. 4*tid+3); returns the total
@@ -285,29 +244,42 @@ __device__ int block_scan4(int (&v)[4], int *sh /*[T]*/)
     return total;
 }
 
-// geometry of entries [e0, e0 + n): once per polyline
+// tangent offsets and slope of entries [e0, e0 + n): once per polyline
 __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
 {
     for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
-        uint8_t kind;
-        entry_setup(d.pts[e], d.pts[e + 1], rd, d.egeo + 3 * e, kind);
-        d.ekind[e] = kind;
+        int2 p = d.pts[e], q = d.pts[e + 1];
+        if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
+            const int2 t = p;
+            p = q;
+            q = t;
+        }
+        const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
+        if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
+            d.og[e] = make_double2(0.0, INFINITY);
+            d.kk[e] = 0.0;
+        } else {
+            const double len = sqrt(dx * dx + dy * dy);
+            d.og[e] = make_double2(rd * dy / len, rd * dx / len);
+            d.kk[e] = dx / dy;
+        }
     }
 }
 
 // Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entry e = pts[e] -> pts[e+1]; entries that
-// join two different polylines must be masked by `tgt(e) < 0`) into the resident tile rows.
-// Work = all (entry, row) pairs of the resident rows, flattened: lane p of item i owns pair
-// 32*i + p, so no lane idles on short segments.
+// join two different polylines are masked by `tgt(e) < 0`) into the resident tile rows of their
+// targets.  All targets of one call share the lattice pitch H.
 template <class TgFn>
-__device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int64_t r)
+__device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int r, int H,
+                               double invH)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double rd = (double)r;
-    const int64_t r2 = r * r;
-    for (int eb = 0; eb < n_ent; eb += 4 * T) {  // batches of 1024 entries
-        const int nb = min(4 * T, n_ent - eb);
-        // ---- rows per entry (resident rows the capsule can touch); packed (active << 21 | rows) ----
+    const double r2d = (double)r * (double)r;
+    const int64_t r2 = (int64_t)r * r;
+    const double amb = AMBIG_UNITS * invH;
+    for (int eb = 0; eb < n_ent; eb += EBATCH) {
+        const int nb = min(EBATCH, n_ent - eb);
+        // ---- resident rows each entry's capsule can touch; packed (active << 21 | rows) ----
         int rows[4], inc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -318,14 +290,14 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                 const int ti = tgt(e);
                 if (ti >= 0) {
                     const int2 a = d.pts[e], b = d.pts[e + 1];
-                    const Target &t = s.tg[ti];
-                    const int64_t ylo = (int64_t)min(a.y, b.y) - r, yhi = (int64_t)max(a.y, b.y) + r;
-                    int64_t jlo = floor_div_fast(ylo - t.L.Y0, t.L) + 1;      // cy > ylo
-                    int64_t jhi = -floor_div_fast(-(yhi - t.L.Y0), t.L) - 1;  // cy < yhi
-                    if (jlo < t.j0) jlo = t.j0;
-                    if (jhi > t.j0 + t.nrows - 1) jhi = t.j0 + t.nrows - 1;
-                    if (jhi >= jlo) rows[q] = (int)(jhi - jlo + 1);
-                    d.estart[e] = (int)jlo;
+                    const Target t = s.tg[ti];
+                    int jlo = floor_div_i(min(a.y, b.y) - r, H, invH) + 1;      // cy > ymin - r
+                    int jhi = -floor_div_i(-(max(a.y, b.y) + r), H, invH) - 1;  // cy < ymax + r
+                    jlo = max(jlo, t.j0);
+                    jhi = min(jhi, t.j0 + t.nrows - 1);
+                    if (jhi >= jlo) rows[q] = jhi - jlo + 1;
+                    d.ejlo[e] = jlo;
+                    d.ek0[e] = jlo - t.j0 + t.koff;
                 }
             }
             inc[q] = rows[q] ? ((1 << 21) | rows[q]) : 0;
@@ -337,12 +309,12 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (rows[q]) {
-                const int a = (int)((unsigned)inc[q] >> 21) - 1;
+                const int ai = (int)((unsigned)inc[q] >> 21) - 1;
                 const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
-                d.act[a] = (uint16_t)(tid * 4 + q);
-                d.apre[a] = first;
+                d.act[ai] = (uint16_t)(tid * 4 + q);
+                d.apre[ai] = first;
                 if (table)
-                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)a;
+                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
             }
         }
         if (tid == 0) d.apre[n_act] = n_pairs;
@@ -366,67 +338,44 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                 ai = lo;
             }
             const int e = e0 + eb + d.act[ai];
-            const int j = d.estart[e] + (p - d.apre[ai]);
-            const Target &t = s.tg[tgt(e)];
-            const int k = (j - t.j0) + t.koff;
-            const int fa = s.rfa[k], fb = s.rfb[k];
-            if (fa > fb) continue;
+            const int qrow = p - d.apre[ai];
+            const int k = d.ek0[e] + qrow;
+            const int cy = (d.ejlo[e] + qrow) * H;
             int2 a = d.pts[e], b = d.pts[e + 1];
             if (b.y < a.y || (b.y == a.y && b.x < a.x)) {
                 const int2 tmp = a;
                 a = b;
                 b = tmp;
             }
-            const double ax = (double)a.x, ay = (double)a.y, bx = (double)b.x, by = (double)b.y;
-            const int64_t cy = t.L.Y0 + (int64_t)j * t.L.H;
-            const double y = (double)cy;
-            const double wa = y - ay, wb = y - by;
-            const double r2d = rd * rd;
-            double xl, xr;
-            if (d.ekind[e] == 0) {
-                const double ox = d.egeo[3 * e], oy = d.egeo[3 * e + 1], kk = d.egeo[3 * e + 2];
-                const double yL0 = ay + oy, yL1 = by + oy, yR0 = ay - oy, yR1 = by - oy;
-                if (y < yL0)
-                    xl = ax - sqrt(fmax(r2d - wa * wa, 0.0));
-                else if (y <= yL1)
-                    xl = (ax - ox) + (y - yL0) * kk;
-                else
-                    xl = bx - sqrt(fmax(r2d - wb * wb, 0.0));
-                if (y < yR0)
-                    xr = ax + sqrt(fmax(r2d - wa * wa, 0.0));
-                else if (y <= yR1)
-                    xr = (ax + ox) + (y - yR0) * kk;
-                else
-                    xr = bx + sqrt(fmax(r2d - wb * wb, 0.0));
-            } else {
-                const double h = sqrt(fmax(r2d - wa * wa, 0.0));
-                xl = ax - h;
-                xr = bx + h;
-            }
-            // lattice indices strictly inside (xl, xr); ambiguous ends decided exactly
-            const double tl = (xl - t.L.X0d) * t.L.invH, th = (xr - t.L.X0d) * t.L.invH;
-            double fl = floor(tl) + 1.0, fh = ceil(th) - 1.0;
-            const double rl = rint(tl), rh = rint(th);
-            if (fabs(tl - rl) < AMBIG)
-                fl = near_seg(t.L.X0 + (int64_t)rl * t.L.H, cy, a.x, a.y, b.x, b.y, r2) ? rl : rl + 1.0;
-            if (fabs(th - rh) < AMBIG)
-                fh = near_seg(t.L.X0 + (int64_t)rh * t.L.H, cy, a.x, a.y, b.x, b.y, r2) ? rh : rh - 1.0;
-            fl = fmax(fl, (double)fa);
-            fh = fmin(fh, (double)fb);
-            if (!(fl <= fh)) continue;
-            const int ia = (int)fl, ib = (int)fh;
-            const int ma = s.rma[k], mb = s.rmb[k];
-            uint32_t *base = s.tile + s.rbase[k];
-            if (ma > mb) {
-                or_span(base, fa >> 5, ia, ib);
-            } else {
-                int nl;
-                row_words(fa, fb, ma, mb, nl);
-                const int lh = ib < ma - 1 ? ib : ma - 1;
-                if (ia <= lh) or_span(base, fa >> 5, ia, lh);
-                const int rlo = ia > mb + 1 ? ia : mb + 1;
-                if (rlo <= ib) or_span(base + nl, (mb + 1) >> 5, rlo, ib);
-            }
+            const double2 og = d.og[e];
+            const double kk = d.kk[e];
+            const double ax = (double)a.x, bx = (double)b.x;
+            const double wa = (double)(cy - a.y), wb = (double)(cy - b.y);
+            // half chords of the end discs: FP32 sqrt of an exact integer (|error| < 2e-3 units)
+            const double hA = (double)sqrtf((float)fmax(r2d - wa * wa, 0.0));
+            const double hB = (double)sqrtf((float)fmax(r2d - wb * wb, 0.0));
+            // left: arc A below yL0 = ay+oy | tangent line up to yL1 = by+oy | arc B;  right: -oy
+            const double xl = (wa < og.y) ? ax - hA : ((wb <= og.y) ? (ax - og.x) + (wa - og.y) * kk : bx - hB);
+            const double xr = (wa < -og.y) ? ax + hA : ((wb <= -og.y) ? (ax + og.x) + (wa + og.y) * kk : bx + hB);
+            // lattice indices strictly inside (xl, xr); certified, ambiguous ends decided exactly
+            const double tl = fmin(fmax(xl * invH, -1.0e9), 1.0e9), th = fmin(fmax(xr * invH, -1.0e9), 1.0e9);
+            const int il = __double2int_rd(tl), ih = __double2int_ru(th);
+            int ia = il + 1, ib = ih - 1;
+            const double fl = tl - (double)il, fh = (double)ih - th;
+            if (fl < amb)
+                ia = near_seg((int64_t)il * H, cy, a.x, a.y, b.x, b.y, r2) ? il : il + 1;
+            else if (fl > 1.0 - amb)
+                ia = near_seg((int64_t)(il + 1) * H, cy, a.x, a.y, b.x, b.y, r2) ? il + 1 : il + 2;
+            if (fh < amb)
+                ib = near_seg((int64_t)ih * H, cy, a.x, a.y, b.x, b.y, r2) ? ih : ih - 1;
+            else if (fh > 1.0 - amb)
+                ib = near_seg((int64_t)(ih - 1) * H, cy, a.x, a.y, b.x, b.y, r2) ? ih - 1 : ih - 2;
+            const int4 w = s.rwin[k];
+            const int2 bias = s.rbias[k];
+            const int s1 = max(ia, w.x), e1 = min(ib, w.y);
+            if (s1 <= e1) or_span(s.tile + bias.x, s1, e1);
+            const int s2 = max(ia, w.z), e2 = min(ib, w.w);
+            if (s2 <= e2) or_span(s.tile + bias.y, s2, e2);
         }
         __syncthreads();
     }
@@ -438,6 +387,8 @@ __device__ __forceinline__ int count_words(const uint32_t *w, int n)
     for (int i = threadIdx.x; i < n; i += T) c += __popc(w[i]);
     return c;
 }
+
+__device__ __forceinline__ int words_of(int lo, int hi) { return hi >= lo ? (hi >> 5) - (lo >> 5) + 1 : 0; }
 
 __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
                                                      const TrigTables *__restrict__ trig,
@@ -471,7 +422,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         return;
     }
     const double W = b.vehicle.working_width;
-    const int64_t rq = qfix(W / 2);
+    const int rq = (int)qfix(W / 2);
     const double rd = (double)rq;
     int grid_err = 0;
 
@@ -482,12 +433,14 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         const double fl = b.field_extent[2 * r.field], fw = b.field_extent[2 * r.field + 1];
         const int g = r.corner_g;
         const int rw = (g + 31) >> 5;
+        const int Hc = (int)qfix(FCPP_CORNER_GRID_H);
+        const double invHc = 1.0 / (double)Hc;
         const bool okc = (g >= 1) && (rw <= TW) && (4 * VPOLY_CAP <= pc);
         if (!okc) grid_err = 1;
-        const int rpt = okc ? min(ROWCAP, TW / rw) : 1;   // rows per tile
-        const int group = (okc && 4 * g <= rpt) ? 4 : 1;  // corners per pass
-        // snapped polylines of the four corners: 15-pt arc + reverse fill (mlp3:1531-1554);
-        // corner ci occupies pts[ci*VPOLY_CAP ...]
+        const int rpt = okc ? min(ROWCAP, TW / rw) : 1;                                 // rows per tile
+        const int group = (okc && 4 * g <= rpt) ? 4 : ((okc && 2 * g <= rpt) ? 2 : 1);  // corners per pass
+        // snapped polylines of the four corners: 15-pt arc + reverse fill (mlp3:1531-1554), relative
+        // to the corner's lattice origin (mlp3:1461-1468); corner ci occupies pts[ci*VPOLY_CAP ...]
         int nv[4];
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -496,6 +449,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             if (!okc) continue;
             const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;  // mlp3:1531-1536
             const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
+            const int64_t X0 = qfix((ci == 0 || ci == 3) ? qx : qx - 2 * r.R);
+            const int64_t Y0 = qfix((ci == 0 || ci == 1) ? qy : qy - 2 * r.R);
             for (int k = tid; k < FCPP_CORNER_POINTS + nv[ci]; k += T) {
                 double x, y;
                 if (k < FCPP_CORNER_POINTS) {
@@ -507,7 +462,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     x = r.vrev[ci][0] + tt_ * r.vrev[ci][2];
                     y = r.vrev[ci][1] + tt_ * r.vrev[ci][3];
                 }
-                d.pts[ci * VPOLY_CAP + k] = make_int2((int)qfix(x), (int)qfix(y));
+                d.pts[ci * VPOLY_CAP + k] = make_int2((int)(qfix(x) - X0), (int)(qfix(y) - Y0));
             }
         }
         __syncthreads();
@@ -518,30 +473,16 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < 4 && okc; c0 += group) {
             for (int j0 = 0; j0 < g; j0 += rpt) {
-                const int nrows = (group == 4) ? g : min(rpt, g - j0);
+                const int nrows = (group > 1) ? g : min(rpt, g - j0);
                 if (tid < group) {
-                    const int ci = c0 + tid;
-                    const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;
-                    const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
-                    const double ox = (ci == 0 || ci == 3) ? qx : qx - 2 * r.R;  // mlp3:1461-1468
-                    const double oy = (ci == 0 || ci == 1) ? qy : qy - 2 * r.R;
                     Target &t = s.tg[tid];
-                    t.L.X0 = qfix(ox);
-                    t.L.Y0 = qfix(oy);
-                    t.L.H = qfix(FCPP_CORNER_GRID_H);
-                    t.L.nx = g;
-                    t.L.ny = g;
-                    lattice_finish(t.L);
                     t.j0 = j0;
                     t.nrows = nrows;
                     t.koff = tid * nrows;
                 }
                 for (int k = tid; k < group * nrows; k += T) {
-                    s.rbase[k] = k * rw;
-                    s.rfa[k] = 0;
-                    s.rfb[k] = g - 1;
-                    s.rma[k] = 1;
-                    s.rmb[k] = 0;
+                    s.rwin[k] = make_int4(0, g - 1, 1, 0);
+                    s.rbias[k] = make_int2(k * rw, 0);
                 }
                 for (int w = tid; w < group * nrows * rw; w += T) s.tile[w] = 0u;
                 if (tid < 8) s.cnt[tid] = 0;
@@ -552,7 +493,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                         const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
                         return (k < FCPP_CORNER_POINTS - 1) ? c - c0 : -1;
                     };
-                    raster_entries(s, d, c0 * VPOLY_CAP, (group - 1) * VPOLY_CAP + FCPP_CORNER_POINTS - 1, tgt, rq);
+                    raster_entries(s, d, c0 * VPOLY_CAP, (group - 1) * VPOLY_CAP + FCPP_CORNER_POINTS - 1, tgt, rq, Hc,
+                                   invHc);
                 }
                 for (int c = 0; c < group; ++c) {
                     const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
@@ -566,7 +508,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                         const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
                         return (k >= FCPP_CORNER_POINTS && k < FCPP_CORNER_POINTS + nv[c] - 1) ? c - c0 : -1;
                     };
-                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq);
+                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq, Hc, invHc);
                 }
                 for (int c = 0; c < group; ++c) {
                     const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
@@ -578,7 +520,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     after[c0 + c] += s.cnt[4 + c];
                 }
                 __syncthreads();
-                if (group == 4) break;
+                if (group > 1) break;
             }
         }
         if (tid == 0)
@@ -592,77 +534,80 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
     // A11: headland band (lattice of cell CENTRES anchored at the field bbox minimum)
     // =====================================================================================
     {
-        int64_t fq[4][2], mq[4][2];
         double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const double x = b.field_verts[(int64_t)r.field * 8 + 2 * k];
             const double y = b.field_verts[(int64_t)r.field * 8 + 2 * k + 1];
-            fq[k][0] = qfix(x);
-            fq[k][1] = qfix(y);
-            mq[k][0] = qfix(r.main_quad[k][0]);
-            mq[k][1] = qfix(r.main_quad[k][1]);
             bx0 = fmin(bx0, x);
             by0 = fmin(by0, y);
             bx1 = fmax(bx1, x);
             by1 = fmax(by1, y);
         }
-        __syncthreads();
-        if (tid < 4) quad_edges_setup(fq, s.qedge[0], tid);
-        if (tid >= 4 && tid < 8) quad_edges_setup(mq, s.qedge[1], tid - 4);
-        Lattice L;
-        L.H = qfix(b.grid_h);
+        const int64_t H64 = qfix(b.grid_h);
         const int64_t X0 = qfix(bx0), Y0 = qfix(by0);
-        const int64_t nx64 = ceil_div(qfix(bx1) - X0, L.H), ny64 = ceil_div(qfix(by1) - Y0, L.H);
-        L.X0 = X0 + L.H / 2;
-        L.Y0 = Y0 + L.H / 2;
-        L.nx = (int)nx64;
-        L.ny = (int)ny64;
-        lattice_finish(L);
+        const int64_t nx64 = ceil_div64(qfix(bx1) - X0, H64), ny64 = ceil_div64(qfix(by1) - Y0, H64);
+        const int64_t Xc0 = X0 + H64 / 2, Yc0 = Y0 + H64 / 2;  // lattice origin: centre of cell (0, 0)
+        const int H = (int)H64, nx = (int)nx64, ny = (int)ny64;
+        const double invH = 1.0 / (double)H;
         const int nh = r.n_head;
-        const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 < (1ll << 30) && ny64 < (1ll << 30);
+        // relative coordinates must fit int32 with headroom (extent + r < 2^30 units = 107 km)
+        const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
+                        H64 < (1 << 20);
         if (!ok) grid_err = 1;
+        __syncthreads();
         if (ok) {
+            if (tid < 4) {
+                s.fq[tid] = make_int2((int)(qfix(b.field_verts[(int64_t)r.field * 8 + 2 * tid]) - Xc0),
+                                      (int)(qfix(b.field_verts[(int64_t)r.field * 8 + 2 * tid + 1]) - Yc0));
+                s.mq[tid] = make_int2((int)(qfix(r.main_quad[tid][0]) - Xc0), (int)(qfix(r.main_quad[tid][1]) - Yc0));
+            }
             for (int k = tid; k < nh; k += T) {
                 double x, y;
                 uint8_t c;
                 gen_point(r, s.tt, W, r.n_main + k, x, y, c);
-                d.pts[k] = make_int2((int)qfix(x), (int)qfix(y));
+                d.pts[k] = make_int2((int)(qfix(x) - Xc0), (int)(qfix(y) - Yc0));
             }
             __syncthreads();
+            if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], tid);
+            if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], tid - 4);
             setup_entries(d, 0, nh - 1, rd);
+            __syncthreads();
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
-            while (j0 < L.ny) {
+            while (j0 < ny) {
                 // --- how many rows to try: from the word count of the first row (uniform) ---
-                int a0, b0, a1, b1, nl0;
-                quad_row_interval(fq, s.qedge[0], L.Y0 + (int64_t)j0 * L.H, L, a0, b0);
-                quad_row_interval(mq, s.qedge[1], L.Y0 + (int64_t)j0 * L.H, L, a1, b1);
-                const int w0 = row_words(a0, b0, a1, b1, nl0);
+                int a0, b0, a1, b1;
+                quad_row_interval(s.fq, s.qedge[0], j0 * H, H, invH, nx, a0, b0);
+                quad_row_interval(s.mq, s.qedge[1], j0 * H, H, invH, nx, a1, b1);
+                int w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
                 int rows_try = 2 * TW / (w0 > 0 ? w0 : 1);
-                if (rows_try < 8) rows_try = 8;
-                if (rows_try > ROWCAP) rows_try = ROWCAP;
-                if (rows_try > L.ny - j0) rows_try = L.ny - j0;
-                // --- row intervals + word counts: thread t owns rows 4t .. 4t+3 ---
-                int wcnt[4], wsum[4];
+                rows_try = min(max(rows_try, 8), min(ROWCAP, ny - j0));
+                // --- row windows + word counts: thread t owns rows 4t .. 4t+3 ---
+                int wcnt[4], wsum[4], n1[4];
+                int4 win[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
                     wcnt[q] = 0;
+                    n1[q] = 0;
+                    win[q] = make_int4(1, 0, 1, 0);
                     if (k < rows_try) {
-                        int fa, fb, ma, mb, nl;
-                        const int64_t cy = L.Y0 + (int64_t)(j0 + k) * L.H;
-                        quad_row_interval(fq, s.qedge[0], cy, L, fa, fb);
-                        quad_row_interval(mq, s.qedge[1], cy, L, ma, mb);
-                        if (ma <= mb) {  // the inset lies inside the field: clamp defensively
-                            if (ma < fa) ma = fa;
-                            if (mb > fb) mb = fb;
+                        int fa, fb, ma, mb;
+                        const int cy = (j0 + k) * H;
+                        quad_row_interval(s.fq, s.qedge[0], cy, H, invH, nx, fa, fb);
+                        quad_row_interval(s.mq, s.qedge[1], cy, H, invH, nx, ma, mb);
+                        if (fa <= fb) {
+                            if (ma <= mb) {  // the inset lies inside the field: clamp defensively
+                                ma = max(ma, fa);
+                                mb = min(mb, fb);
+                                win[q] = make_int4(fa, ma - 1, mb + 1, fb);
+                            } else {
+                                win[q] = make_int4(fa, fb, 1, 0);
+                            }
                         }
-                        s.rfa[k] = fa;
-                        s.rfb[k] = fb;
-                        s.rma[k] = ma;
-                        s.rmb[k] = mb;
-                        wcnt[q] = row_words(fa, fb, ma, mb, nl);
+                        n1[q] = words_of(win[q].x, win[q].y);
+                        wcnt[q] = n1[q] + words_of(win[q].z, win[q].w);
                     }
                     wsum[q] = wcnt[q];
                 }
@@ -676,7 +621,9 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
                     if (k < rows_try) {
-                        s.rbase[k] = wsum[q] - wcnt[q];
+                        const int base = wsum[q] - wcnt[q];
+                        s.rwin[k] = win[q];
+                        s.rbias[k] = make_int2(base - (win[q].x >> 5), base + n1[q] - (win[q].z >> 5));
                         if (wsum[q] <= TW) {
                             fit_rows = k + 1;
                             fit_words = wsum[q];
@@ -697,14 +644,11 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = tid * 4 + q;
-                    if (k < nrows) {
-                        const int fa = s.rfa[k], fb = s.rfb[k], ma = s.rma[k], mb = s.rmb[k];
-                        if (fa <= fb) my_total += (unsigned long long)((fb - fa + 1) - (ma <= mb ? (mb - ma + 1) : 0));
-                    }
+                    if (k < nrows)
+                        my_total += (unsigned long long)(max(win[q].y - win[q].x + 1, 0) + max(win[q].w - win[q].z + 1, 0));
                 }
                 if (tid == 0) {
                     Target &t = s.tg[0];
-                    t.L = L;
                     t.j0 = j0;
                     t.nrows = nrows;
                     t.koff = 0;
@@ -712,7 +656,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 __syncthreads();
                 {
                     auto tgt = [&](int) { return 0; };
-                    raster_entries(s, d, 0, nh - 1, tgt, rq);
+                    raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH);
                 }
                 my_cov += (unsigned long long)count_words(s.tile, nwords);
                 __syncthreads();
@@ -775,43 +719,42 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
     CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
     const CoverDyn d = carve_dyn(smem_raw, WIN_PC);
     const int tid = threadIdx.x;
-    Lattice L;
-    L.X0 = qfix(ox);
-    L.Y0 = qfix(oy);
-    L.H = qfix(hc);
-    L.nx = g;
-    L.ny = g;
-    lattice_finish(L);
-    const int64_t rq = qfix(radius);
+    const int64_t X0 = qfix(ox), Y0 = qfix(oy);
+    const int H = (int)qfix(hc);
+    const double invH = 1.0 / (double)H;
+    const int rq = (int)qfix(radius);
     const int rw = (g + 31) >> 5;
     const int rows_per_tile = min(ROWCAP, TW / rw);
+    const int64_t lim = (1ll << 30);
     for (int j0 = 0; j0 < g; j0 += rows_per_tile) {
         const int nrows = min(rows_per_tile, g - j0);
         for (int k = tid; k < nrows; k += T) {
-            s.rbase[k] = k * rw;
-            s.rfa[k] = 0;
-            s.rfb[k] = g - 1;
-            s.rma[k] = 1;
-            s.rmb[k] = 0;
+            s.rwin[k] = make_int4(0, g - 1, 1, 0);
+            s.rbias[k] = make_int2(k * rw, 0);
         }
         for (int w = tid; w < nrows * rw; w += T) s.tile[w] = 0u;
         if (tid == 0) {
             Target &t = s.tg[0];
-            t.L = L;
             t.j0 = j0;
             t.nrows = nrows;
             t.koff = 0;
         }
         __syncthreads();
-        // polyline in chunks of 1024 points (chunks overlap by one point)
+        // polyline in chunks of 1024 points (chunks overlap by one point); points far outside
+        // the window are clamped (they cannot reach it, the capsule radius is tiny against 2^30)
         for (int p0 = 0; p0 + 1 < n_pts; p0 += 1023) {
             const int np = min(1024, n_pts - p0);
-            for (int k = tid; k < np; k += T)
-                d.pts[k] = make_int2((int)qfix(path[2 * (p0 + k)]), (int)qfix(path[2 * (p0 + k) + 1]));
+            for (int k = tid; k < np; k += T) {
+                int64_t x = qfix(path[2 * (p0 + k)]) - X0, y = qfix(path[2 * (p0 + k) + 1]) - Y0;
+                x = x < -lim ? -lim : (x > lim ? lim : x);
+                y = y < -lim ? -lim : (y > lim ? lim : y);
+                d.pts[k] = make_int2((int)x, (int)y);
+            }
             __syncthreads();
             setup_entries(d, 0, np - 1, (double)rq);
+            __syncthreads();
             auto tgt = [&](int) { return 0; };
-            raster_entries(s, d, 0, np - 1, tgt, rq);
+            raster_entries(s, d, 0, np - 1, tgt, rq, H, invH);
         }
         // merge into the global bit grid
         for (int c = tid; c < nrows * g; c += T) {
