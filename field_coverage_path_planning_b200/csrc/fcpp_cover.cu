@@ -358,8 +358,10 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const double xl = (wa < og.y) ? ax - hA : ((wb <= og.y) ? (ax - og.x) + (wa - og.y) * kk : bx - hB);
             const double xr = (wa < -og.y) ? ax + hA : ((wb <= -og.y) ? (ax + og.x) + (wa + og.y) * kk : bx + hB);
             // lattice indices strictly inside (xl, xr); certified, ambiguous ends decided exactly
-            const double tl = fmin(fmax(xl * invH, -1.0e9), 1.0e9), th = fmin(fmax(xr * invH, -1.0e9), 1.0e9);
-            const int il = __double2int_rd(tl), ih = __double2int_ru(th);
+            const double tl = xl * invH, th = xr * invH;
+            // (the conversions saturate; the clamps keep il+2 / ih-2 from wrapping)
+            const int il = min(max(__double2int_rd(tl), -(1 << 30)), 1 << 30);
+            const int ih = min(max(__double2int_ru(th), -(1 << 30)), 1 << 30);
             int ia = il + 1, ib = ih - 1;
             const double fl = tl - (double)il, fh = (double)ih - th;
             if (fl < amb)
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
     if (tid < 8) s.cnt[tid] = 0;
     for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
         ((double *)&s.tt)[k] = ((const double *)trig)[k];
-    mbar_wait(&s.bar, 0);
+    mbar_wait_block(&s.bar, 0);
     __syncthreads();
     const CandRec &r = s.rec;
     if (r.status != 0 || r.n_total == 0) {
@@ -576,13 +578,17 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
             while (j0 < ny) {
-                // --- how many rows to try: from the word count of the first row (uniform) ---
-                int a0, b0, a1, b1;
-                quad_row_interval(s.fq, s.qedge[0], j0 * H, H, invH, nx, a0, b0);
-                quad_row_interval(s.mq, s.qedge[1], j0 * H, H, invH, nx, a1, b1);
-                int w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
-                int rows_try = 2 * TW / (w0 > 0 ? w0 : 1);
-                rows_try = min(max(rows_try, 8), min(ROWCAP, ny - j0));
+                // --- how many rows to try: from the word count of the first row (one thread) ---
+                if (tid == 0) {
+                    int a0, b0, a1, b1;
+                    quad_row_interval(s.fq, s.qedge[0], j0 * H, H, invH, nx, a0, b0);
+                    quad_row_interval(s.mq, s.qedge[1], j0 * H, H, invH, nx, a1, b1);
+                    const int w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
+                    const int rt = 2 * TW / (w0 > 0 ? w0 : 1);
+                    s.cnt[0] = min(max(rt, 8), min(ROWCAP, ny - j0));
+                }
+                __syncthreads();
+                const int rows_try = s.cnt[0];
                 // --- row windows + word counts: thread t owns rows 4t .. 4t+3 ---
                 int wcnt[4], wsum[4], n1[4];
                 int4 win[4];

@@ -13,7 +13,7 @@
 #include "../../include/fcpp.h"
 
 #define FCPP_PLAN_THREADS 256
-#define FCPP_COVER_THREADS 256
+#define FCPP_COVER_THREADS 512
 
 // speed classes of a path point (initial speeds)
 enum : uint8_t { CLS_WORK = 0, CLS_TURN = 1, CLS_HEAD = 2, CLS_REVERSE = 3 };
@@ -105,19 +105,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
 {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
         : "memory");
+    return ok != 0;
+}
+
+// Block-wide wait for a TMA completion: ONE thread polls the mbarrier (256 spinning threads cost
+// 14 % of the plan kernel's instructions), the block barrier releases the rest, and every thread
+// then observes the completed phase itself (acquire of the async-proxy writes).
+__device__ __forceinline__ void mbar_wait_block(uint64_t *bar, uint32_t phase)
+{
+    if (threadIdx.x == 0)
+        while (!mbar_try_wait(bar, phase)) {
+        }
+    __syncthreads();
+    while (!mbar_try_wait(bar, phase)) {
+    }
 }
 
 // D1: mitred inset of a convex CCW quad (oracle/geom.py inset_convex — same operation order).

@@ -45,6 +45,7 @@ struct Smem {
     TrigTables *tt;
     double *obs_xy;    // [obs_cap_verts][2]
     int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
+    double *obs_bb;    // [obs_cap_polys][4] bbox of each obstacle grown by W/2 + 1e-6 (early reject)
     double *scratch;   // [128]
     uint64_t *bar;
 };
@@ -60,6 +61,7 @@ __host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int o
     s += align16(sizeof(TrigTables));
     s += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
     s += align16(sizeof(int32_t) * (obs_polys + 1));
+    s += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
     s += align16(sizeof(double) * 128);
     s += 16;
     return s;
@@ -85,6 +87,8 @@ __device__ inline Smem carve(unsigned char *base, int ncap, int obs_verts, int o
     o += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
     s.obs_vs = (int32_t *)(base + o);
     o += align16(sizeof(int32_t) * (obs_polys + 1));
+    s.obs_bb = (double *)(base + o);
+    o += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
     s.scratch = (double *)(base + o);
     o += align16(sizeof(double) * 128);
     s.bar = (uint64_t *)(base + o);
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
         // trig tables + polygon starts through the ordinary path meanwhile
         for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
             ((double *)s.tt)[k] = ((const double *)a.trig)[k];
-        mbar_wait(s.bar, 0);
+        mbar_wait_block(s.bar, 0);
         const CandRec &r = *s.rec;
         if (a.b.obs_poly_start) {
             const int p0 = a.b.obs_poly_start[r.field], p1 = a.b.obs_poly_start[r.field + 1];
@@ -326,6 +330,22 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
         }
         const double rr = W / 2;
         const double r2 = rr * rr;
+        // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above
+        // any rounding of the exact test) can neither be inside it nor within W/2 of an edge
+        for (int p = tid; p < n_obs_poly; p += T) {
+            double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+            for (int q = s.obs_vs[p]; q < s.obs_vs[p + 1]; ++q) {
+                x0 = fmin(x0, s.obs_xy[2 * q]);
+                x1 = fmax(x1, s.obs_xy[2 * q]);
+                y0 = fmin(y0, s.obs_xy[2 * q + 1]);
+                y1 = fmax(y1, s.obs_xy[2 * q + 1]);
+            }
+            s.obs_bb[4 * p] = x0 - rr - 1e-6;
+            s.obs_bb[4 * p + 1] = y0 - rr - 1e-6;
+            s.obs_bb[4 * p + 2] = x1 + rr + 1e-6;
+            s.obs_bb[4 * p + 3] = y1 + rr + 1e-6;
+        }
+        __syncthreads();
         double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
         for (int i = tid; i < N; i += T) {
             double x, y;
@@ -341,6 +361,8 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
             n_bviol += outb;
             bool hit = false;
             for (int p = 0; p < n_obs_poly && !hit; ++p) {
+                if (x < s.obs_bb[4 * p] || y < s.obs_bb[4 * p + 1] || x > s.obs_bb[4 * p + 2] || y > s.obs_bb[4 * p + 3])
+                    continue;
                 const int vs = s.obs_vs[p], ve = s.obs_vs[p + 1];
                 bool inside = false;
                 for (int q = vs; q < ve; ++q) {
