@@ -56,6 +56,7 @@ int ensure_workspace(fcpp_handle *h, int64_t n_cand)
     const int64_t tiles = n_cand / 4096 + 2;
     if (tiles > h->scan_tmp_cap) {
         if (h->d_scan_tmp) cudaFree(h->d_scan_tmp);
+    if (h->d_big) cudaFree(h->d_big);
         h->d_scan_tmp = nullptr;
         h->scan_tmp_cap = 0;
         cudaError_t e = cudaMalloc(&h->d_scan_tmp, (size_t)(tiles + 1024) * sizeof(int64_t));
@@ -128,6 +129,7 @@ void fcpp_destroy(fcpp_handle *h)
     if (h->d_trig) cudaFree(h->d_trig);
     if (h->d_rec) cudaFree(h->d_rec);
     if (h->d_scan_tmp) cudaFree(h->d_scan_tmp);
+    if (h->d_big) cudaFree(h->d_big);
     if (h->d_maxn) cudaFree(h->d_maxn);
     if (h->h_maxn) cudaFreeHost(h->h_maxn);
     for (int k = 0; k < 4; ++k)

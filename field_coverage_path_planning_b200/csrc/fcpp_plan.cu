@@ -36,6 +36,12 @@ struct PlanArgs {
     int ncap;          // smem capacity in points
     int obs_cap_verts; // smem capacity for obstacle vertices
     int obs_cap_polys;
+    // plans longer than the shared-memory staging go through plan_big_kernel (HBM/L2 staging)
+    int big_enabled;          // regular kernel: leave candidates with N > ncap to the big kernel
+    int big_ncap;             // big kernel: point capacity of one CTA's scratch slice
+    unsigned char *big_scratch;
+    int64_t big_stride;       // bytes per CTA slice
+    int64_t n_items;          // candidates / paths in the batch
 };
 
 struct Smem {
@@ -217,13 +223,13 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
     return v0;
 }
 
-template <bool GEN>
-__global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
+// One plan (GEN) or one caller-supplied path (!GEN).  `s` points at the staging arrays (shared
+// memory in plan_kernel, an HBM/L2 scratch slice in plan_big_kernel), `cap` is their capacity.
+template <bool GEN, bool BIG>
+__device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
+                                          const uint32_t phase)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
     const int tid = threadIdx.x;
-    const int64_t cand = blockIdx.x;
     const fcpp_vehicle &veh = GEN ? a.b.vehicle : a.veh;
     fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
 
@@ -233,10 +239,6 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
     if (GEN) {
         // stage the candidate record (and the field's obstacle vertices) with TMA bulk copies
         int f = 0, v0 = 0, nv = 0;
-        if (tid == 0) {
-            mbar_init(s.bar, 1);
-        }
-        __syncthreads();
         if (tid == 0) {
             f = a.recs[cand].field;
             uint32_t bytes = sizeof(CandRec);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
         // trig tables + polygon starts through the ordinary path meanwhile
         for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
             ((double *)s.tt)[k] = ((const double *)a.trig)[k];
-        mbar_wait_block(s.bar, 0);
+        mbar_wait_block(s.bar, phase);
         const CandRec &r = *s.rec;
         if (a.b.obs_poly_start) {
             const int p0 = a.b.obs_poly_start[r.field], p1 = a.b.obs_poly_start[r.field + 1];
@@ -276,7 +278,10 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
             sum->corner_g = r.corner_g;
         }
         int st = r.status;
-        if (N > a.ncap) st |= FCPP_CAND_TOO_LARGE;
+        if (N > cap) {
+            if (!BIG && a.big_enabled) return;  // plan_big_kernel owns this candidate
+            st |= FCPP_CAND_TOO_LARGE;
+        }
         if (st != 0 || N == 0) {
             if (sum && tid == 0) {
                 sum->status = st;
@@ -297,7 +302,8 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
         off = a.in_offsets[cand];
         N = (int)(a.in_offsets[cand + 1] - off);
         n_main = N;
-        if (N > a.ncap || N == 0) {
+        if (N > cap && !BIG && a.big_enabled) return;
+        if (N > cap || N == 0) {
             if (sum && tid == 0) {
                 sum->status = N ? FCPP_CAND_TOO_LARGE : 0;
                 sum->n_main = N;
@@ -614,10 +620,72 @@ __global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
 }
 
 template <bool GEN>
+__global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    if (threadIdx.x == 0) mbar_init(s.bar, 1);
+    __syncthreads();
+    plan_body<GEN, false>(a, s, blockIdx.x, a.ncap, 0);
+}
+
+// Plans that do not fit the shared-memory staging (N > ~9000 points, e.g. a 5 km x 3 km field):
+// a few persistent CTAs walk the batch and run the same body with x/y/u/class staged in a
+// per-CTA slice of library-owned HBM (L2-resident in practice).
+template <bool GEN>
+__global__ void __launch_bounds__(T, 3) plan_big_kernel(const PlanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s = carve(smem_raw, 0, a.obs_cap_verts, a.obs_cap_polys);
+    unsigned char *slice = a.big_scratch + (int64_t)blockIdx.x * a.big_stride;
+    const size_t arr = align16(sizeof(double) * (size_t)a.big_ncap);
+    s.X = (double *)slice;
+    s.Y = (double *)(slice + arr);
+    s.U = (double *)(slice + 2 * arr);
+    s.CLS = (uint8_t *)(slice + 3 * arr);
+    if (threadIdx.x == 0) mbar_init(s.bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int64_t c = blockIdx.x; c < a.n_items; c += gridDim.x) {
+        const int n = GEN ? a.recs[c].n_total : (int)(a.in_offsets[c + 1] - a.in_offsets[c]);
+        if (n <= a.ncap) continue;  // handled by plan_kernel
+        plan_body<GEN, true>(a, s, c, a.big_ncap, phase);
+        if (GEN) phase ^= 1u;
+        __syncthreads();
+    }
+}
+
+template <bool GEN>
 cudaError_t configure(fcpp_handle *h, size_t bytes)
 {
     if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
     return cudaFuncSetAttribute(plan_kernel<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// launch plan_big_kernel when the longest plan exceeds the shared-memory capacity
+template <bool GEN>
+cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_points, cudaStream_t st)
+{
+    const int big_ncap = (max_points + 255) / 256 * 256;
+    const int64_t stride = (int64_t)(3 * align16(sizeof(double) * (size_t)big_ncap) + align16((size_t)big_ncap));
+    int64_t ctas = n_items < 2 * h->sm_count ? n_items : 2 * h->sm_count;
+    while (ctas > 1 && ctas * stride > ((int64_t)8 << 30)) ctas /= 2;  // at most 8 GiB of scratch
+    if (ctas * stride > h->big_cap) {
+        if (h->d_big) cudaFree(h->d_big);
+        h->d_big = nullptr;
+        h->big_cap = 0;
+        cudaError_t e = cudaMalloc(&h->d_big, (size_t)(ctas * stride));
+        if (e != cudaSuccess) return e;
+        h->big_cap = ctas * stride;
+    }
+    a.big_ncap = big_ncap;
+    a.big_scratch = (unsigned char *)h->d_big;
+    a.big_stride = stride;
+    a.n_items = n_items;
+    const size_t bytes = plan_smem_bytes(0, a.obs_cap_verts, a.obs_cap_polys);
+    plan_big_kernel<GEN><<<(unsigned)ctas, T, bytes, st>>>(a);
+    h->launches++;
+    return cudaGetLastError();
 }
 
 int capacity_for(fcpp_handle *h, int obs_verts, int obs_polys, int want)
@@ -650,12 +718,17 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     a.obs_cap_polys = b.obs_poly_start ? b.max_obs_polys : 0;
     a.ncap = capacity_for(h, a.obs_cap_verts, a.obs_cap_polys, h->plan_ncap_hint);
     if (ncap_out) *ncap_out = a.ncap;
+    const bool big = h->plan_ncap_hint > a.ncap;
+    a.big_enabled = big ? 1 : 0;
+    a.n_items = b.n_cand;
     const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
     cudaError_t e = configure<true>(h, bytes);
     if (e != cudaSuccess) return e;
     plan_kernel<true><<<(unsigned)b.n_cand, T, bytes, st>>>(a);
     h->launches++;
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && big) e = launch_big<true>(h, a, b.n_cand, h->plan_ncap_hint, st);
+    return e;
 }
 
 cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, const double *d_path,
@@ -673,11 +746,17 @@ cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, co
     a.out.summary = d_summary;
     a.out.speeds_kmh = d_speeds_out;
     a.out.curvature = d_curv;
-    a.ncap = capacity_for(h, 0, 0, max_len > 0 ? (int)((max_len + 255) / 256 * 256) : 0);
+    const int want = max_len > 0 ? (int)((max_len + 255) / 256 * 256) : 0;
+    a.ncap = capacity_for(h, 0, 0, want);
+    const bool big = want > a.ncap;
+    a.big_enabled = big ? 1 : 0;
+    a.n_items = n_paths;
     const size_t bytes = plan_smem_bytes(a.ncap, 0, 0);
     cudaError_t e = configure<false>(h, bytes);
     if (e != cudaSuccess) return e;
     plan_kernel<false><<<(unsigned)n_paths, T, bytes, st>>>(a);
     h->launches++;
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && big) e = launch_big<false>(h, a, n_paths, want, st);
+    return e;
 }

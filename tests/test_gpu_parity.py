@@ -372,3 +372,40 @@ def test_integration_md_ctypes_stub_runs(fc):
     (mp, ms), (hp, hs) = ns["plan_on_gpu"](shim, 0)
     assert np.array_equal(mp, want["main_work"]["path"]) and np.array_equal(hp, want["headland"]["path"])
     assert np.array_equal(ms, want["main_work"]["speeds"]) and np.array_equal(hs, want["headland"]["speeds"])
+
+
+def test_plan_longer_than_shared_memory_staging(fc):
+    """A 5 km x 3 km field has ~20 000 points per plan — more than fits the on-chip staging; such
+    plans run through the HBM-staged variant of the same kernel.  Mixed batch (one small, one huge)."""
+    from oracle import batch as ob, ref_planner as rp
+    huge = [(0, 0), (5000, 0), (5000, 3000), (0, 3000)]
+    fields = [RECT, huge]
+    cand = fc.make_candidates(2, start_corners=[0, 2])
+    res = fc.plan_batch(fields, fc.VehicleParams(), cand, outputs="paths", grid_h=0.5)
+    assert (res.summary["status"] == 0).all()
+    assert int(res.summary["n_main"][2]) > 20000
+    for b in range(4):
+        o = ob.evaluate_candidate(fields[int(cand["field_id"][b])], rp.VehicleParams(),
+                                  start_corner=int(cand["start_corner"][b]), grid_h=0.5, keep_paths=True)
+        _summary_vs_oracle(res.summary[b], o)
+        p, s, _ = res.path(b)
+        assert np.abs(p - o["path"]).max() <= TIGHT and np.abs(s - o["speeds"]).max() <= TIGHT
+    # caller-supplied path longer than the staging (verify_curvature_constraints on 30 000 points)
+    rng = np.random.default_rng(9)
+    path = np.cumsum(rng.normal(0, 1.0, size=(30000, 2)), axis=0)
+    speeds = rng.choice([4.0, 9.0, 15.0], size=len(path))
+    pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=500, field_width=200)
+    got = pl._apply_curvature_based_speed_limit(path, speeds)
+    assert np.abs(got - rp.speed_plan(path, speeds, rp.VehicleParams())).max() <= 1e-9
+
+
+def test_edge_cases(fc):
+    """Empty batch, fields without candidates, invalid grid size."""
+    res = fc.plan_batch([RECT], fc.VehicleParams(), {"field_id": np.zeros(0, dtype=np.int32)})
+    assert len(res.summary) == 0 and int(res.best_cand[0]) == -1 and np.isinf(res.best_cost[0])
+    res = fc.plan_batch([RECT, RECT], fc.VehicleParams(), {"field_id": np.array([1], dtype=np.int32)}, outputs="paths")
+    assert int(res.best_cand[0]) == -1 and int(res.best_cand[1]) == 0 and res.offsets[-1] == 1691
+    with pytest.raises(fc.FcppError):
+        fc.plan_batch([RECT], fc.VehicleParams(), grid_h=0.0333)          # not an even multiple of 1e-4 m
+    res = fc.plan_batch([RECT], fc.VehicleParams(), coverage=False)
+    assert int(res.summary["cov_total"][0]) == 0 and int(res.summary["n_main"][0]) == 1256
