@@ -62,6 +62,9 @@ class Batch(C.Structure):
         ("do_coverage", C.c_int32),
         ("max_points_hint", C.c_int32),
         ("max_head_points_hint", C.c_int32),
+        ("turn_model", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("clothoid_share", C.c_double),
     ]
 
 

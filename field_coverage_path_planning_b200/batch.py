@@ -77,6 +77,8 @@ class PreparedBatch:
     max_obs_polys: int
     grid_h: float
     coverage: bool
+    turn_model: str = "arc"
+    clothoid_share: float = 0.5
 
     def h2d_bytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays.values()))
@@ -85,7 +87,7 @@ class PreparedBatch:
 def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str, np.ndarray]] = None,
                   obstacles: Optional[Sequence[Sequence[Sequence[Sequence[float]]]]] = None,
                   start_points: Optional[np.ndarray] = None, grid_h: float = 0.1,
-                  coverage: bool = True) -> PreparedBatch:
+                  coverage: bool = True, turn_model: str = "arc", clothoid_share: float = 0.5) -> PreparedBatch:
     """FP64 host set-up (A2).  ``fields`` [F,4,2] convex CCW quads; ``obstacles`` = per field a
     list of polygons; ``candidates`` = dict with ``field_id`` and optional ``heading`` (rad),
     ``R``, ``start_corner`` arrays of length B (default: one candidate per field with the
@@ -154,7 +156,10 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
         arrays["obs_vert_start"] = np.asarray(vert_start, dtype=np.int32)
         arrays["obs_verts"] = np.asarray(verts, dtype=np.float64).reshape(-1, 2)
         arrays["obs_moments"] = np.asarray(moms, dtype=np.float64).reshape(-1, 3)
-    return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage))
+    if turn_model not in ("arc", "clothoid"):
+        raise ValueError("turn_model must be 'arc' (the reference's sampled arcs) or 'clothoid'")
+    return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage), turn_model,
+                         float(clothoid_share))
 
 
 class DeviceBatch:
@@ -179,6 +184,8 @@ class DeviceBatch:
         b.max_obs_polys = pb.max_obs_polys
         b.grid_h = pb.grid_h
         b.do_coverage = 1 if pb.coverage else 0
+        b.turn_model = 1 if pb.turn_model == "clothoid" else 0
+        b.clothoid_share = pb.clothoid_share
         self.c = b
 
 
@@ -297,13 +304,18 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
 def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,
                obstacles=None, start_points=None, outputs: str = "summary", grid_h: float = 0.1,
                coverage: bool = True, cost: str = "length", device=None, want_curvature: bool = False,
-               distributed: bool = False) -> BatchResult:
+               distributed: bool = False, turn_model: str = "arc", clothoid_share: float = 0.5) -> BatchResult:
     """Evaluate B candidate plans.  See ``prepare_batch`` for the inputs.
 
     Returns a ``BatchResult``: per-candidate ``summary`` records (layout counts, path lengths and
     times per layer, accel/boundary/obstacle violation counts, headland and corner coverage cell
     counts, status) and the per-field argmin of ``cost`` ('length' = len_main+len_head metres,
     'time' = time_main+time_head seconds; ties to the lowest candidate index).
+
+    ``turn_model='clothoid'`` (opt-in) replaces the sampled circular arcs of the
+    U-turns and headland corners by clothoid -> arc -> clothoid turns (same sample counts) whose
+    Fresnel integrals are evaluated per sample point on the device; ``clothoid_share`` in (0, 1] is
+    the share of each turn's deflection spent on the clothoids.
 
     ``distributed=True`` (inside a torch.distributed job): the candidates are sharded over the
     ranks in contiguous ranges, each rank plans its shard on its own GPU and the per-field best
@@ -312,8 +324,9 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     if distributed:
         from . import dist
         return dist.plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h,
-                                       coverage, cost, device, want_curvature)
+                                       coverage, cost, device, want_curvature, turn_model, clothoid_share)
     dev = _dev(device)
-    pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage)
+    pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage, turn_model,
+                       clothoid_share)
     db = DeviceBatch(pb, dev)
     return run_device_batch(db, outputs, want_curvature, cost)

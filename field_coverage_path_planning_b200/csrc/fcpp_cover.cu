@@ -426,6 +426,9 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
     const double W = b.vehicle.working_width;
     const int rq = (int)qfix(W / 2);
     const double rd = (double)rq;
+    TurnModel tm;
+    tm.model = b.turn_model;
+    tm.lam = b.clothoid_share;
     int grid_err = 0;
 
     // =====================================================================================
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             for (int k = tid; k < FCPP_CORNER_POINTS + nv[ci]; k += T) {
                 double x, y;
                 if (k < FCPP_CORNER_POINTS) {
-                    corner_arc_pt(s.tt, qx, qy, r.R, ci, k, x, y);
+                    corner_arc_pt(s.tt, tm, qx, qy, r.R, ci, k, x, y);
                 } else {
                     const int m = k - FCPP_CORNER_POINTS;
                     const double len = r.vrev[ci][4];
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             for (int k = tid; k < nh; k += T) {
                 double x, y;
                 uint8_t c;
-                gen_point(r, s.tt, W, r.n_main + k, x, y, c);
+                gen_point(r, s.tt, tm, W, r.n_main + k, x, y, c);
                 d.pts[k] = make_int2((int)(qfix(x) - Xc0), (int)(qfix(y) - Yc0));
             }
             __syncthreads();

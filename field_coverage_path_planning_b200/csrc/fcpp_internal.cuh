@@ -208,10 +208,100 @@ __device__ __forceinline__ void rotate_pt(double px, double py, double ca, doubl
     oy = yn + cy;
 }
 
-// 15-point quarter arc sample j at ring corner ci (mlp3:1049-1060, :1592-1603)
-__device__ __forceinline__ void corner_arc_pt(const TrigTables &tt, double x, double y, double R, int ci, int j,
-                                              double &ox, double &oy)
+// Turn model of a batch (fcpp_batch.turn_model / clothoid_share)
+struct TurnModel {
+    int model;   // FCPP_TURN_ARC | FCPP_TURN_CLOTHOID
+    double lam;  // clothoid share of the deflection
+};
+
+// Fresnel integrals S(t) = int_0^t sin(pi u^2/2) du, C(t) = int_0^t cos(pi u^2/2) du by their power
+// series; |t| <= 1 here (a clothoid never deflects more than pi/2), 14 terms give < 4e-16.
+__device__ __forceinline__ void fresnel_sc(double t, double &S, double &C)
 {
+    const double x = 1.5707963267948966 * t * t;
+    const double x2 = x * x;
+    double tc = 1.0, ts = x, sc = 1.0, ss = x / 3.0;
+#pragma unroll
+    for (int k = 1; k < 14; ++k) {
+        tc *= -x2 / (double)((2 * k - 1) * (2 * k));
+        ts *= -x2 / (double)((2 * k) * (2 * k + 1));
+        sc += tc / (double)(4 * k + 1);
+        ss += ts / (double)(4 * k + 3);
+    }
+    C = t * sc;
+    S = t * ss;
+}
+
+// Unit-radius clothoid -> arc -> clothoid turn of total deflection phi sampled at n equal
+// arc-length steps: local coordinates of sample i (xi along the entry heading, eta to the
+// turning side).  oracle/clothoid.py cac_unit is the scipy.special.fresnel restatement.
+static __device__ __noinline__ void cac_unit(double phi, int n, int i, double lam, double &xi, double &eta)
+{
+    const double alpha = lam * phi / 2, Lc = 2 * alpha, La = phi - 2 * alpha, Lt = 2 * Lc + La;
+    const double s = (i == n - 1) ? Lt : i * (Lt / (n - 1));
+    if (!(Lc > 0.0)) {
+        double sn, cs;
+        sincos(s, &sn, &cs);
+        xi = sn;
+        eta = 1 - cs;
+        return;
+    }
+    const double a = sqrt(3.141592653589793 * Lc);
+    if (s <= Lc) {
+        double S, C;
+        fresnel_sc(s / a, S, C);
+        xi = a * C;
+        eta = a * S;
+        return;
+    }
+    double S1, C1, sa, ca;
+    fresnel_sc(Lc / a, S1, C1);
+    sincos(alpha, &sa, &ca);
+    const double p1x = a * C1, p1y = a * S1;
+    if (s <= Lc + La) {
+        double sf, cf;
+        sincos(alpha + (s - Lc), &sf, &cf);
+        xi = p1x - sa + sf;
+        eta = p1y + ca - cf;
+        return;
+    }
+    double s2, c2, sp, cp;
+    sincos(alpha + La, &s2, &c2);
+    sincos(phi, &sp, &cp);
+    const double p2x = p1x - sa + s2, p2y = p1y + ca - c2;
+    const double cb = -cp, sb = -sp;  // rotation by phi + pi
+    const double m1x = a * C1, m1y = -a * S1;
+    const double ex = p2x - (cb * m1x - sb * m1y), ey = p2y - (sb * m1x + cb * m1y);
+    double S, C;
+    fresnel_sc((Lt - s) / a, S, C);
+    const double mx = a * C, my = -a * S;
+    xi = ex + (cb * mx - sb * my);
+    eta = ey + (sb * mx + cb * my);
+}
+
+// 15-point quarter turn sample j at ring corner ci (mlp3:1049-1060, :1592-1603)
+__device__ __forceinline__ void corner_arc_pt(const TrigTables &tt, const TurnModel &tm, double x, double y, double R,
+                                              int ci, int j, double &ox, double &oy)
+{
+    if (tm.model == FCPP_TURN_CLOTHOID) {
+        // same start pose and (clockwise) turning sense as the reference's arc, clothoid-arc-clothoid
+        double xi, eta;
+        cac_unit(1.5707963267948966, FCPP_CORNER_POINTS, j, tm.lam, xi, eta);
+        if (ci == 0) {
+            ox = x + R * eta;
+            oy = y + R * xi;
+        } else if (ci == 1) {
+            ox = x - R * xi;
+            oy = y + R * eta;
+        } else if (ci == 2) {
+            ox = x - R * eta;
+            oy = y - R * xi;
+        } else {
+            ox = x + R * xi;
+            oy = y - R * eta;
+        }
+        return;
+    }
     const double c = tt.cos15[j], s = tt.sin15[j];
     if (ci == 0) {
         ox = x + R * (1 - c);
@@ -234,8 +324,8 @@ __device__ __forceinline__ int64_t qfix(double x) { return __double2ll_rn(x * FC
 // ---------------------------------------------------------------------------------------------
 // point generation: index -> (x, y, speed class)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, double W, int i, double &x,
-                                          double &y, uint8_t &cls)
+__device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W, int i,
+                                          double &x, double &y, uint8_t &cls)
 {
     if (i < r.n_main) {
         // mlp3:744-780: visit index idx, pass index pi, 2 endpoints + 20 arc samples per pass
@@ -253,9 +343,20 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
             cls = CLS_WORK;
         } else {
             const int a = j - 2;
-            const bool turn_right = !go_left;  // mlp3:776
-            px = turn_right ? (r.max_x - r.R * tt.cos20[a]) : (r.min_x + r.R * tt.cos20[a]);  // mlp3:815, :822
-            py = yy + r.R * tt.sin20[a];                                                       // mlp3:816, :823
+            if (tm.model == FCPP_TURN_CLOTHOID) {
+                // clothoid-arc-clothoid U-turn leaving the swath end tangentially towards the next swath
+                double xi, eta;
+                cac_unit(3.141592653589793, FCPP_UTURN_POINTS, a, tm.lam, xi, eta);
+                const double xe = go_left ? r.min_x + r.R : r.max_x - r.R;
+                const double dir_x = go_left ? -1.0 : 1.0;
+                const double dir_y = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? -1.0 : 1.0;
+                px = xe + dir_x * (r.R * xi);
+                py = yy + dir_y * (r.R * eta);
+            } else {
+                const bool turn_right = !go_left;  // mlp3:776
+                px = turn_right ? (r.max_x - r.R * tt.cos20[a]) : (r.min_x + r.R * tt.cos20[a]);  // mlp3:815, :822
+                py = yy + r.R * tt.sin20[a];                                                       // mlp3:816, :823
+            }
             cls = CLS_TURN;
         }
         if (r.flags & FCPP_FLAG_ROTATED)
@@ -307,7 +408,7 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
         m -= FCPP_STRAIGHT_POINTS;
         if (t < 3) {
             if (m < FCPP_CORNER_POINTS) {
-                corner_arc_pt(tt, r.corners[k][ni][0], r.corners[k][ni][1], r.R, ni, m, x, y);
+                corner_arc_pt(tt, tm, r.corners[k][ni][0], r.corners[k][ni][1], r.R, ni, m, x, y);
                 cls = CLS_TURN;
                 return;
             }

@@ -33,12 +33,12 @@ __device__ double distance_to_boundary(double x, double y, double dx, double dy,
 }
 
 // mlp3:1154-1218: chord direction of the last two arc samples, length, sample count
-__device__ int reverse_fill(const TrigTables &tt, double cx, double cy, int ci, double R, double fl, double fw,
-                            double *rev /*[5]*/)
+__device__ int reverse_fill(const TrigTables &tt, const TurnModel &tm, double cx, double cy, int ci, double R,
+                            double fl, double fw, double *rev /*[5]*/)
 {
     double ex, ey, sx, sy;
-    corner_arc_pt(tt, cx, cy, R, ci, FCPP_CORNER_POINTS - 1, ex, ey);
-    corner_arc_pt(tt, cx, cy, R, ci, FCPP_CORNER_POINTS - 2, sx, sy);
+    corner_arc_pt(tt, tm, cx, cy, R, ci, FCPP_CORNER_POINTS - 1, ex, ey);
+    corner_arc_pt(tt, tm, cx, cy, R, ci, FCPP_CORNER_POINTS - 2, sx, sy);
     const double tx = ex - sx, ty = ey - sy;
     const double nrm = sqrt(tx * tx + ty * ty);
     double dx, dy;
@@ -64,6 +64,9 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
                           int32_t *__restrict__ n_pts, int64_t c)
 {
     const TrigTables &tt = *trig;
+    TurnModel tm;
+    tm.model = b.turn_model;
+    tm.lam = b.clothoid_share;
     CandRec &r = recs[c];
     const int f = b.cand_field[c];
     const double R = b.cand_R[c];
@@ -162,7 +165,7 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
         const int ni = (sc + t + 1) & 3;
         int n = 0;
         if (K > 0 && gate && ((fflags >> ni) & 1))  // mlp3:1043, :1070
-            n = reverse_fill(tt, r.corners[0][ni][0], r.corners[0][ni][1], ni, R, fl, fw, r.rev[t]);
+            n = reverse_fill(tt, tm, r.corners[0][ni][0], r.corners[0][ni][1], ni, R, fl, fw, r.rev[t]);
         else {
 #pragma unroll
             for (int q = 0; q < 5; ++q) r.rev[t][q] = 0.0;
@@ -176,7 +179,7 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
         const double qy = (ci == 0 || ci == 1) ? R : fw - R;
         int n = 0;
         if (gate)
-            n = reverse_fill(tt, qx, qy, ci, R, fl, fw, r.vrev[ci]);
+            n = reverse_fill(tt, tm, qx, qy, ci, R, fl, fw, r.vrev[ci]);
         else {
 #pragma unroll
             for (int q = 0; q < 5; ++q) r.vrev[ci][q] = 0.0;

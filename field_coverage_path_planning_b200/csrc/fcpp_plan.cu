@@ -336,6 +336,9 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
         }
         const double rr = W / 2;
         const double r2 = rr * rr;
+        TurnModel tm;
+        tm.model = a.b.turn_model;
+        tm.lam = a.b.clothoid_share;
         // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above
         // any rounding of the exact test) can neither be inside it nor within W/2 of an edge
         for (int p = tid; p < n_obs_poly; p += T) {
@@ -356,7 +359,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
         for (int i = tid; i < N; i += T) {
             double x, y;
             uint8_t c;
-            gen_point(r, *s.tt, W, i, x, y, c);
+            gen_point(r, *s.tt, tm, W, i, x, y, c);
             s.X[i] = x;
             s.Y[i] = y;
             s.CLS[i] = c;

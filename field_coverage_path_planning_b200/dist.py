@@ -64,7 +64,7 @@ def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, 
 
 
 def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h, coverage, cost,
-                       device, want_curvature):
+                       device, want_curvature, turn_model="arc", clothoid_share=0.5):
     """plan_batch over all ranks of the default process group (see batch.plan_batch)."""
     from .batch import DeviceBatch, _dev, prepare_batch, run_device_batch
     if not dist.is_initialized():
@@ -78,7 +78,7 @@ def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, out
     hi = lo + len(local["field_id"])
     sp = None if start_points is None else np.asarray(start_points, dtype=np.float64).reshape(n, 2)[lo:hi]
     dev = _dev(device)
-    pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage)
+    pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage, turn_model, clothoid_share)
     db = DeviceBatch(pb, dev)
     res = run_device_batch(db, outputs, want_curvature, cost, cand_base=lo)
     bufs = res.extras["buffers"]

@@ -34,7 +34,7 @@ class TwoLayerPathPlannerV37:
                  field_width: float = None, field_vertices: List[Tuple[float, float]] = None,
                  obstacles: List[List[Tuple[float, float]]] = None, start_point: Tuple[float, float] = None,
                  end_point: Tuple[float, float] = None, *, vehicle: VehicleParams = None, device=None,
-                 verbose: bool = False, grid_h: float = 0.1):
+                 verbose: bool = False, grid_h: float = 0.1, turn_model: str = "arc", clothoid_share: float = 0.5):
         if vehicle_params is None:
             vehicle_params = vehicle          # README spelling (README.md:262-266)
         if vehicle_params is None:
@@ -43,6 +43,8 @@ class TwoLayerPathPlannerV37:
         self.obstacles = obstacles or []
         self.verbose = verbose
         self.grid_h = grid_h
+        self.turn_model = turn_model          # 'arc' = reference behaviour; 'clothoid' = opt-in (README.md:105-113)
+        self.clothoid_share = clothoid_share
         self._device = device
         self._process_field_input(field_length, field_width, field_vertices)
         self.corner_angles = [float(a) for a in G.corner_angles_deg(np.asarray(self.field_vertices, dtype=np.float64)[None])[0]] \
@@ -130,7 +132,8 @@ class TwoLayerPathPlannerV37:
             sci, _, _ = self._select_best_start_corner(self.start_point)
         cands = {"field_id": np.zeros(1, dtype=np.int32), "start_corner": np.array([sci], dtype=np.int32)}
         sp = np.array([[np.nan, np.nan]]) if not self.start_point else np.array([self.start_point], dtype=np.float64)
-        pb = prepare_batch([self.field_vertices], self.vehicle, cands, [self.obstacles], sp, self.grid_h, True)
+        pb = prepare_batch([self.field_vertices], self.vehicle, cands, [self.obstacles], sp, self.grid_h, True,
+                           self.turn_model, self.clothoid_share)
         # start_corner only selects the headland start; the pass order comes from the start point
         # (mlp3:649-658) or stays (False, False) without one
         if not self.start_point:

@@ -103,7 +103,16 @@ typedef struct {
                                       previous fcpp_layout of the same batch): fcpp_layout then skips its
                                       8-byte readback + stream synchronisation and stays fully asynchronous */
     int32_t max_head_points_hint;  /* same for the headland part alone (n_head); used with max_points_hint */
+    /* ---- turn model (README.md:105-113 describes it, the reference has no code) ---- */
+    int32_t turn_model;            /* 0: the reference's sampled circular arcs (mlp3:807-830, :1046-1062);
+                                      1: clothoid -> arc -> clothoid turns with Fresnel integrals evaluated
+                                      per sample point on the device (same sample counts, same layout) */
+    int32_t reserved0;
+    double clothoid_share;         /* share of a turn's deflection spent on the two clothoids, (0, 1] */
 } fcpp_batch;
+
+#define FCPP_TURN_ARC 0
+#define FCPP_TURN_CLOTHOID 1
 
 #define FCPP_FLAG_CORNER_MASK 3
 #define FCPP_FLAG_REVERSE_ORDER 4

@@ -22,10 +22,11 @@ STATUS_LOOP_SKIPPED = 2
 def evaluate_candidate(field_vertices, vehicle: rp.VehicleParams, R: Optional[float] = None,
                        heading: Optional[float] = None, start_corner: Optional[int] = None,
                        obstacles: Sequence = (), grid_h: float = 0.1, coverage: bool = True,
-                       keep_paths: bool = False) -> Dict:
+                       keep_paths: bool = False, turn_model: str = "arc", clothoid_share: float = 0.5) -> Dict:
     veh = replace(vehicle, min_turn_radius=float(R)) if R is not None else vehicle
     fs = rp.setup_field(veh, field_vertices=[tuple(map(float, v)) for v in field_vertices],
-                        obstacles=[list(map(tuple, o)) for o in obstacles])
+                        obstacles=[list(map(tuple, o)) for o in obstacles], turn_model=turn_model,
+                        clothoid_share=clothoid_share)
     out: Dict = {"status": 0}
     try:
         res = rp.plan_complete_coverage(fs, heading=heading, start_corner=start_corner)

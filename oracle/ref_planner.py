@@ -80,6 +80,10 @@ class FieldSetup:
     obstacles: List[List[Pt]]
     start_point: Optional[Pt]
     end_point: Optional[Pt]
+    # build-defined opt-in: "arc" = the reference's sampled circular arcs,
+    # "clothoid" = clothoid-arc-clothoid turns (oracle/clothoid.py); parity unpinned for the latter
+    turn_model: str = "arc"
+    clothoid_share: float = 0.5
 
 
 def corner_angle(vertices: Sequence[Pt], i: int) -> float:
@@ -121,7 +125,8 @@ def validate_point(p: Optional[Pt], field_length: float, field_width: float) -> 
 
 
 def setup_field(vehicle: VehicleParams, field_length=None, field_width=None, field_vertices=None,
-                obstacles=None, start_point=None, end_point=None) -> FieldSetup:
+                obstacles=None, start_point=None, end_point=None, turn_model="arc",
+                clothoid_share=0.5) -> FieldSetup:
     """mlp3:63-135 (constructor + _process_field_input)."""
     if field_vertices is not None:
         verts = [tuple(v) for v in field_vertices]
@@ -147,7 +152,8 @@ def setup_field(vehicle: VehicleParams, field_length=None, field_width=None, fie
     pattern = "Ω型跨行" if aspect < 1.5 else "U型往复"
     return FieldSetup(vehicle, verts, fl, fw, shape, angles, vehicle.min_turn_radius, pattern,
                       [list(map(tuple, o)) for o in (obstacles or [])],
-                      validate_point(start_point, fl, fw), validate_point(end_point, fl, fw))
+                      validate_point(start_point, fl, fw), validate_point(end_point, fl, fw),
+                      turn_model, clothoid_share)
 
 
 def select_best_start_corner(fs: FieldSetup, parking: Pt) -> int:
@@ -193,8 +199,11 @@ def uturn_tables():
     return np.cos(a20), np.sin(a20), np.cos(a15), np.sin(a15)
 
 
-def u_pattern_in_rotated_space(bnds, v: VehicleParams, reverse_order: bool, start_from_right: bool):
-    """mlp3:720-830 (swath layout + 20-pt half-circle 'turns', Q3/Q4)."""
+def u_pattern_in_rotated_space(bnds, v: VehicleParams, reverse_order: bool, start_from_right: bool,
+                               turn_model: str = "arc", clothoid_share: float = 0.5):
+    """mlp3:720-830 (swath layout + 20-pt half-circle 'turns', Q3/Q4).  With
+    turn_model='clothoid' the 20 turn samples are a clothoid-arc-clothoid U-turn that leaves the
+    swath end TANGENTIALLY towards the next swath (build-defined, A16)."""
     min_x, min_y, max_x, max_y = bnds
     R = v.min_turn_radius
     line_start_x = min_x + R
@@ -213,7 +222,16 @@ def u_pattern_in_rotated_space(bnds, v: VehicleParams, reverse_order: bool, star
             line = np.array([[line_start_x, y], [line_end_x, y]])
         segs.append(line)
         speeds.extend([v.max_work_speed_kmh] * 2)
-        if idx < num_passes - 1:
+        if idx < num_passes - 1 and turn_model == "clothoid":
+            from .clothoid import cac_unit
+            xi, eta = cac_unit(np.pi, UTURN_POINTS, clothoid_share)
+            dir_x = -1.0 if go_left else 1.0
+            dir_y = -1.0 if reverse_order else 1.0
+            arc_x = line[-1][0] + dir_x * (R * xi)
+            arc_y = y + dir_y * (R * eta)
+            segs.append(np.column_stack([arc_x, arc_y]))
+            speeds.extend([v.headland_turn_speed_kmh] * UTURN_POINTS)
+        elif idx < num_passes - 1:
             turn_right = not go_left
             if turn_right:
                 arc_x = max_x - R * np.cos(angles)
@@ -264,7 +282,8 @@ def plan_main_work(fs: FieldSetup, heading: Optional[float] = None,
             reverse_order = True
         if sp[0] > (bnds[0] + bnds[2]) / 2:
             start_from_right = True
-    path, speeds, P = u_pattern_in_rotated_space(bnds, v, reverse_order, start_from_right)
+    path, speeds, P = u_pattern_in_rotated_space(bnds, v, reverse_order, start_from_right, fs.turn_model,
+                                                 fs.clothoid_share)
     if rotated:
         cp, sp_ = float(np.cos(angle)), float(np.sin(angle))
         x = path[:, 0] - center[0]
@@ -281,9 +300,21 @@ def plan_main_work(fs: FieldSetup, heading: Optional[float] = None,
 # ------------------------------------------------------------------------------------------
 # A5/A6  layer 2 (mlp3:860-1288, :1580-1608)
 # ------------------------------------------------------------------------------------------
-def corner_turn_arc(corner: Pt, corner_index: int, R: float, num_points: int = CORNER_ARC_POINTS):
-    """mlp3:1580-1608 (also :1046-1062 and, with 30 points, :1124-1140)."""
+def corner_turn_arc(corner: Pt, corner_index: int, R: float, num_points: int = CORNER_ARC_POINTS,
+                    turn_model: str = "arc", clothoid_share: float = 0.5):
+    """mlp3:1580-1608 (also :1046-1062 and, with 30 points, :1124-1140).  turn_model='clothoid':
+    same start pose and turning sense, clothoid-arc-clothoid quarter turn (A16)."""
     x, y = corner
+    if turn_model == "clothoid":
+        from .clothoid import cac_unit
+        xi, eta = cac_unit(np.pi / 2, num_points, clothoid_share)
+        if corner_index == 0:
+            return np.column_stack([x + R * eta, y + R * xi])
+        if corner_index == 1:
+            return np.column_stack([x - R * xi, y + R * eta])
+        if corner_index == 2:
+            return np.column_stack([x - R * eta, y - R * xi])
+        return np.column_stack([x + R * xi, y - R * eta])
     a = np.linspace(0, np.pi / 2, num_points)
     if corner_index == 0:
         ax = x + R * (1 - np.cos(a)); ay = y + R * np.sin(a)
@@ -383,7 +414,7 @@ def headland_loop(fs: FieldSetup, offset: float, loop_index: int, start_corner_i
         segs.append(np.column_stack([sx, sy]))
         speeds.extend([v.max_headland_speed_kmh] * STRAIGHT_POINTS)
         if i < 3:
-            arc = corner_turn_arc(nxt, ni, R)
+            arc = corner_turn_arc(nxt, ni, R, CORNER_ARC_POINTS, fs.turn_model, fs.clothoid_share)
             tsp = [v.headland_turn_speed_kmh] * CORNER_ARC_POINTS
             if loop_index == 0 and should_apply_reverse_filling(fs, ni) and gap_gate(nxt, ni, R, W):
                 rev, _ = optimal_reverse_path(fs, arc[-1], arc[-2])
@@ -544,7 +575,7 @@ def verification_corner_paths(fs: FieldSetup):
             (fs.field_length - hw, fs.field_width - hw, 2), (hw, fs.field_width - hw, 3)]
     out = []
     for cx, cy, ci in data:
-        arc = corner_turn_arc((cx, cy), ci, R)
+        arc = corner_turn_arc((cx, cy), ci, R, CORNER_ARC_POINTS, fs.turn_model, fs.clothoid_share)
         rev = None
         if gap_gate((cx, cy), ci, R, W):
             rev, _ = optimal_reverse_path(fs, arc[-1], arc[-2])

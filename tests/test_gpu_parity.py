@@ -409,3 +409,32 @@ def test_edge_cases(fc):
         fc.plan_batch([RECT], fc.VehicleParams(), grid_h=0.0333)          # not an even multiple of 1e-4 m
     res = fc.plan_batch([RECT], fc.VehicleParams(), coverage=False)
     assert int(res.summary["cov_total"][0]) == 0 and int(res.summary["n_main"][0]) == 1256
+
+
+def test_clothoid_turn_model_vs_scipy_oracle(fc):
+    """Row A16 (opt-in, no reference code): clothoid -> arc -> clothoid turns with device-side
+    Fresnel series vs oracle/clothoid.py (scipy.special.fresnel).  Parity with the reference is
+    unpinned; the layout (point counts) must equal the arc model's."""
+    from oracle import batch as ob, ref_planner as rp
+    para = [(100, 50), (600, 120), (640, 330), (140, 260)]
+    fields = [RECT, para]
+    cand = fc.make_candidates(2, radii=[6.0, 8.0], start_corners=[0, 3])
+    for lam in (0.5, 1.0, 0.2):
+        res = fc.plan_batch(fields, fc.VehicleParams(), cand, outputs="paths", turn_model="clothoid", clothoid_share=lam)
+        arc = fc.plan_batch(fields, fc.VehicleParams(), cand, coverage=False)
+        assert (res.summary["n_main"] == arc.summary["n_main"]).all()
+        for b in range(len(res.summary)):
+            o = ob.evaluate_candidate(fields[int(cand["field_id"][b])], rp.VehicleParams(), R=cand["R"][b],
+                                      start_corner=int(cand["start_corner"][b]), keep_paths=True,
+                                      turn_model="clothoid", clothoid_share=lam, coverage=(b % 3 == 0))
+            _summary_vs_oracle(res.summary[b], o, coverage=(b % 3 == 0))
+            p, s, _ = res.path(b)
+            assert np.abs(p - o["path"]).max() <= TIGHT
+            assert np.abs(s - o["speeds"]).max() <= 1e-7
+    # the clothoid turn lowers the peak curvature seen by the speed planner
+    assert res.summary["max_curvature"].max() <= arc.summary["max_curvature"].max()
+    pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=500, field_width=200, turn_model="clothoid")
+    r = pl.plan()
+    assert len(r["main_work"]["path"]) == 1256
+    with pytest.raises(ValueError):
+        fc.plan_batch(fields, fc.VehicleParams(), cand, turn_model="bezier")
