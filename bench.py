@@ -94,7 +94,7 @@ def make_pool():
 # clocks (nvidia-smi / NVML sampled DURING the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
@@ -136,6 +136,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of
+    this same workload (profiles/ncu_traffic.json, written by profiles/summarize.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["dram_read_bytes"]) + float(t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -152,7 +163,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=64, help="candidates in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="candidates in the bounded CPU sample (default: 1024 for cpu_baseline ~ 10 s on 16 cores, "
+                         "256 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -164,7 +177,7 @@ def main():
         if rank != 0:
             return 0
         pool, cores = make_pool()
-        sample = cpu_sample(n_gpus, args.cpu_sample)
+        sample = cpu_sample(n_gpus, args.cpu_sample or 256)
         steps = max(1, args.steps)
         for _ in range(min(args.warmup, 1)):
             run_cpu(pool, sample[:cores])
@@ -299,7 +312,7 @@ def main():
     else:
         dom, ach = "plan_kernel", bytes_plan / (k_plan * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": ncu_traffic(dom), "peak_source": peak_src,
                 "kernel_ms": {"plan_kernel": k_plan, "cover_kernel": k_cover, "step": dev_ms_max / args.steps},
                 "algorithmic_bytes_per_launch": {"plan_kernel": bytes_plan, "cover_kernel": bytes_cover},
                 "note": "grid lives in shared memory: real DRAM traffic is far below the algorithmic bytes; "
@@ -309,7 +322,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         pool, cores = make_pool()
-        sample = cpu_sample(n_gpus, args.cpu_sample)
+        sample = cpu_sample(n_gpus, args.cpu_sample or 1024)
         run_cpu(pool, sample[:cores])
         dt = run_cpu(pool, sample)
         pool.close()
