@@ -78,6 +78,28 @@ class Outputs(C.Structure):
     ]
 
 
+class GAConfigC(C.Structure):
+    """fcpp_ga_config (GAConfig ga:20-29 + seed)."""
+    _fields_ = [
+        ("population_size", C.c_int32), ("max_generations", C.c_int32),
+        ("crossover_rate", C.c_double), ("mutation_rate", C.c_double),
+        ("elite_size", C.c_int32), ("tournament_size", C.c_int32),
+        ("convergence_threshold", C.c_int32), ("check_every", C.c_int32),
+        ("seed", C.c_uint64),
+    ]
+
+
+class GAResultC(C.Structure):
+    """fcpp_ga_result (stats of ga:122-127)."""
+    _fields_ = [
+        ("generations", C.c_int32), ("convergence_gen", C.c_int32), ("final_population", C.c_int32),
+        ("reserved", C.c_int32), ("best_distance", C.c_double), ("best_fitness", C.c_double),
+    ]
+
+
+GA_TRACE_INTS = 48
+GA_MAX_TOURNAMENT = 16
+
 # numpy mirror of fcpp_summary (176 bytes)
 SUMMARY_DTYPE = np.dtype([
     ("status", "<i4"), ("n_passes", "<i4"), ("n_loops", "<i4"), ("n_main", "<i4"), ("n_head", "<i4"),
@@ -93,7 +115,8 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
     "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_speed_verify", "fcpp_raster_window",
-    "fcpp_tour_lengths", "fcpp_launch_count", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_set_profiling", "fcpp_kernel_times",
+    "fcpp_tour_lengths", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve",
+    "fcpp_launch_count", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_set_profiling", "fcpp_kernel_times",
 ]
 
 _lib = None
@@ -138,6 +161,14 @@ def load():
         L.fcpp_raster_window.argtypes = [vp, vp, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
         L.fcpp_tour_lengths.restype = C.c_int
         L.fcpp_tour_lengths.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
+        L.fcpp_ga_init_population.restype = C.c_int
+        L.fcpp_ga_init_population.argtypes = [vp, C.POINTER(GAConfigC), i32, vp, vp]
+        L.fcpp_ga_next_size.restype = i32
+        L.fcpp_ga_next_size.argtypes = [C.POINTER(GAConfigC), i32]
+        L.fcpp_ga_generation.restype = C.c_int
+        L.fcpp_ga_generation.argtypes = [vp, C.POINTER(GAConfigC), i32, i32, vp, vp, i32, vp, vp, vp]
+        L.fcpp_ga_solve.restype = C.c_int
+        L.fcpp_ga_solve.argtypes = [vp, C.POINTER(GAConfigC), vp, i32, vp, vp, vp, C.POINTER(GAResultC), vp]
         L.fcpp_last_max_points.restype = i32
         L.fcpp_last_max_points.argtypes = [vp]
         L.fcpp_last_max_head_points.restype = i32

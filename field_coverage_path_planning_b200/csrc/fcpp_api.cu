@@ -136,6 +136,9 @@ void fcpp_destroy(fcpp_handle *h)
     if (h->d_big) cudaFree(h->d_big);
     if (h->d_maxn) cudaFree(h->d_maxn);
     if (h->h_maxn) cudaFreeHost(h->h_maxn);
+    if (h->d_ga) cudaFree(h->d_ga);
+    if (h->h_ga_state) cudaFreeHost(h->h_ga_state);
+    if (h->ga_stream) cudaStreamDestroy(h->ga_stream);
     for (int k = 0; k < 4; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     free(h);
@@ -303,6 +306,233 @@ int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_
     cudaSetDevice(h->device);
     cudaError_t e = fcpp_launch_tours(h, d_D, n, d_pop, pop_size, d_out, d_fitness, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(h, e, "tour kernel");
+    return FCPP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// GA evolution on the device (fcpp_ga.cu)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int check_ga(fcpp_handle *h, const fcpp_ga_config *c, int n, int m_in)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (!c) return fail(h, FCPP_ERR_INVALID, "GA config is NULL");
+    if (n < 1 || n > 12288) return fail(h, FCPP_ERR_INVALID, "GA: n must be in 1..12288 (got %d)", n);
+    if (m_in < 1) return fail(h, FCPP_ERR_INVALID, "GA: empty population");
+    if (c->tournament_size < 1 || c->tournament_size > FCPP_GA_MAX_TOURNAMENT)
+        return fail(h, FCPP_ERR_INVALID, "GA: tournament_size must be in 1..%d", FCPP_GA_MAX_TOURNAMENT);
+    if (c->tournament_size > m_in)  // random.sample raises ValueError (ga:189)
+        return fail(h, FCPP_ERR_INVALID, "GA: tournament_size %d larger than the population %d", c->tournament_size,
+                    m_in);
+    if (c->elite_size < 0) return fail(h, FCPP_ERR_INVALID, "GA: negative elite_size");
+    return FCPP_OK;
+}
+
+struct GaWs {
+    int32_t *pop[2];
+    double *len, *fit;
+    int *rank;
+    void *state;
+    int32_t *best;
+};
+
+size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int ga_workspace(fcpp_handle *h, int cap, int n, GaWs &w)
+{
+    const size_t pop_b = al256((size_t)cap * n * 4), vec_b = al256((size_t)cap * 8), rank_b = al256((size_t)cap * 4);
+    const size_t st_b = al256(fcpp_ga_state_bytes()), best_b = al256((size_t)n * 4);
+    const size_t total = 2 * pop_b + 2 * vec_b + rank_b + st_b + best_b;
+    if (total > h->ga_bytes) {
+        if (h->d_ga) cudaFree(h->d_ga);
+        h->d_ga = nullptr;
+        h->ga_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->d_ga, total);
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(GA workspace)");
+        h->ga_bytes = total;
+    }
+    if (!h->h_ga_state) {
+        cudaError_t e = cudaMallocHost(&h->h_ga_state, fcpp_ga_state_bytes());
+        if (e != cudaSuccess) return cuda_fail(h, e, "cudaMallocHost(GA state)");
+    }
+    unsigned char *p = (unsigned char *)h->d_ga;
+    w.pop[0] = (int32_t *)p;
+    p += pop_b;
+    w.pop[1] = (int32_t *)p;
+    p += pop_b;
+    w.len = (double *)p;
+    p += vec_b;
+    w.fit = (double *)p;
+    p += vec_b;
+    w.rank = (int *)p;
+    p += rank_b;
+    w.state = p;
+    p += st_b;
+    w.best = (int32_t *)p;
+    return FCPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fcpp_ga_next_size(const fcpp_ga_config *cfg, int32_t m_in)
+{
+    if (!cfg || m_in < 1) return 0;
+    int keep, e_take, m_out;
+    fcpp_ga_sizes(*cfg, m_in, keep, e_take, m_out);
+    return m_out;
+}
+
+int fcpp_ga_init_population(fcpp_handle *h, const fcpp_ga_config *cfg, int32_t n, int32_t *d_pop, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (!cfg || !d_pop || n < 1 || cfg->population_size < 0)
+        return fail(h, FCPP_ERR_INVALID, "fcpp_ga_init_population: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_ga_init(h, *cfg, n, d_pop, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "GA init kernel");
+    return FCPP_OK;
+}
+
+int fcpp_ga_generation(fcpp_handle *h, const fcpp_ga_config *cfg, int32_t generation, int32_t n,
+                       const int32_t *d_pop_in, const double *d_fitness, int32_t m_in, int32_t *d_pop_out,
+                       int32_t *d_trace, void *stream)
+{
+    int rc = check_ga(h, cfg, n, m_in);
+    if (rc) return rc;
+    if (!d_pop_in || !d_fitness || !d_pop_out || generation < 0)
+        return fail(h, FCPP_ERR_INVALID, "fcpp_ga_generation: bad argument");
+    cudaSetDevice(h->device);
+    GaWs w;
+    rc = ga_workspace(h, m_in + 2, n, w);
+    if (rc) return rc;
+    cudaError_t e = fcpp_launch_ga_generation(h, *cfg, generation, n, d_pop_in, d_fitness, m_in, d_pop_out, w.rank,
+                                              d_trace, nullptr, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "GA generation kernels");
+    return FCPP_OK;
+}
+
+int fcpp_ga_solve(fcpp_handle *h, const fcpp_ga_config *cfg, const double *d_D, int32_t n, const int32_t *d_pop_init,
+                  int32_t *d_best_route, double *d_history, fcpp_ga_result *host_result, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (!cfg || !d_D || !d_best_route || !host_result) return fail(h, FCPP_ERR_INVALID, "fcpp_ga_solve: NULL argument");
+    int m = d_pop_init ? cfg->population_size : 2 * (cfg->population_size / 2);  // ga:141-151
+    int rc = check_ga(h, cfg, n, m);
+    if (rc) return rc;
+    if (cfg->max_generations < 0) return fail(h, FCPP_ERR_INVALID, "GA: negative max_generations");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    GaWs w;
+    rc = ga_workspace(h, cfg->population_size + 2, n, w);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
+#define GA_CK(call, what)                          \
+    do {                                           \
+        e = (call);                                \
+        if (e != cudaSuccess) {                    \
+            if (exec) cudaGraphExecDestroy(exec);  \
+            return cuda_fail(h, e, what);          \
+        }                                          \
+    } while (0)
+    cudaGraphExec_t exec = nullptr;
+    if (d_pop_init)
+        GA_CK(cudaMemcpyAsync(w.pop[0], d_pop_init, (size_t)m * n * 4, cudaMemcpyDeviceToDevice, st), "GA copy");
+    else
+        GA_CK(fcpp_launch_ga_init(h, *cfg, n, w.pop[0], st), "GA init kernel");
+    GA_CK(fcpp_launch_tours(h, d_D, n, w.pop[0], m, w.len, w.fit, st), "tour kernel");                       // ga:68
+    GA_CK(fcpp_launch_ga_track(h, w.fit, w.len, w.pop[0], m, n, cfg->convergence_threshold, 1, w.state, w.best,
+                               nullptr, st),
+          "GA track kernel");                                                                                // ga:70-72
+    int cur = 0, launched = 0;
+    const int G = cfg->max_generations;
+    int check = cfg->check_every > 0 ? cfg->check_every : 16;
+    check += check & 1;
+    auto one_generation = [&](cudaStream_t s) -> cudaError_t {
+        int keep, e_take, m_out;
+        fcpp_ga_sizes(*cfg, m, keep, e_take, m_out);
+        cudaError_t err = fcpp_launch_ga_generation(h, *cfg, -1, n, w.pop[cur], w.fit, m, w.pop[cur ^ 1], w.rank,
+                                                    nullptr, w.state, s);                                     // ga:78-88
+        if (err != cudaSuccess) return err;
+        cur ^= 1;
+        m = m_out;
+        err = fcpp_launch_tours(h, d_D, n, w.pop[cur], m, w.len, w.fit, s);                                   // ga:91
+        if (err != cudaSuccess) return err;
+        return fcpp_launch_ga_track(h, w.fit, w.len, w.pop[cur], m, n, cfg->convergence_threshold, 0, w.state,
+                                    w.best, d_history, s);                                                    // ga:94-116
+    };
+    auto poll = [&](int &done) -> cudaError_t {
+        cudaError_t err = cudaMemcpyAsync(h->h_ga_state, w.state, fcpp_ga_state_bytes(), cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        int g, sg, lg;
+        double bf, bl;
+        fcpp_ga_read_state(h->h_ga_state, g, sg, done, lg, bf, bl);
+        return err;
+    };
+    int done = 0;
+    // generations whose population size still changes (an odd population grows once) run directly
+    while (launched < G && fcpp_ga_next_size(cfg, m) != m) {
+        GA_CK(one_generation(st), "GA generation");
+        ++launched;
+    }
+    if (launched > 0) GA_CK(poll(done), "GA poll");
+    // steady state: a CUDA graph of two generations (ping-pong returns to the same buffer)
+    if (!done && G - launched >= 2) {
+        if (!h->ga_stream) GA_CK(cudaStreamCreateWithFlags(&h->ga_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = h->launches;
+        GA_CK(cudaStreamBeginCapture(h->ga_stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+        cudaError_t e1 = one_generation(h->ga_stream);
+        cudaError_t e2 = (e1 == cudaSuccess) ? one_generation(h->ga_stream) : e1;
+        cudaError_t e3 = cudaStreamEndCapture(h->ga_stream, &graph);
+        const int64_t per_unit = h->launches - l0;
+        h->launches = l0;
+        if (e2 != cudaSuccess || e3 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return cuda_fail(h, e2 != cudaSuccess ? e2 : e3, "GA graph capture");
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            exec = nullptr;
+            return cuda_fail(h, e, "cudaGraphInstantiate");
+        }
+        int since = 0;
+        while (!done && G - launched >= 2) {
+            GA_CK(cudaGraphLaunch(exec, st), "cudaGraphLaunch");
+            h->launches += per_unit;
+            launched += 2;
+            since += 2;
+            if (since >= check) {
+                GA_CK(poll(done), "GA poll");
+                since = 0;
+            }
+        }
+        if (!done) GA_CK(poll(done), "GA poll");
+        cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+    while (!done && launched < G) {
+        GA_CK(one_generation(st), "GA generation");
+        ++launched;
+        GA_CK(poll(done), "GA poll");
+    }
+    GA_CK(fcpp_launch_ga_rotate(h, w.best, n, d_best_route, st), "GA rotate kernel");                        // ga:119-120
+    GA_CK(poll(done), "GA poll");
+#undef GA_CK
+    int g, sg, lg;
+    double bf, bl;
+    fcpp_ga_read_state(h->h_ga_state, g, sg, done, lg, bf, bl);
+    host_result->generations = g;                 // ga:123 generation + 1
+    host_result->convergence_gen = lg - sg;       // ga:126
+    host_result->final_population = m;
+    host_result->reserved = 0;
+    host_result->best_distance = bl;
+    host_result->best_fitness = bf;
     return FCPP_OK;
 }
 

@@ -74,6 +74,10 @@ struct fcpp_handle {
     int last_maxhead;
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
     int64_t layout_ncand;
+    void *d_ga;              // GA workspace (two populations, lengths, fitness, ranks, state, best route)
+    size_t ga_bytes;
+    void *h_ga_state;        // pinned host copy of the GA state
+    cudaStream_t ga_stream;  // capture stream of the generation graph
     char err[512];
 };
 
@@ -446,6 +450,18 @@ cudaError_t fcpp_launch_raster_window(fcpp_handle *h, const double *d_path, int3
                                       int64_t *d_count, cudaStream_t st);
 cudaError_t fcpp_launch_tours(fcpp_handle *h, const double *d_D, int32_t n, const int32_t *d_pop,
                               int64_t pop_size, double *d_out, double *d_fit, cudaStream_t st);
+void fcpp_ga_sizes(const fcpp_ga_config &cfg, int m_in, int &keep, int &e_take, int &m_out);
+cudaError_t fcpp_launch_ga_init(fcpp_handle *h, const fcpp_ga_config &cfg, int n, int32_t *d_pop, cudaStream_t st);
+cudaError_t fcpp_launch_ga_generation(fcpp_handle *h, const fcpp_ga_config &cfg, int gen, int n,
+                                      const int32_t *d_pop_in, const double *d_fit, int m_in, int32_t *d_pop_out,
+                                      int *d_rank, int32_t *d_trace, const void *d_state, cudaStream_t st);
+cudaError_t fcpp_launch_ga_track(fcpp_handle *h, const double *d_fit, const double *d_len, const int32_t *d_pop,
+                                 int m, int n, int threshold, int initial, void *d_state, int32_t *d_best_route,
+                                 double *d_history, cudaStream_t st);
+cudaError_t fcpp_launch_ga_rotate(fcpp_handle *h, const int32_t *d_route, int n, int32_t *d_out, cudaStream_t st);
+size_t fcpp_ga_state_bytes();
+void fcpp_ga_read_state(const void *host_copy, int &gen, int &stagnant, int &done, int &last_gen, double &best_fit,
+                        double &best_len);
 cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32_t *d_cand_field,
                                int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
                                double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);

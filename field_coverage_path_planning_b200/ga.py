@@ -5,13 +5,17 @@ lengths in one kernel launch (genetic_algorithm_solver.py:168-181, "ga").  The F
 left to right per tour exactly like the reference loop, so lengths are bit-identical.
 
 ``GeneticAlgorithmSolver`` keeps the reference's interface (``GAConfig``, ``solve(distance_matrix,
-verbose) -> (route, stats)``, ``best_fitness_history`` / ``avg_fitness_history``) with the fitness
-of every generation evaluated on the GPU.  The evolution operators stay on the host (SURVEY.md
-§8(f) N1: they are RNG-driven list operations and the reference uses an unseeded global
-``random``, so parity for them is statistical, not bitwise): tournament selection (ga:183-196),
-OX crossover (ga:198-242), swap mutation (ga:244-252), elitism that overwrites the LAST
-``elite_size`` children (ga:254-268), stop after ``convergence_threshold`` stagnant generations
-(ga:113-116), final rotation so that node 0 (the depot) comes first (ga:119-120).
+verbose) -> (route, stats)``, ``best_fitness_history`` / ``avg_fitness_history``).  By default
+(``operators="device"``) the WHOLE solve loop runs on the GPU through ``fcpp_ga_solve``
+(SURVEY.md §8(f) N1): tournament selection (ga:183-196), OX crossover (ga:198-242), swap mutation
+(ga:244-252), elitism that overwrites the LAST ``elite_size`` children (ga:254-268), fitness,
+best tracking and the stop after ``convergence_threshold`` stagnant generations (ga:113-116), the
+final rotation to node 0 (ga:119-120) — two generations per CUDA graph, the host only polls the
+convergence flag.  The reference draws from Python's unseeded global ``random``; here a Philox
+counter-based generator keyed by ``seed`` makes runs reproducible.  Whole-run parity is
+statistical; operator parity is exact given the same decisions (``ga_generation(...,
+return_trace=True)`` exposes them; tests replay them through the reference's operators).
+``operators="host"`` keeps the numpy restatement of the operators with only the fitness on the GPU.
 """
 from __future__ import annotations
 
@@ -81,6 +85,87 @@ def tour_lengths(distance_matrix, population, device=None, return_fitness: bool 
     return out.cpu().numpy()
 
 
+def _cfg_c(config, seed: int, check_every: int = 0) -> "_lib.GAConfigC":
+    return _lib.GAConfigC(int(config.population_size), int(config.max_generations), float(config.crossover_rate),
+                          float(config.mutation_rate), int(config.elite_size), int(config.tournament_size),
+                          int(config.convergence_threshold), int(check_every), int(seed) & (2 ** 64 - 1))
+
+
+def ga_init_population(config, n: int, seed: int = 0, device=None) -> torch.Tensor:
+    """ga:137-166 on the device: 2*(population_size//2) individuals [pop, n] int32 (CUDA tensor)."""
+    dev = _dev(device)
+    h = _lib.handle(dev.index)
+    m = 2 * (int(config.population_size) // 2)
+    with torch.cuda.device(dev):
+        pop = torch.empty((m, n), dtype=torch.int32, device=dev)
+        cfg = _cfg_c(config, seed)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        h.check(h.lib.fcpp_ga_init_population(h.h, C.byref(cfg), n, pop.data_ptr(), st))
+    return pop
+
+
+def ga_generation(config, population, fitness, generation: int = 0, seed: int = 0, device=None,
+                  return_trace: bool = False):
+    """One generation ga:78-88 on the device: selection + OX crossover + mutation + elitism.
+
+    ``population`` [m, n] int32 and ``fitness`` [m] float64 (numpy or CUDA tensors) -> new
+    population (CUDA tensor, ``fcpp_ga_next_size`` rows).  ``return_trace`` adds the int32
+    [(m+1)//2, 48] decision trace (layout in include/fcpp.h)."""
+    dev = _dev(device if device is not None else (population.device if torch.is_tensor(population) else None))
+    h = _lib.handle(dev.index)
+    P = population if torch.is_tensor(population) else torch.from_numpy(np.ascontiguousarray(population, dtype=np.int32))
+    F = fitness if torch.is_tensor(fitness) else torch.from_numpy(np.ascontiguousarray(fitness, dtype=np.float64))
+    P = P.to(dev, dtype=torch.int32).contiguous()
+    F = F.to(dev, dtype=torch.float64).contiguous()
+    m, n = P.shape
+    if F.shape != (m,):
+        raise ValueError("fitness must be [population]")
+    cfg = _cfg_c(config, seed)
+    m_out = int(h.lib.fcpp_ga_next_size(C.byref(cfg), m))
+    with torch.cuda.device(dev):
+        out = torch.empty((m_out, n), dtype=torch.int32, device=dev)
+        trace = torch.zeros(((m + 1) // 2, _lib.GA_TRACE_INTS), dtype=torch.int32, device=dev) if return_trace else None
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        h.check(h.lib.fcpp_ga_generation(h.h, C.byref(cfg), int(generation), n, P.data_ptr(), F.data_ptr(), m,
+                                         out.data_ptr(), trace.data_ptr() if trace is not None else None, st))
+    return (out, trace) if return_trace else out
+
+
+def ga_solve_device(config, distance_matrix, seed: int = 0, initial_population=None, device=None,
+                    check_every: int = 0):
+    """``solve()`` ga:44-135 entirely on the device.  Returns (route list, stats dict, history [G, 2])."""
+    dev = _dev(device)
+    h = _lib.handle(dev.index)
+    D = distance_matrix if torch.is_tensor(distance_matrix) else torch.from_numpy(
+        np.ascontiguousarray(distance_matrix, dtype=np.float64))
+    D = D.to(dev, dtype=torch.float64).contiguous()
+    n = D.shape[0]
+    if D.shape != (n, n):
+        raise ValueError("distance_matrix must be [n, n]")
+    P0 = None
+    if initial_population is not None:
+        P0 = initial_population if torch.is_tensor(initial_population) else torch.from_numpy(
+            np.ascontiguousarray(initial_population, dtype=np.int32))
+        P0 = P0.to(dev, dtype=torch.int32).contiguous()
+        if P0.shape != (int(config.population_size), n):
+            raise ValueError("initial_population must be [population_size, n]")
+    cfg = _cfg_c(config, seed, check_every)
+    res = _lib.GAResultC()
+    G = max(int(config.max_generations), 0)
+    with torch.cuda.device(dev):
+        route = torch.empty(n, dtype=torch.int32, device=dev)
+        hist = torch.zeros((max(G, 1), 2), dtype=torch.float64, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        h.check(h.lib.fcpp_ga_solve(h.h, C.byref(cfg), D.data_ptr(), n, P0.data_ptr() if P0 is not None else None,
+                                    route.data_ptr(), hist.data_ptr(), C.byref(res), st))
+        route_h = route.cpu().tolist()
+        hist_h = hist[:res.generations].cpu().numpy()
+    stats = {'generations': int(res.generations), 'best_distance': float(res.best_distance),
+             'best_fitness': float(res.best_fitness), 'convergence_gen': int(res.convergence_gen),
+             'final_population': int(res.final_population)}
+    return route_h, stats, hist_h
+
+
 @dataclass
 class GAConfig:
     """ga:20-29."""
@@ -96,11 +181,17 @@ class GAConfig:
 class GeneticAlgorithmSolver:
     """Permutation GA for the multi-field TSP ordering (ga:32-268) with GPU fitness."""
 
-    def __init__(self, config: GAConfig = None, seed: Optional[int] = None, device=None):
+    def __init__(self, config: GAConfig = None, seed: Optional[int] = None, device=None,
+                 operators: str = "device"):
+        if operators not in ("device", "host"):
+            raise ValueError("operators must be 'device' or 'host'")
         self.config = config or GAConfig()
         self.best_fitness_history: List[float] = []
         self.avg_fitness_history: List[float] = []
         self.rng = np.random.default_rng(seed)
+        # the reference is unseeded (global `random`): without a seed every solver draws a fresh one
+        self.seed = int(seed) if seed is not None else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+        self.operators = operators
         self._device = device
 
     # -- fitness on the device (the hot path) ------------------------------------------------
@@ -172,14 +263,25 @@ class GeneticAlgorithmSolver:
 
     def _elitism(self, old: np.ndarray, fit: np.ndarray, new: np.ndarray) -> np.ndarray:
         e = self.config.elite_size
-        elite = old[np.argsort(-fit, kind="stable")[:e]]
-        return np.concatenate([new[:-e], elite]) if e > 0 else new   # drops the LAST children (ga:266)
+        if e <= 0:            # python slicing of ga:262-266: new[:-0] is empty, argsort[-0:] is everything
+            return old[np.argsort(fit, kind="stable")]
+        elite = old[np.argsort(fit, kind="stable")[-e:]]
+        return np.concatenate([new[:-e], elite])                     # drops the LAST children (ga:266)
 
     def solve(self, distance_matrix: np.ndarray, verbose: bool = True) -> Tuple[List[int], dict]:
         """ga:44-135."""
         cfg = self.config
         t0 = time.time()
         n = len(distance_matrix)
+        if self.operators == "device":
+            route, stats, hist = ga_solve_device(cfg, distance_matrix, seed=self.seed, device=self._device)
+            self.best_fitness_history = hist[:, 0].tolist()
+            self.avg_fitness_history = hist[:, 1].tolist()
+            stats['time'] = time.time() - t0
+            if verbose:
+                print(f"[fcpp GA] nodes={n} generations={stats['generations']} best={stats['best_distance']:.1f} m "
+                      f"time={stats['time']:.2f} s (device operators)")
+            return route, stats
         dev = _dev(self._device)
         D_dev = torch.from_numpy(np.ascontiguousarray(distance_matrix, dtype=np.float64)).to(dev)
         pop = self._initialize_population(n)

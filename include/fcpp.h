@@ -213,6 +213,62 @@ int fcpp_raster_window(fcpp_handle *h, const double *d_path_xy, int32_t n_pts, d
 int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_t *d_pop,
                       int64_t pop_size, double *d_out, double *d_fitness, void *stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * GA evolution on the device ("ga" = genetic_algorithm_solver.py)
+ * ------------------------------------------------------------------------------------------- */
+#define FCPP_GA_MAX_TOURNAMENT 16
+#define FCPP_GA_TRACE_INTS 48 /* per offspring pair: [0] parent A, [1] parent B (indices into the old
+                                 population), [2] crossed, [3] cut a, [4] cut b, [5..7] child 1 mutated / i / j,
+                                 [8..10] child 2 mutated / i / j, [11] tournament size,
+                                 [12..28) tournament draws of A, [28..44) tournament draws of B */
+
+/* GAConfig, ga:20-29, + the seed of the counter-based generator (the reference uses Python's
+ * unseeded global `random`; parity of whole runs is statistical, of the operators exact) */
+typedef struct {
+    int32_t population_size;
+    int32_t max_generations;
+    double crossover_rate;
+    double mutation_rate;
+    int32_t elite_size;
+    int32_t tournament_size;       /* 1 .. FCPP_GA_MAX_TOURNAMENT and <= population (random.sample, ga:189) */
+    int32_t convergence_threshold;
+    int32_t check_every;           /* generations between host polls of the convergence flag (0: 16) */
+    uint64_t seed;
+} fcpp_ga_config;
+
+/* stats of ga:122-127 */
+typedef struct {
+    int32_t generations;
+    int32_t convergence_gen;
+    int32_t final_population; /* an odd population grows by one individual in its first generation (ga:205) */
+    int32_t reserved;
+    double best_distance;
+    double best_fitness;
+} fcpp_ga_result;
+
+/* ga:137-166: 2*(population_size/2) individuals x n into d_pop (int32, row-major). */
+int fcpp_ga_init_population(fcpp_handle *h, const fcpp_ga_config *cfg, int32_t n, int32_t *d_pop, void *stream);
+
+/* Individuals after one generation over m_in individuals (python slicing of ga:262-266 included). */
+int32_t fcpp_ga_next_size(const fcpp_ga_config *cfg, int32_t m_in);
+
+/* One generation ga:78-88: tournament selection, OX crossover, swap mutation, elitism.  d_pop_in
+ * [m_in][n] + d_fitness [m_in] -> d_pop_out [fcpp_ga_next_size][n].  d_trace (optional)
+ * [(m_in+1)/2][FCPP_GA_TRACE_INTS] receives every random decision taken. */
+int fcpp_ga_generation(fcpp_handle *h, const fcpp_ga_config *cfg, int32_t generation, int32_t n,
+                       const int32_t *d_pop_in, const double *d_fitness, int32_t m_in, int32_t *d_pop_out,
+                       int32_t *d_trace, void *stream);
+
+/* solve(), ga:44-135, entirely on the device: initial population (d_pop_init [population_size][n] or
+ * NULL = fcpp_ga_init_population), fitness, evolution loop with best tracking and the
+ * convergence stop, final rotation to node 0.  d_best_route [n] int32; d_history (optional)
+ * [max_generations][2] = best_fitness_history / avg_fitness_history.  Synchronises the stream
+ * every check_every generations and before returning (host_result is host memory). */
+int fcpp_ga_solve(fcpp_handle *h, const fcpp_ga_config *cfg, const double *d_D, int32_t n,
+                  const int32_t *d_pop_init, int32_t *d_best_route, double *d_history,
+                  fcpp_ga_result *host_result, void *stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t fcpp_launch_count(const fcpp_handle *h);
 
