@@ -160,6 +160,35 @@ def main():
                     "gpu_tours_per_s": 8192 / (ms / 1e3), "e2e_tours_per_s": 8192 / e2e,
                     "cpu_tours_per_s_1core_python_loop": cpu})
         print(out[-1], flush=True)
+        # whole generations on the device (N1): selection + OX + mutation + elitism + fitness + tracking
+        from field_coverage_path_planning_b200 import ga
+        G = 200
+        cfg = fc.GAConfig(population_size=8192, max_generations=G, convergence_threshold=10 ** 9)
+        ga.ga_solve_device(cfg, dD, seed=1, initial_population=dP)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        route, stats, hist = ga.ga_solve_device(cfg, dD, seed=1, initial_population=dP)
+        dt = time.perf_counter() - t0
+        # the reference's generation on one core: its own operators on a 512-individual slice, scaled
+        cpu_gen = None
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ref_ga", "/root/reference/genetic_algorithm_solver.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            sol = mod.GeneticAlgorithmSolver(mod.GAConfig(population_size=512))
+            P = [list(map(int, r)) for r in pop[:512]]
+            t1 = time.perf_counter()
+            fit = [sol._calculate_fitness(r, D) for r in P]
+            new = sol._elitism(P, sol._mutation(sol._crossover(sol._selection(P, fit))), fit)
+            cpu_gen = (time.perf_counter() - t1) * (8192 / 512)
+        except Exception:       # the GPU box has no /root/reference
+            pass
+        out.append({"config": "c4 GA whole generations on the device, 201 nodes, population 8192", "generations": G,
+                    "wall_s": dt, "generations_per_s": G / dt, "ms_per_generation": 1e3 * dt / G,
+                    "best_distance": stats["best_distance"], "first_best": float(1 / hist[0, 0]),
+                    "reference_cpu_s_per_generation_1core_scaled_from_512": cpu_gen})
+        print(out[-1], flush=True)
     if "c5" in want:
         big = [(0.0, 0.0), (2000.0, 0.0), (2000.0, 1000.0), (0.0, 1000.0)]
         n = args.c5_cands // 4

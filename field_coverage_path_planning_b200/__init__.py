@@ -10,7 +10,11 @@ from .batch import BatchResult, make_candidates, plan_batch, prepare_batch  # no
 from .planner import (TwoLayerPathPlannerV35, TwoLayerPathPlannerV36, TwoLayerPathPlannerV37,  # noqa: F401
                       TwoLayerPlannerV35, TwoLayerPlannerV36, TwoLayerPlannerV37)
 from .ga import GAConfig, GeneticAlgorithmSolver, tour_lengths  # noqa: F401
+from .multi_field import (Connection, FieldData, MultiFieldPlannerV38, OptimizedRoute,  # noqa: F401
+                          connection_matrix, distance_matrix)
 
 __all__ = ["VehicleParams", "TwoLayerPathPlannerV37", "TwoLayerPathPlannerV35", "TwoLayerPathPlannerV36",
            "TwoLayerPlannerV35", "TwoLayerPlannerV36", "TwoLayerPlannerV37", "plan_batch", "prepare_batch",
-           "make_candidates", "BatchResult", "tour_lengths", "GeneticAlgorithmSolver", "GAConfig", "FcppError"]
+           "make_candidates", "BatchResult", "tour_lengths", "GeneticAlgorithmSolver", "GAConfig", "FcppError",
+           "MultiFieldPlannerV38", "FieldData", "Connection", "OptimizedRoute", "distance_matrix",
+           "connection_matrix"]

@@ -115,7 +115,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
     "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_speed_verify", "fcpp_raster_window",
-    "fcpp_tour_lengths", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve",
+    "fcpp_tour_lengths", "fcpp_distance_matrix", "fcpp_connection_matrix", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve",
     "fcpp_launch_count", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_set_profiling", "fcpp_kernel_times",
 ]
 
@@ -161,6 +161,10 @@ def load():
         L.fcpp_raster_window.argtypes = [vp, vp, i32, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
         L.fcpp_tour_lengths.restype = C.c_int
         L.fcpp_tour_lengths.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
+        L.fcpp_distance_matrix.restype = C.c_int
+        L.fcpp_distance_matrix.argtypes = [vp, vp, i32, vp, vp]
+        L.fcpp_connection_matrix.restype = C.c_int
+        L.fcpp_connection_matrix.argtypes = [vp, vp, i32, dbl, dbl, vp, vp, vp]
         L.fcpp_ga_init_population.restype = C.c_int
         L.fcpp_ga_init_population.argtypes = [vp, C.POINTER(GAConfigC), i32, vp, vp]
         L.fcpp_ga_next_size.restype = i32

@@ -311,6 +311,33 @@ int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_
 
 }  // extern "C"
 
+extern "C" {
+
+int fcpp_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (n < 0 || n > 65535 || (n > 0 && (!d_pos || !d_D))) return fail(h, FCPP_ERR_INVALID, "fcpp_distance_matrix: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_distance_matrix(h, d_pos, n, d_D, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "distance matrix kernel");
+    return FCPP_OK;
+}
+
+int fcpp_connection_matrix(fcpp_handle *h, const double *d_field_verts, int32_t n_fields, double depot_x,
+                           double depot_y, double *d_C, int32_t *d_arg, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (n_fields < 0 || n_fields > 65534 || !d_C || !d_arg || (n_fields > 0 && !d_field_verts))
+        return fail(h, FCPP_ERR_INVALID, "fcpp_connection_matrix: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_connection_matrix(h, d_field_verts, n_fields, depot_x, depot_y, d_C, d_arg,
+                                                  (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "connection matrix kernel");
+    return FCPP_OK;
+}
+
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------
 // GA evolution on the device (fcpp_ga.cu)
 // ---------------------------------------------------------------------------------------------

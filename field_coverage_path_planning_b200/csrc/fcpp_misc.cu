@@ -107,7 +107,67 @@ __global__ void argmin_final(unsigned long long *key, int64_t *cand, int n_field
     }
 }
 
+// multi_field_planner.py:263-288 ("mfp"): D[i][j] = ||pos_i - pos_j||, 0 on the diagonal
+__global__ void distance_matrix_kernel(const double *__restrict__ pos, int n, double *__restrict__ D)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n) return;
+    const double dx = pos[2 * i] - pos[2 * j], dy = pos[2 * i + 1] - pos[2 * j + 1];
+    D[(int64_t)i * n + j] = (i == j) ? 0.0 : sqrt(dx * dx + dy * dy);
+}
+
+// mfp:290-320 for every ordered pair of nodes at once.  Node 0 is the depot (one candidate point),
+// node f+1 is field f (its four vertices are both exit and entry points, mfp:140-141).
+// C[a][b] = min over (from point of a) x (to point of b) of the distance, from points in the outer
+// loop, strict '<' so the FIRST minimum wins; arg[a][b] = from_index * 4 + to_index.
+__global__ void connection_matrix_kernel(const double *__restrict__ verts, int n_fields, double depot_x,
+                                         double depot_y, double *__restrict__ Cm, int32_t *__restrict__ arg)
+{
+    const int n = n_fields + 1;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= n) return;
+    double fx[4], fy[4], tx[4], ty[4];
+    const int nf = a == 0 ? 1 : 4, nt = b == 0 ? 1 : 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        fx[k] = a == 0 ? depot_x : verts[(int64_t)(a - 1) * 8 + 2 * k];
+        fy[k] = a == 0 ? depot_y : verts[(int64_t)(a - 1) * 8 + 2 * k + 1];
+        tx[k] = b == 0 ? depot_x : verts[(int64_t)(b - 1) * 8 + 2 * k];
+        ty[k] = b == 0 ? depot_y : verts[(int64_t)(b - 1) * 8 + 2 * k + 1];
+    }
+    double best = INFINITY;
+    int bi = 0;
+    for (int p = 0; p < nf; ++p)
+        for (int q = 0; q < nt; ++q) {
+            const double dx = fx[p] - tx[q], dy = fy[p] - ty[q];
+            const double d = sqrt(dx * dx + dy * dy);
+            if (d < best) {
+                best = d;
+                bi = p * 4 + q;
+            }
+        }
+    Cm[(int64_t)a * n + b] = best;
+    arg[(int64_t)a * n + b] = bi;
+}
+
 }  // namespace
+
+cudaError_t fcpp_launch_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    distance_matrix_kernel<<<dim3((n + 127) / 128, n), 128, 0, st>>>(d_pos, n, d_D);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t fcpp_launch_connection_matrix(fcpp_handle *h, const double *d_verts, int32_t n_fields, double depot_x,
+                                          double depot_y, double *d_C, int32_t *d_arg, cudaStream_t st)
+{
+    const int n = n_fields + 1;
+    connection_matrix_kernel<<<dim3((n + 127) / 128, n), 128, 0, st>>>(d_verts, n_fields, depot_x, depot_y, d_C, d_arg);
+    h->launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t fcpp_launch_tours(fcpp_handle *h, const double *d_D, int32_t n, const int32_t *d_pop,
                               int64_t pop_size, double *d_out, double *d_fit, cudaStream_t st)

@@ -215,6 +215,21 @@ int fcpp_tour_lengths(fcpp_handle *h, const double *d_D, int32_t n, const int32_
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-field glue ("mfp" = multi_field_planner.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* mfp:263-288 _calculate_distance_matrix: d_D[i*n+j] = ||pos_i - pos_j|| (0 on the diagonal);
+ * d_pos [n][2], row 0 = depot, row f+1 = centroid of field f. */
+int fcpp_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, void *stream);
+
+/* mfp:290-320 _find_best_connection for EVERY ordered pair of nodes (node 0 = depot, node f+1 = field
+ * f whose four vertices d_field_verts[f][4][2] are its exit and entry points, mfp:123-141):
+ * d_C[a*(F+1)+b] = shortest exit-vertex -> entry-vertex distance, d_arg = from_index*4 + to_index of
+ * the FIRST minimum in the reference's loop order (strict '<', mfp:308-311). */
+int fcpp_connection_matrix(fcpp_handle *h, const double *d_field_verts, int32_t n_fields, double depot_x,
+                           double depot_y, double *d_C, int32_t *d_arg, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GA evolution on the device ("ga" = genetic_algorithm_solver.py)
  * ------------------------------------------------------------------------------------------- */
 #define FCPP_GA_MAX_TOURNAMENT 16

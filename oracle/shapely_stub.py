@@ -308,6 +308,7 @@ def install():
         pat.Polygon, pat.Rectangle = _Dummy, _Dummy
         mpl.pyplot, mpl.patches = plt, pat
         mpl.use = lambda *a, **k: None
+        mpl.rcParams = {}
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
         sys.modules["matplotlib.patches"] = pat
