@@ -32,8 +32,12 @@ constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
 constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
 constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fill), per corner
 constexpr int ICAP = 2048;      // item -> active-entry table
-constexpr int EBATCH = 4 * T;   // entries per scheduling batch
-constexpr double AMBIG_UNITS = 0.05;  // capsule boundaries: 5e-6 m certification margin
+constexpr int EPT = 2;          // entries per thread in a scheduling batch
+constexpr int EBATCH = EPT * T; // entries per scheduling batch
+// capsule boundaries: certification margin in lattice units (1e-4 m) = 0.03 + 3e-6 r.  The FP64
+// tangent lines are good to 2e-7 units; the arcs use an approximate FP32 sqrt of an exact integer
+// (relative error < 5e-7, i.e. < 5e-7 r units): at r = 1.6 m the margin is 0.078 units = 7.8e-6 m.
+constexpr double AMBIG_BASE = 0.03, AMBIG_REL = 3e-6;
 constexpr double AMBIG_Q = 1e-5;      // quad row intervals: margin in cells
 
 struct Target {
@@ -49,6 +53,7 @@ struct CoverFixed {
     int2 rbias[ROWCAP];  // per tile row: tile word index of cell i in window w = bias.w + (i >> 5)
     int scan[T];
     double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey (relative coordinates)
+    int4 qtype[2][4];       // per edge: x = +1 upper bound / -1 lower bound / 0 horizontal, y = ay, z = sign(ex)
     int2 fq[4], mq[4];      // snapped field quad and R-inset, relative to the band lattice origin
     Target tg[4];
     int nrows, total_words;
@@ -59,11 +64,11 @@ struct CoverFixed {
 
 // dynamic part, sized by the point capacity pc (>= longest polyline staged)
 struct CoverDyn {
-    int2 *pts;        // [pc] snapped points relative to their lattice origin
-    double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len of entry e = pts[e] -> pts[e+1]; oy = +inf if dy == 0
+    int2 *pts;        // [pc] snapped points relative to their lattice origin (staging; aliased by erow)
+    int2 *erow;       // [pc] per pass: first resident lattice row of the entry, its tile row
+    int4 *seg;        // [pc] entry e = pts[e] -> pts[e+1] with the lower end first: ax, ay, bx, by
+    double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len; oy = +inf if dy == 0
     double *kk;       // [pc] dx/dy
-    int *ejlo;        // [pc] first resident lattice row of the entry (per pass)
-    int *ek0;         // [pc] tile row of ejlo
     int *apre;        // [EBATCH + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries
     uint16_t *act;    // [EBATCH] active entries (batch-local index)
     uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
@@ -72,8 +77,8 @@ struct CoverDyn {
 __host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 __host__ __device__ inline size_t cover_smem_bytes(int pc)
 {
-    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(double2) * pc) + a16(sizeof(double) * pc) +
-           2 * a16(sizeof(int) * pc) + a16(sizeof(int) * (EBATCH + 1)) + a16(sizeof(uint16_t) * EBATCH) +
+    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(int4) * pc) + a16(sizeof(double2) * pc) +
+           a16(sizeof(double) * pc) + a16(sizeof(int) * (EBATCH + 1)) + a16(sizeof(uint16_t) * EBATCH) +
            a16(sizeof(uint16_t) * ICAP);
 }
 __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
@@ -81,15 +86,14 @@ __device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
     CoverDyn d;
     size_t o = a16(sizeof(CoverFixed));
     d.pts = (int2 *)(base + o);
+    d.erow = d.pts;  // the points are dead once setup_entries has built the segment records
     o += a16(sizeof(int2) * pc);
+    d.seg = (int4 *)(base + o);
+    o += a16(sizeof(int4) * pc);
     d.og = (double2 *)(base + o);
     o += a16(sizeof(double2) * pc);
     d.kk = (double *)(base + o);
     o += a16(sizeof(double) * pc);
-    d.ejlo = (int *)(base + o);
-    o += a16(sizeof(int) * pc);
-    d.ek0 = (int *)(base + o);
-    o += a16(sizeof(int) * pc);
     d.apre = (int *)(base + o);
     o += a16(sizeof(int) * (EBATCH + 1));
     d.act = (uint16_t *)(base + o);
@@ -150,54 +154,52 @@ __device__ __noinline__ bool in_quad(const int2 *q, int px, int py)
 }
 
 // per-edge constants of a convex quad for the row-interval evaluation
-__device__ void quad_edges_setup(const int2 *q, double (*e)[3], int k)
+__device__ void quad_edges_setup(const int2 *q, double (*e)[3], int4 *ty, int k)
 {
     const int k1 = (k + 1) & 3;
-    const double ex = (double)(q[k1].x - q[k].x), ey = (double)(q[k1].y - q[k].y);
+    const int exi = q[k1].x - q[k].x, eyi = q[k1].y - q[k].y;
+    const double ex = (double)exi, ey = (double)eyi;
     e[k][0] = (double)q[k].x;
     e[k][1] = (double)q[k].y;
     e[k][2] = (ey != 0.0) ? ex / ey : 0.0;
+    ty[k] = make_int4(eyi > 0 ? 1 : (eyi < 0 ? -1 : 0), q[k].y, exi > 0 ? 1 : (exi < 0 ? -1 : 0), 0);
 }
 
 // inclusive lattice-index interval [a, b] of row cy (relative) inside the CLOSED convex quad
-// (empty: a > b).  FP64 boundary + exact test of a lattice point only when the boundary is within
-// AMBIG_Q of it.
-__device__ void quad_row_interval(const int2 *q, const double (*e)[3], int cy, int H, double invH, int nx, int &a,
-                                  int &b)
+// (empty: a > b).  Every edge is a half-plane bound for every row (convexity): edges going up
+// bound x from above, edges going down from below, horizontal edges decide emptiness.  FP64
+// boundary + exact test of a lattice point only when the boundary is within AMBIG_Q of it.
+__device__ __forceinline__ void quad_row_interval(const int2 *q, const double (*e)[3], const int4 *ty, int cy, int H,
+                                                  double invH, int nx, int &a, int &b)
 {
     double lo = -1e300, hi = 1e300;
     bool empty = false;
     const double y = (double)cy;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int k1 = (k + 1) & 3;
-        const int eyi = q[k1].y - q[k].y;
+        const int4 t = ty[k];
         const double x = e[k][0] + e[k][2] * (y - e[k][1]);
-        if (eyi > 0)
-            hi = fmin(hi, x);
-        else if (eyi < 0)
-            lo = fmax(lo, x);
-        else if ((int64_t)(q[k1].x - q[k].x) * (cy - q[k].y) < 0)
+        if (t.x > 0)
+            hi = (x < hi) ? x : hi;
+        else if (t.x < 0)
+            lo = (x > lo) ? x : lo;
+        else if (t.z * (cy - t.y) < 0)
             empty = true;
     }
-    if (empty || !(lo <= hi + 2.0)) {
-        a = 0;
-        b = -1;
-        return;
-    }
-    const double tl = fmin(fmax(lo * invH, -1.0e9), 1.0e9), th = fmin(fmax(hi * invH, -1.0e9), 1.0e9);
-    const int il = __double2int_ru(tl), ih = __double2int_rd(th);  // closed: i >= tl, i <= th
-    int ia = il, ib = ih;
+    a = 0;
+    b = -1;
+    if (empty || !(lo <= hi + 2.0)) return;
+    // |lo|, |hi| < 2^31 here (they bound a non-empty row of a quad whose coordinates fit 2^30)
+    const double tl = lo * invH, th = hi * invH;
     const int rl = __double2int_rn(tl), rh = __double2int_rn(th);
-    if (fabs(tl - (double)rl) < AMBIG_Q) ia = in_quad(q, rl * H, cy) ? rl : rl + 1;
-    if (fabs(th - (double)rh) < AMBIG_Q) ib = in_quad(q, rh * H, cy) ? rh : rh - 1;
+    const double dl = tl - (double)rl, dh = th - (double)rh;
+    int ia = rl + (dl > 0.0 ? 1 : 0);  // closed: smallest i >= tl
+    int ib = rh - (dh < 0.0 ? 1 : 0);  //         largest  i <= th
+    if (fabs(dl) < AMBIG_Q) ia = in_quad(q, rl * H, cy) ? rl : rl + 1;
+    if (fabs(dh) < AMBIG_Q) ib = in_quad(q, rh * H, cy) ? rh : rh - 1;
     ia = max(ia, 0);
     ib = min(ib, nx - 1);
-    if (ia > ib) {
-        a = 0;
-        b = -1;
-        return;
-    }
+    if (ia > ib) return;
     a = ia;
     b = ib;
 }
@@ -210,19 +212,21 @@ __device__ __forceinline__ void or_span(uint32_t *base, int ia, int ib)
         atomicOr(base + w0, m0 & m1);
     } else {
         atomicOr(base + w0, m0);
-        for (int w = w0 + 1; w < w1; ++w) atomicOr(base + w, 0xffffffffu);
+        // interior words: a plain store of all-ones is a benign race with the atomics of other
+        // lanes (whatever they OR in is a subset)
+        for (int w = w0 + 1; w < w1; ++w) base[w] = 0xffffffffu;
         atomicOr(base + w1, m1);
     }
 }
 
-// block-wide inclusive scan of 4 ints per thread (entries 4*tid .. 4*tid+3); returns the total
-__device__ int block_scan4(int (&v)[4], int *sh /*[T]*/)
+// block-wide inclusive scan of N ints per thread (entries N*tid .. N*tid+N-1); returns the total
+template <int N>
+__device__ int block_scan(int (&v)[N], int *sh /*[T]*/)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v[1] += v[0];
-    v[2] += v[1];
-    v[3] += v[2];
-    int inc = v[3];
+#pragma unroll
+    for (int q = 1; q < N; ++q) v[q] += v[q - 1];
+    int inc = v[N - 1];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int o = __shfl_up_sync(0xffffffffu, inc, d);
@@ -231,20 +235,29 @@ __device__ int block_scan4(int (&v)[4], int *sh /*[T]*/)
     __syncthreads();
     if (lane == 31) sh[warp] = inc;
     __syncthreads();
-    int woff = 0, total = 0;
+    // the NWARP warp totals: one per lane, prefix by shuffles
+    int wt = (lane < NWARP) ? sh[lane] : 0, wi = wt;
 #pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
-        const int x = sh[w];
-        if (w < warp) woff += x;
-        total += x;
+    for (int d = 1; d < NWARP; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += o;
     }
-    const int off = woff + inc - v[3];
+    const int total = __shfl_sync(0xffffffffu, wi, NWARP - 1);
+    const int woff = __shfl_sync(0xffffffffu, wi - wt, warp);
+    const int off = woff + inc - v[N - 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] += off;
+    for (int q = 0; q < N; ++q) v[q] += off;
     return total;
 }
 
-// tangent offsets and slope of entries [e0, e0 + n): once per polyline
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// segment records of entries [e0, e0 + n): lower end first, tangent offsets and slope; once per polyline
 __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
 {
     for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
@@ -254,6 +267,7 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
             p = q;
             q = t;
         }
+        d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
         const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
         if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
             d.og[e] = make_double2(0.0, INFINITY);
@@ -266,9 +280,10 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
     }
 }
 
-// Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entry e = pts[e] -> pts[e+1]; entries that
-// join two different polylines are masked by `tgt(e) < 0`) into the resident tile rows of their
-// targets.  All targets of one call share the lattice pitch H.
+// Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entries that join two different polylines
+// are masked by `tgt(e) < 0`) into the resident tile rows of their targets.  All targets of one
+// call share the lattice pitch H.  Must be called after a __syncthreads() that follows
+// setup_entries (the staging points are overwritten by the per-pass row records).
 template <class TgFn>
 __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int r, int H,
                                double invH)
@@ -276,42 +291,41 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double r2d = (double)r * (double)r;
     const int64_t r2 = (int64_t)r * r;
-    const double amb = AMBIG_UNITS * invH;
+    const double amb = (AMBIG_BASE + AMBIG_REL * (double)r) * invH;
     for (int eb = 0; eb < n_ent; eb += EBATCH) {
         const int nb = min(EBATCH, n_ent - eb);
         // ---- resident rows each entry's capsule can touch; packed (active << 21 | rows) ----
-        int rows[4], inc[4];
+        int rows[EPT], inc[EPT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int le = tid * 4 + q;
+        for (int q = 0; q < EPT; ++q) {
+            const int le = tid * EPT + q;
             rows[q] = 0;
             if (le < nb) {
                 const int e = e0 + eb + le;
                 const int ti = tgt(e);
                 if (ti >= 0) {
-                    const int2 a = d.pts[e], b = d.pts[e + 1];
+                    const int4 sg = d.seg[e];
                     const Target t = s.tg[ti];
-                    int jlo = floor_div_i(min(a.y, b.y) - r, H, invH) + 1;      // cy > ymin - r
-                    int jhi = -floor_div_i(-(max(a.y, b.y) + r), H, invH) - 1;  // cy < ymax + r
+                    int jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
+                    int jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
                     jlo = max(jlo, t.j0);
                     jhi = min(jhi, t.j0 + t.nrows - 1);
                     if (jhi >= jlo) rows[q] = jhi - jlo + 1;
-                    d.ejlo[e] = jlo;
-                    d.ek0[e] = jlo - t.j0 + t.koff;
+                    d.erow[e] = make_int2(jlo, jlo - t.j0 + t.koff);
                 }
             }
             inc[q] = rows[q] ? ((1 << 21) | rows[q]) : 0;
         }
-        const unsigned tot = (unsigned)block_scan4(inc, s.scan);
+        const unsigned tot = (unsigned)block_scan<EPT>(inc, s.scan);
         const int n_act = (int)(tot >> 21), n_pairs = (int)(tot & 0x1fffffu);
         const int n_items = (n_pairs + 31) >> 5;
         const bool table = n_items <= ICAP;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < EPT; ++q) {
             if (rows[q]) {
                 const int ai = (int)((unsigned)inc[q] >> 21) - 1;
                 const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
-                d.act[ai] = (uint16_t)(tid * 4 + q);
+                d.act[ai] = (uint16_t)(tid * EPT + q);
                 d.apre[ai] = first;
                 if (table)
                     for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
@@ -320,58 +334,60 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
         if (tid == 0) d.apre[n_act] = n_pairs;
         __syncthreads();
         for (int item = warp; item < n_items; item += NWARP) {
-            const int p = 32 * item + lane;
-            if (p >= n_pairs) continue;
-            int ai;
+            const int pbase = 32 * item;
+            // ---- pair -> active entry: the entry boundaries inside this item as a bit mask ----
+            int base_ai;
             if (table) {
-                ai = d.item_first[item];
-                while (p >= d.apre[ai + 1]) ++ai;
-            } else {  // upper_bound over the pair prefix
-                int lo = 0, hi = n_act - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (d.apre[mid] <= p)
-                        lo = mid;
-                    else
-                        hi = mid - 1;
+                base_ai = d.item_first[item];
+            } else {  // upper_bound over the pair prefix (one lane), then broadcast
+                int lo = 0;
+                if (lane == 0) {
+                    int hi = n_act - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (d.apre[mid] <= pbase)
+                            lo = mid;
+                        else
+                            hi = mid - 1;
+                    }
                 }
-                ai = lo;
+                base_ai = __shfl_sync(0xffffffffu, lo, 0);
             }
+            const int bidx = base_ai + 1 + lane;
+            const int bnd = (bidx <= n_act) ? d.apre[bidx] : 0x7fffffff;  // > pbase: entry base_ai holds pair pbase
+            const unsigned mbit = (bnd < pbase + 32) ? (1u << ((bnd - pbase) & 31)) : 0u;
+            const unsigned bmask = __reduce_or_sync(0xffffffffu, mbit);
+            const int p = pbase + lane;
+            if (p >= n_pairs) continue;
+            const int ai = base_ai + __popc(bmask & ((2u << lane) - 1u));
             const int e = e0 + eb + d.act[ai];
             const int qrow = p - d.apre[ai];
-            const int k = d.ek0[e] + qrow;
-            const int cy = (d.ejlo[e] + qrow) * H;
-            int2 a = d.pts[e], b = d.pts[e + 1];
-            if (b.y < a.y || (b.y == a.y && b.x < a.x)) {
-                const int2 tmp = a;
-                a = b;
-                b = tmp;
-            }
+            const int4 sg = d.seg[e];
+            const int2 er = d.erow[e];
             const double2 og = d.og[e];
             const double kk = d.kk[e];
-            const double ax = (double)a.x, bx = (double)b.x;
-            const double wa = (double)(cy - a.y), wb = (double)(cy - b.y);
-            // half chords of the end discs: FP32 sqrt of an exact integer (|error| < 2e-3 units)
-            const double hA = (double)sqrtf((float)fmax(r2d - wa * wa, 0.0));
-            const double hB = (double)sqrtf((float)fmax(r2d - wb * wb, 0.0));
+            const int k = er.y + qrow;
+            const int cy = (er.x + qrow) * H;
+            const double ax = (double)sg.x, bx = (double)sg.z;
+            const double wa = (double)(cy - sg.y), wb = (double)(cy - sg.w);
+            // half chords of the end discs: approximate FP32 sqrt of an exact integer
+            const double ta = r2d - wa * wa, tb = r2d - wb * wb;
+            const double hA = (double)sqrt_approx((float)(ta > 0.0 ? ta : 0.0));
+            const double hB = (double)sqrt_approx((float)(tb > 0.0 ? tb : 0.0));
             // left: arc A below yL0 = ay+oy | tangent line up to yL1 = by+oy | arc B;  right: -oy
             const double xl = (wa < og.y) ? ax - hA : ((wb <= og.y) ? (ax - og.x) + (wa - og.y) * kk : bx - hB);
             const double xr = (wa < -og.y) ? ax + hA : ((wb <= -og.y) ? (ax + og.x) + (wa + og.y) * kk : bx + hB);
-            // lattice indices strictly inside (xl, xr); certified, ambiguous ends decided exactly
+            // lattice indices strictly inside (xl, xr); |xl|, |xr| < 2^31.  Certified: an end within
+            // `amb` of a lattice point is decided by the exact integer predicate
             const double tl = xl * invH, th = xr * invH;
-            // (the conversions saturate; the clamps keep il+2 / ih-2 from wrapping)
-            const int il = min(max(__double2int_rd(tl), -(1 << 30)), 1 << 30);
-            const int ih = min(max(__double2int_ru(th), -(1 << 30)), 1 << 30);
-            int ia = il + 1, ib = ih - 1;
-            const double fl = tl - (double)il, fh = (double)ih - th;
-            if (fl < amb)
-                ia = near_seg((int64_t)il * H, cy, a.x, a.y, b.x, b.y, r2) ? il : il + 1;
-            else if (fl > 1.0 - amb)
-                ia = near_seg((int64_t)(il + 1) * H, cy, a.x, a.y, b.x, b.y, r2) ? il + 1 : il + 2;
-            if (fh < amb)
-                ib = near_seg((int64_t)ih * H, cy, a.x, a.y, b.x, b.y, r2) ? ih : ih - 1;
-            else if (fh > 1.0 - amb)
-                ib = near_seg((int64_t)(ih - 1) * H, cy, a.x, a.y, b.x, b.y, r2) ? ih - 1 : ih - 2;
+            const int rl = __double2int_rn(tl), rh = __double2int_rn(th);
+            const double dl = tl - (double)rl, dh = th - (double)rh;
+            int ia = rl + (dl >= 0.0 ? 1 : 0);  // smallest i > tl
+            int ib = rh - (dh <= 0.0 ? 1 : 0);  // largest  i < th
+            if (fabs(dl) < amb || fabs(dh) < amb) {
+                if (fabs(dl) < amb) ia = near_seg((int64_t)rl * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rl : rl + 1;
+                if (fabs(dh) < amb) ib = near_seg((int64_t)rh * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rh : rh - 1;
+            }
             const int4 w = s.rwin[k];
             const int2 bias = s.rbias[k];
             const int s1 = max(ia, w.x), e1 = min(ib, w.y);
@@ -574,8 +590,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 d.pts[k] = make_int2((int)(qfix(x) - Xc0), (int)(qfix(y) - Yc0));
             }
             __syncthreads();
-            if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], tid);
-            if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], tid - 4);
+            if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
+            if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
             setup_entries(d, 0, nh - 1, rd);
             __syncthreads();
             unsigned long long my_total = 0ull, my_cov = 0ull;
@@ -584,10 +600,10 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 // --- how many rows to try: from the word count of the first row (one thread) ---
                 if (tid == 0) {
                     int a0, b0, a1, b1;
-                    quad_row_interval(s.fq, s.qedge[0], j0 * H, H, invH, nx, a0, b0);
-                    quad_row_interval(s.mq, s.qedge[1], j0 * H, H, invH, nx, a1, b1);
+                    quad_row_interval(s.fq, s.qedge[0], s.qtype[0], j0 * H, H, invH, nx, a0, b0);
+                    quad_row_interval(s.mq, s.qedge[1], s.qtype[1], j0 * H, H, invH, nx, a1, b1);
                     const int w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
-                    const int rt = 2 * TW / (w0 > 0 ? w0 : 1);
+                    const int rt = (5 * TW) / (4 * (w0 > 0 ? w0 : 1)) + 8;
                     s.cnt[0] = min(max(rt, 8), min(ROWCAP, ny - j0));
                 }
                 __syncthreads();
@@ -604,8 +620,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     if (k < rows_try) {
                         int fa, fb, ma, mb;
                         const int cy = (j0 + k) * H;
-                        quad_row_interval(s.fq, s.qedge[0], cy, H, invH, nx, fa, fb);
-                        quad_row_interval(s.mq, s.qedge[1], cy, H, invH, nx, ma, mb);
+                        quad_row_interval(s.fq, s.qedge[0], s.qtype[0], cy, H, invH, nx, fa, fb);
+                        quad_row_interval(s.mq, s.qedge[1], s.qtype[1], cy, H, invH, nx, ma, mb);
                         if (fa <= fb) {
                             if (ma <= mb) {  // the inset lies inside the field: clamp defensively
                                 ma = max(ma, fa);
@@ -624,7 +640,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     s.nrows = 0;
                     s.total_words = 0;
                 }
-                block_scan4(wsum, s.scan);  // inclusive prefix of the row word counts (syncs inside)
+                block_scan<4>(wsum, s.scan);  // inclusive prefix of the row word counts (syncs inside)
                 int fit_rows = 0, fit_words = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
