@@ -12,7 +12,9 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfcpp.so")
+# FCPP_LIB selects another build of the same library (A/B timing of kernel variants); there is still
+# no fallback: the file must exist and export the ABI
+LIB_PATH = os.environ.get("FCPP_LIB") or os.path.join(_HERE, "libfcpp.so")
 ABI_VERSION = 1
 
 FLAG_CORNER_MASK = 3

@@ -28,10 +28,10 @@ namespace {
 
 constexpr int T = FCPP_COVER_THREADS;
 constexpr int NWARP = T / 32;
-constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
+constexpr int TW = 7680;        // occupancy tile, 32-bit words (30 KB)
 constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
 constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fill), per corner
-constexpr int ICAP = 2048;      // item -> active-entry table
+constexpr int ICAP = 1024;      // item -> active-entry table
 constexpr int EPT = 2;          // entries per thread in a scheduling batch
 constexpr int EBATCH = EPT * T; // entries per scheduling batch
 // capsule boundaries: certification margin in lattice units (1e-4 m) = 0.03 + 3e-6 r.  The FP64
@@ -39,6 +39,25 @@ constexpr int EBATCH = EPT * T; // entries per scheduling batch
 // (relative error < 5e-7, i.e. < 5e-7 r units): at r = 1.6 m the margin is 0.078 units = 7.8e-6 m.
 constexpr double AMBIG_BASE = 0.03, AMBIG_REL = 3e-6;
 constexpr double AMBIG_Q = 1e-5;      // quad row intervals: margin in cells
+
+// Straight runs (>= RUN_MIN_SEGS collinear segments, e.g. a 20-point headland straight or a reverse
+// fill): inside the run's tangent zone the union of the sub-capsules is one trapezoid per row, known
+// up to the deviation RUN_DELTA of the snapped points from their chord.  The trapezoid is written
+// by ONE entry with two linear boundaries (no square roots); lattice points within the margin of a
+// boundary are decided afterwards by the exact predicate over the run's sub-segments.
+constexpr int RCAP = 64;            // runs per staging
+constexpr int QCAP = 128;           // deferred boundary points per raster batch
+constexpr int RUN_MIN_SEGS = 4;
+constexpr int RUN_MIN_ROWS = 8;
+constexpr double RUN_DELTA = 2.0;   // lattice units (2e-4 m)
+constexpr double RUN_MAX_MCELLS = 0.2;
+
+struct Run {
+    int i0, i1;    // sub-segment entries [i0, i1)
+    int j0, j1;    // lattice rows of the trapezoid zone (inclusive)
+    float mcells;  // boundary margin in cells: (RUN_DELTA + 0.05) * len / |dy| / H
+    int pad[3];
+};
 
 struct Target {
     int j0, nrows;  // lattice rows [j0, j0 + nrows) are resident
@@ -51,12 +70,17 @@ struct CoverFixed {
     uint32_t tile[TW];
     int4 rwin[ROWCAP];   // per tile row: window 1 cells [x, y], window 2 cells [z, w] (empty: lo > hi)
     int2 rbias[ROWCAP];  // per tile row: tile word index of cell i in window w = bias.w + (i >> 5)
-    int scan[T];
+    int scan[32];
+    Run runs[RCAP];
+    int4 queue[QCAP];       // deferred boundary points: lattice column, tile row, cy, run
     double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey (relative coordinates)
     int4 qtype[2][4];       // per edge: x = +1 upper bound / -1 lower bound / 0 horizontal, y = ay, z = sign(ex)
     int2 fq[4], mq[4];      // snapped field quad and R-inset, relative to the band lattice origin
     Target tg[4];
     int nrows, total_words;
+    int next_item;
+    int n_runs, qn;
+    int next_w0;
     int cnt[8];
     unsigned long long acc[2];
     uint64_t bar;
@@ -69,36 +93,34 @@ struct CoverDyn {
     int4 *seg;        // [pc] entry e = pts[e] -> pts[e+1] with the lower end first: ax, ay, bx, by
     double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len; oy = +inf if dy == 0
     double *kk;       // [pc] dx/dy
+    uint8_t *runid;   // [pc] run of a sub-segment entry (0xff: none)
     int *apre;        // [EBATCH + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries
     uint16_t *act;    // [EBATCH] active entries (batch-local index)
     uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
 };
 
 __host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
+// pc is a multiple of 16, so every array below starts 16-byte aligned without further rounding
+constexpr size_t DYN_TAIL = sizeof(int) * (EBATCH + 16) + sizeof(uint16_t) * EBATCH + sizeof(uint16_t) * ICAP;
 __host__ __device__ inline size_t cover_smem_bytes(int pc)
 {
-    return a16(sizeof(CoverFixed)) + a16(sizeof(int2) * pc) + a16(sizeof(int4) * pc) + a16(sizeof(double2) * pc) +
-           a16(sizeof(double) * pc) + a16(sizeof(int) * (EBATCH + 1)) + a16(sizeof(uint16_t) * EBATCH) +
-           a16(sizeof(uint16_t) * ICAP);
+    return a16(sizeof(CoverFixed)) +
+           (size_t)pc * (sizeof(int2) + sizeof(int4) + sizeof(double2) + sizeof(double) + sizeof(uint8_t)) + DYN_TAIL;
 }
-__device__ inline CoverDyn carve_dyn(unsigned char *base, int pc)
+__device__ __forceinline__ CoverDyn carve_dyn(unsigned char *base, int pc)
 {
     CoverDyn d;
-    size_t o = a16(sizeof(CoverFixed));
-    d.pts = (int2 *)(base + o);
+    unsigned char *p = base + a16(sizeof(CoverFixed));
+    d.pts = (int2 *)p;
     d.erow = d.pts;  // the points are dead once setup_entries has built the segment records
-    o += a16(sizeof(int2) * pc);
-    d.seg = (int4 *)(base + o);
-    o += a16(sizeof(int4) * pc);
-    d.og = (double2 *)(base + o);
-    o += a16(sizeof(double2) * pc);
-    d.kk = (double *)(base + o);
-    o += a16(sizeof(double) * pc);
-    d.apre = (int *)(base + o);
-    o += a16(sizeof(int) * (EBATCH + 1));
-    d.act = (uint16_t *)(base + o);
-    o += a16(sizeof(uint16_t) * EBATCH);
-    d.item_first = (uint16_t *)(base + o);
+    d.seg = (int4 *)(p + (size_t)pc * 8);
+    d.og = (double2 *)(p + (size_t)pc * 24);
+    d.kk = (double *)(p + (size_t)pc * 40);
+    d.runid = (uint8_t *)(p + (size_t)pc * 48);
+    p += (size_t)pc * 49;
+    d.apre = (int *)p;
+    d.act = (uint16_t *)(p + sizeof(int) * (EBATCH + 16));
+    d.item_first = d.act + EBATCH;
     return d;
 }
 
@@ -268,6 +290,7 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
             q = t;
         }
         d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
+        d.runid[e] = 0;
         const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
         if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
             d.og[e] = make_double2(0.0, INFINITY);
@@ -280,20 +303,150 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
     }
 }
 
+__device__ __forceinline__ bool straight_joint(const int2 *p, int i)  // joint at point i of a polyline
+{
+    const double ax = (double)(p[i].x - p[i - 1].x), ay = (double)(p[i].y - p[i - 1].y);
+    const double bx = (double)(p[i + 1].x - p[i].x), by = (double)(p[i + 1].y - p[i].y);
+    if ((ax == 0.0 && ay == 0.0) || (bx == 0.0 && by == 0.0)) return false;
+    if (ax * bx + ay * by <= 0.0) return false;
+    const double cr = ax * by - ay * bx, sx = ax + bx, sy = ay + by;
+    return cr * cr <= (RUN_DELTA * RUN_DELTA) * (sx * sx + sy * sy);
+}
+
+// Finds the straight runs of the polyline pts[p0 .. p0+np) (entries p0 .. p0+np-2), verifies each
+// against its chord and appends a trapezoid entry per run at tbase + slot.  Block-wide (every
+// thread must call it): one thread per joint / point / segment in every phase, so that nobody
+// waits on serial chord checks.  Call after the __syncthreads() that follows setup_entries and
+// before the first raster_entries (the staging points are still live).
+// d.runid[e]: bit 7 = joint at the segment's first point is straight (temporary), final value
+// 0x40 | slot for the sub-segments of a run, 0 otherwise.  d.apre is scratch here.
+template <class MergeFn>
+__device__ void build_runs(CoverFixed &s, const CoverDyn &d, int p0, int np, int tbase, int H, double invH, double rd,
+                           MergeFn mergeable)
+{
+    const int ns = np - 1;  // segments
+    if (ns > EBATCH || ns < RUN_MIN_SEGS) return;
+    const int2 *P = d.pts + p0;
+    uint8_t *F = d.runid + p0;
+    for (int i = threadIdx.x; i < ns; i += T) {
+        const bool st = i > 0 && mergeable(p0 + i - 1) && mergeable(p0 + i) && straight_joint(P, i);
+        F[i] = st ? 0x80 : 0;
+        d.apre[i] = 0;
+    }
+    __syncthreads();
+    // every interior point of a chain against the chain's chord
+    for (int j = threadIdx.x; j < ns; j += T) {
+        if (!(F[j] & 0x80)) continue;
+        int i = j - 1;
+        while (F[i] & 0x80) --i;  // F[0] is never set
+        int e = j + 1;
+        while (e < ns && (F[e] & 0x80)) ++e;
+        if (e - i < RUN_MIN_SEGS) continue;
+        const int2 a = P[i], b = P[e];
+        const double cx = (double)(b.x - a.x), cy = (double)(b.y - a.y), len2 = cx * cx + cy * cy;
+        const double wx = (double)(P[j].x - a.x), wy = (double)(P[j].y - a.y);
+        const double ux = (double)(P[j - 1].x - a.x), uy = (double)(P[j - 1].y - a.y);
+        const double cr = wx * cy - wy * cx, pj = wx * cx + wy * cy, pp = ux * cx + uy * cy;
+        if (!((cr * cr <= (RUN_DELTA * RUN_DELTA) * len2) && (pj > pp) && (pj < len2))) atomicOr(&d.apre[i], 1);
+    }
+    __syncthreads();
+    // chain heads: geometry of the trapezoid zone, slot, trapezoid entry
+    for (int i = threadIdx.x; i < ns; i += T) {
+        if ((F[i] & 0x80) || !mergeable(p0 + i) || i + 1 >= ns || !(F[i + 1] & 0x80)) continue;
+        int e = i + 1;
+        while (e < ns && (F[e] & 0x80)) ++e;
+        if (e - i < RUN_MIN_SEGS || (d.apre[i] & 1)) continue;
+        int2 a = P[i], b = P[e];
+        if (b.y < a.y) {
+            const int2 t = a;
+            a = b;
+            b = t;
+        }
+        const int dyi = b.y - a.y;
+        if (dyi <= 0) continue;  // horizontal chord: no tangent zone on rows
+        const double dx = (double)(b.x - a.x), dy = (double)dyi, len = sqrt(dx * dx + dy * dy);
+        const double m = (RUN_DELTA + 0.05) * len / dy;  // x shift of a tangent line moved by RUN_DELTA
+        if (m * invH > RUN_MAX_MCELLS) continue;
+        const double oy = fabs(rd * dx / len);
+        const double y0 = (double)a.y + oy + (RUN_DELTA + 1.0), y1 = (double)b.y - oy - (RUN_DELTA + 1.0);
+        if (!(y1 - y0 >= (double)(RUN_MIN_ROWS) * (double)H)) continue;
+        const int j0 = __double2int_ru(y0 * invH) + 1, j1 = __double2int_rd(y1 * invH) - 1;  // one row of slack
+        if (j1 - j0 + 1 < RUN_MIN_ROWS) continue;
+        const int slot = atomicAdd(&s.n_runs, 1);
+        if (slot >= RCAP) continue;
+        Run R;
+        R.i0 = p0 + i;
+        R.i1 = p0 + e;
+        R.j0 = j0;
+        R.j1 = j1;
+        R.mcells = (float)(m * invH);
+        R.pad[0] = R.pad[1] = R.pad[2] = 0;
+        s.runs[slot] = R;
+        d.seg[tbase + slot] = make_int4(a.x, a.y, b.x, b.y);
+        d.og[tbase + slot] = make_double2(rd * dy / len, rd * dx / len);
+        d.kk[tbase + slot] = dx / dy;
+        d.apre[i] = (slot + 1) << 8;
+    }
+    __syncthreads();
+    // every segment learns its run from its chain head
+    int rid[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        const int i = threadIdx.x + q * T;
+        rid[q] = 0;
+        if (i < ns) {
+            int h = i;
+            while (F[h] & 0x80) --h;
+            const int v = d.apre[h] >> 8;
+            if (v) rid[q] = 0x40 | (v - 1);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        const int i = threadIdx.x + q * T;
+        if (i < ns) F[i] = (uint8_t)rid[q];
+    }
+}
+
+// exact decision of one deferred boundary point of a run: inside iff within r of a sub-segment
+__device__ __noinline__ void resolve_run_point(CoverFixed &s, const CoverDyn &d, int4 q, int H, int64_t r2)
+{
+    const Run R = s.runs[q.w];
+    const int64_t px = (int64_t)q.x * H;
+    bool in = false;
+    for (int j = R.i0; j < R.i1 && !in; ++j) {
+        const int4 g = d.seg[j];
+        in = near_seg(px, q.z, g.x, g.y, g.z, g.w, r2);
+    }
+    if (!in) return;
+    const int4 w = s.rwin[q.y];
+    const int2 bias = s.rbias[q.y];
+    if (q.x >= w.x && q.x <= w.y)
+        atomicOr(s.tile + bias.x + (q.x >> 5), 1u << (q.x & 31));
+    else if (q.x >= w.z && q.x <= w.w)
+        atomicOr(s.tile + bias.y + (q.x >> 5), 1u << (q.x & 31));
+}
+
 // Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entries that join two different polylines
 // are masked by `tgt(e) < 0`) into the resident tile rows of their targets.  All targets of one
 // call share the lattice pitch H.  Must be called after a __syncthreads() that follows
 // setup_entries (the staging points are overwritten by the per-pass row records).
+// Logical entries [0, n_ent) are the segments e0 + i, logical entries [n_ent, n_ent + n_t) the
+// trapezoids of the runs 0 .. n_t-1 (records at t0 + slot); a sub-segment of a run skips the rows
+// its run's trapezoid writes.
 template <class TgFn>
 __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int r, int H,
-                               double invH)
+                               double invH, int t0 = 0, int n_t = 0)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double r2d = (double)r * (double)r;
     const int64_t r2 = (int64_t)r * r;
     const double amb = (AMBIG_BASE + AMBIG_REL * (double)r) * invH;
-    for (int eb = 0; eb < n_ent; eb += EBATCH) {
-        const int nb = min(EBATCH, n_ent - eb);
+    const int n_log = n_ent + n_t;
+    for (int eb = 0; eb < n_log; eb += EBATCH) {
+        const int nb = min(EBATCH, n_log - eb);
+        if (tid == 0) s.qn = 0;
         // ---- resident rows each entry's capsule can touch; packed (active << 21 | rows) ----
         int rows[EPT], inc[EPT];
 #pragma unroll
@@ -301,13 +454,35 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const int le = tid * EPT + q;
             rows[q] = 0;
             if (le < nb) {
-                const int e = e0 + eb + le;
-                const int ti = tgt(e);
+                const int lg = eb + le;
+                int e, ti, jlo, jhi;
+                if (lg < n_ent) {
+                    e = e0 + lg;
+                    ti = tgt(e);
+                    if (ti >= 0) {
+                        const int4 sg = d.seg[e];
+                        jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
+                        jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
+                        const int rid = d.runid[e];
+                        if (rid & 0x40) {  // the run's trapezoid owns rows [j0, j1]
+                            const int tj0 = s.runs[rid & 0x3f].j0, tj1 = s.runs[rid & 0x3f].j1;
+                            if (jlo >= tj0 && jhi <= tj1)
+                                jhi = jlo - 1;
+                            else if (jlo >= tj0)
+                                jlo = max(jlo, tj1 + 1);
+                            else if (jhi <= tj1)
+                                jhi = min(jhi, tj0 - 1);
+                        }
+                    }
+                } else {
+                    const Run R = s.runs[lg - n_ent];
+                    e = t0 + (lg - n_ent);
+                    ti = tgt(R.i0);
+                    jlo = R.j0;
+                    jhi = R.j1;
+                }
                 if (ti >= 0) {
-                    const int4 sg = d.seg[e];
                     const Target t = s.tg[ti];
-                    int jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
-                    int jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
                     jlo = max(jlo, t.j0);
                     jhi = min(jhi, t.j0 + t.nrows - 1);
                     if (jhi >= jlo) rows[q] = jhi - jlo + 1;
@@ -331,10 +506,22 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                     for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
             }
         }
-        if (tid == 0) d.apre[n_act] = n_pairs;
+        if (tid == 0) {
+            d.apre[n_act] = n_pairs;
+            s.next_item = NWARP;
+        }
         __syncthreads();
-        for (int item = warp; item < n_items; item += NWARP) {
+        // items are handed out dynamically (the first one statically): their cost varies with the
+        // span lengths, and the block barrier below waits for the slowest warp
+        for (int item = warp; item < n_items;) {
             const int pbase = 32 * item;
+#ifdef FCPP_DYNAMIC_ITEMS
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&s.next_item, 1);
+            const int next_item = __shfl_sync(0xffffffffu, nxt, 0);
+#else
+            const int next_item = item + NWARP;
+#endif
             // ---- pair -> active entry: the entry boundaries inside this item as a bit mask ----
             int base_ai;
             if (table) {
@@ -358,9 +545,12 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const unsigned mbit = (bnd < pbase + 32) ? (1u << ((bnd - pbase) & 31)) : 0u;
             const unsigned bmask = __reduce_or_sync(0xffffffffu, mbit);
             const int p = pbase + lane;
+            item = next_item;
             if (p >= n_pairs) continue;
             const int ai = base_ai + __popc(bmask & ((2u << lane) - 1u));
-            const int e = e0 + eb + d.act[ai];
+            const int lg = eb + d.act[ai];
+            const bool trap = lg >= n_ent;
+            const int e = trap ? t0 + (lg - n_ent) : e0 + lg;
             const int qrow = p - d.apre[ai];
             const int4 sg = d.seg[e];
             const int2 er = d.erow[e];
@@ -370,6 +560,32 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const int cy = (er.x + qrow) * H;
             const double ax = (double)sg.x, bx = (double)sg.z;
             const double wa = (double)(cy - sg.y), wb = (double)(cy - sg.w);
+            int ia, ib;
+            if (trap) {
+                // tangent zone of a straight run: two lines; points within the run's margin of a
+                // line are decided later by the exact predicate over the sub-segments
+                const double mc = (double)s.runs[lg - n_ent].mcells;
+                const double tl = ((ax - og.x) + (wa - og.y) * kk) * invH, th = ((ax + og.x) + (wa + og.y) * kk) * invH;
+                ia = __double2int_ru(tl + mc);
+                ib = __double2int_rd(th - mc);
+                const int ja = __double2int_ru(tl - mc), jb = __double2int_rd(th + mc);
+                for (int i = ja; i < ia; ++i) {
+                    const int4 qe = make_int4(i, k, cy, lg - n_ent);
+                    const int slot = atomicAdd(&s.qn, 1);
+                    if (slot < QCAP)
+                        s.queue[slot] = qe;
+                    else
+                        resolve_run_point(s, d, qe, H, r2);
+                }
+                for (int i = max(ib, ia - 1) + 1; i <= jb; ++i) {
+                    const int4 qe = make_int4(i, k, cy, lg - n_ent);
+                    const int slot = atomicAdd(&s.qn, 1);
+                    if (slot < QCAP)
+                        s.queue[slot] = qe;
+                    else
+                        resolve_run_point(s, d, qe, H, r2);
+                }
+            } else {
             // half chords of the end discs: approximate FP32 sqrt of an exact integer
             const double ta = r2d - wa * wa, tb = r2d - wb * wb;
             const double hA = (double)sqrt_approx((float)(ta > 0.0 ? ta : 0.0));
@@ -382,11 +598,12 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const double tl = xl * invH, th = xr * invH;
             const int rl = __double2int_rn(tl), rh = __double2int_rn(th);
             const double dl = tl - (double)rl, dh = th - (double)rh;
-            int ia = rl + (dl >= 0.0 ? 1 : 0);  // smallest i > tl
-            int ib = rh - (dh <= 0.0 ? 1 : 0);  // largest  i < th
+            ia = rl + (dl >= 0.0 ? 1 : 0);  // smallest i > tl
+            ib = rh - (dh <= 0.0 ? 1 : 0);  // largest  i < th
             if (fabs(dl) < amb || fabs(dh) < amb) {
                 if (fabs(dl) < amb) ia = near_seg((int64_t)rl * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rl : rl + 1;
                 if (fabs(dh) < amb) ib = near_seg((int64_t)rh * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rh : rh - 1;
+            }
             }
             const int4 w = s.rwin[k];
             const int2 bias = s.rbias[k];
@@ -396,14 +613,30 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             if (s2 <= e2) or_span(s.tile + bias.y, s2, e2);
         }
         __syncthreads();
+        if (n_t > 0) {  // deferred boundary points of the trapezoids
+            const int nq = min(s.qn, QCAP);
+            for (int q = tid; q < nq; q += T) resolve_run_point(s, d, s.queue[q], H, r2);
+            __syncthreads();
+        }
     }
 }
 
+// popcount of n words starting at a 16-byte aligned address (the words up to the next multiple
+// of 4 are read too: callers keep them zero)
 __device__ __forceinline__ int count_words(const uint32_t *w, int n)
 {
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += T) c += __popc(w[i]);
+    const uint4 *v = reinterpret_cast<const uint4 *>(w);
+    for (int i = threadIdx.x; i < (n + 3) >> 2; i += T) {
+        const uint4 x = v[i];
+        c += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
     return c;
+}
+__device__ __forceinline__ void zero_words(uint32_t *w, int n)  // rounds n up to a multiple of 4
+{
+    uint4 *v = reinterpret_cast<uint4 *>(w);
+    for (int i = threadIdx.x; i < (n + 3) >> 2; i += T) v[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ int words_of(int lo, int hi) { return hi >= lo ? (hi >> 5) - (lo >> 5) + 1 : 0; }
@@ -456,9 +689,9 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         const int rw = (g + 31) >> 5;
         const int Hc = (int)qfix(FCPP_CORNER_GRID_H);
         const double invHc = 1.0 / (double)Hc;
-        const bool okc = (g >= 1) && (rw <= TW) && (4 * VPOLY_CAP <= pc);
+        const bool okc = (g >= 1) && (rw <= TW - 16) && (4 * VPOLY_CAP + RCAP <= pc);
         if (!okc) grid_err = 1;
-        const int rpt = okc ? min(ROWCAP, TW / rw) : 1;                                 // rows per tile
+        const int rpt = okc ? min(ROWCAP, (TW - 16) / rw) : 1;                          // rows per tile
         const int group = (okc && 4 * g <= rpt) ? 4 : ((okc && 2 * g <= rpt) ? 2 : 1);  // corners per pass
         // snapped polylines of the four corners: 15-pt arc + reverse fill (mlp3:1531-1554), relative
         // to the corner's lattice origin (mlp3:1461-1468); corner ci occupies pts[ci*VPOLY_CAP ...]
@@ -486,15 +719,30 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 d.pts[ci * VPOLY_CAP + k] = make_int2((int)(qfix(x) - X0), (int)(qfix(y) - Y0));
             }
         }
+        if (tid == 0) s.n_runs = 0;
         __syncthreads();
+        int n_runs = 0;
         if (okc) {
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) setup_entries(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
+#ifdef FCPP_MERGE_RUNS
+            __syncthreads();
+            // straight runs (the reverse fills); entry 14 joins arc and fill and belongs to neither
+            auto mergeable = [&](int e) {
+                const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
+                return k != FCPP_CORNER_POINTS - 1 && k < FCPP_CORNER_POINTS + nv[c] - 1;
+            };
+            // (one call over the four staged polylines: the gaps between them are not mergeable)
+            build_runs(s, d, 0, 4 * VPOLY_CAP, 4 * VPOLY_CAP, Hc, invHc, rd, mergeable);
+            __syncthreads();
+            n_runs = min(s.n_runs, RCAP);
+#endif
         }
         int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < 4 && okc; c0 += group) {
             for (int j0 = 0; j0 < g; j0 += rpt) {
                 const int nrows = (group > 1) ? g : min(rpt, g - j0);
+                const int cstride = (nrows * rw + 3) & ~3;  // words per corner, 16-byte aligned
                 if (tid < group) {
                     Target &t = s.tg[tid];
                     t.j0 = j0;
@@ -502,23 +750,24 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     t.koff = tid * nrows;
                 }
                 for (int k = tid; k < group * nrows; k += T) {
+                    const int c = k / nrows;
                     s.rwin[k] = make_int4(0, g - 1, 1, 0);
-                    s.rbias[k] = make_int2(k * rw, 0);
+                    s.rbias[k] = make_int2(c * cstride + (k - c * nrows) * rw, 0);
                 }
-                for (int w = tid; w < group * nrows * rw; w += T) s.tile[w] = 0u;
+                zero_words(s.tile, group * cstride);
                 if (tid < 8) s.cnt[tid] = 0;
                 __syncthreads();
                 // pass 1: the turn arcs (entries 0..13 of every corner of the group)
                 {
                     auto tgt = [&](int e) {
                         const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
-                        return (k < FCPP_CORNER_POINTS - 1) ? c - c0 : -1;
+                        return (k < FCPP_CORNER_POINTS - 1 && c >= c0 && c < c0 + group) ? c - c0 : -1;
                     };
                     raster_entries(s, d, c0 * VPOLY_CAP, (group - 1) * VPOLY_CAP + FCPP_CORNER_POINTS - 1, tgt, rq, Hc,
-                                   invHc);
+                                   invHc, 4 * VPOLY_CAP, n_runs);
                 }
                 for (int c = 0; c < group; ++c) {
-                    const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
+                    const int n = count_words(s.tile + c * cstride, nrows * rw);
                     if (n) atomicAdd(&s.cnt[c], n);
                 }
                 __syncthreads();
@@ -527,12 +776,15 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 {
                     auto tgt = [&](int e) {
                         const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
-                        return (k >= FCPP_CORNER_POINTS && k < FCPP_CORNER_POINTS + nv[c] - 1) ? c - c0 : -1;
+                        return (k >= FCPP_CORNER_POINTS && k < FCPP_CORNER_POINTS + nv[c] - 1 && c >= c0 && c < c0 + group)
+                                   ? c - c0
+                                   : -1;
                     };
-                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq, Hc, invHc);
+                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq, Hc, invHc, 4 * VPOLY_CAP,
+                                   n_runs);
                 }
                 for (int c = 0; c < group; ++c) {
-                    const int n = count_words(s.tile + c * nrows * rw, nrows * rw);
+                    const int n = count_words(s.tile + c * cstride, nrows * rw);
                     if (n) atomicAdd(&s.cnt[4 + c], n);
                 }
                 __syncthreads();
@@ -573,7 +825,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         const double invH = 1.0 / (double)H;
         const int nh = r.n_head;
         // relative coordinates must fit int32 with headroom (extent + r < 2^30 units = 107 km)
-        const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
+        const bool ok = (nh + RCAP <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
                         H64 < (1 << 20);
         if (!ok) grid_err = 1;
         __syncthreads();
@@ -592,31 +844,52 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             __syncthreads();
             if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
             if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
+            if (tid == 0) s.n_runs = 0;
             setup_entries(d, 0, nh - 1, rd);
             __syncthreads();
+            int n_runs = 0;
+#ifdef FCPP_MERGE_RUNS
+            {
+                auto mergeable = [&](int) { return true; };
+                build_runs(s, d, 0, nh, nh, H, invH, rd, mergeable);
+                __syncthreads();
+                n_runs = min(s.n_runs, RCAP);
+            }
+#endif
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
+            if (tid == 0) s.next_w0 = 0;
             while (j0 < ny) {
-                // --- how many rows to try: from the word count of the first row (one thread) ---
+                // --- how many rows to try: from the word count of the first row.  The previous pass
+                // has usually computed it already (its first row that did not fit) ---
                 if (tid == 0) {
-                    int a0, b0, a1, b1;
-                    quad_row_interval(s.fq, s.qedge[0], s.qtype[0], j0 * H, H, invH, nx, a0, b0);
-                    quad_row_interval(s.mq, s.qedge[1], s.qtype[1], j0 * H, H, invH, nx, a1, b1);
-                    const int w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
+                    int w0 = s.next_w0;
+                    if (w0 <= 0) {
+                        int a0, b0, a1, b1;
+                        quad_row_interval(s.fq, s.qedge[0], s.qtype[0], j0 * H, H, invH, nx, a0, b0);
+                        quad_row_interval(s.mq, s.qedge[1], s.qtype[1], j0 * H, H, invH, nx, a1, b1);
+                        w0 = (a1 <= b1) ? words_of(a0, a1 - 1) + words_of(b1 + 1, b0) : words_of(a0, b0);
+                    }
                     const int rt = (5 * TW) / (4 * (w0 > 0 ? w0 : 1)) + 8;
                     s.cnt[0] = min(max(rt, 8), min(ROWCAP, ny - j0));
+                    s.next_w0 = 0;
+                    s.nrows = 0;
+                    s.total_words = 0;
                 }
                 __syncthreads();
                 const int rows_try = s.cnt[0];
-                // --- row windows + word counts: thread t owns rows 4t .. 4t+3 ---
-                int wcnt[4], wsum[4], n1[4];
-                int4 win[4];
+                // --- row windows + word counts: one row per thread and round (rows k = tid + round*T) ---
+                constexpr int ROUNDS = ROWCAP / T;
+                int wcnt[ROUNDS], cells[ROUNDS];
+                int fit_rows = 0, fit_words = 0, carry = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = tid * 4 + q;
+                for (int q = 0; q < ROUNDS; ++q) {
+                    const int k = tid + q * T;
                     wcnt[q] = 0;
-                    n1[q] = 0;
-                    win[q] = make_int4(1, 0, 1, 0);
+                    cells[q] = 0;
+                    if (q * T >= rows_try) continue;  // uniform
+                    int4 win = make_int4(1, 0, 1, 0);
+                    int n1 = 0;
                     if (k < rows_try) {
                         int fa, fb, ma, mb;
                         const int cy = (j0 + k) * H;
@@ -626,32 +899,26 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                             if (ma <= mb) {  // the inset lies inside the field: clamp defensively
                                 ma = max(ma, fa);
                                 mb = min(mb, fb);
-                                win[q] = make_int4(fa, ma - 1, mb + 1, fb);
+                                win = make_int4(fa, ma - 1, mb + 1, fb);
                             } else {
-                                win[q] = make_int4(fa, fb, 1, 0);
+                                win = make_int4(fa, fb, 1, 0);
                             }
                         }
-                        n1[q] = words_of(win[q].x, win[q].y);
-                        wcnt[q] = n1[q] + words_of(win[q].z, win[q].w);
+                        n1 = words_of(win.x, win.y);
+                        wcnt[q] = n1 + words_of(win.z, win.w);
+                        cells[q] = max(win.y - win.x + 1, 0) + max(win.w - win.z + 1, 0);
                     }
-                    wsum[q] = wcnt[q];
-                }
-                if (tid == 0) {
-                    s.nrows = 0;
-                    s.total_words = 0;
-                }
-                block_scan<4>(wsum, s.scan);  // inclusive prefix of the row word counts (syncs inside)
-                int fit_rows = 0, fit_words = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = tid * 4 + q;
+                    int v[1] = {wcnt[q]};
+                    const int round_total = block_scan<1>(v, s.scan);  // inclusive prefix (syncs inside)
+                    const int wsum = carry + v[0];
+                    carry += round_total;
                     if (k < rows_try) {
-                        const int base = wsum[q] - wcnt[q];
-                        s.rwin[k] = win[q];
-                        s.rbias[k] = make_int2(base - (win[q].x >> 5), base + n1[q] - (win[q].z >> 5));
-                        if (wsum[q] <= TW) {
+                        const int base = wsum - wcnt[q];
+                        s.rwin[k] = win;
+                        s.rbias[k] = make_int2(base - (win.x >> 5), base + n1 - (win.z >> 5));
+                        if (wsum <= TW) {
                             fit_rows = k + 1;
-                            fit_words = wsum[q];
+                            fit_words = wsum;
                         }
                     }
                 }
@@ -665,12 +932,12 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     grid_err = 1;
                     break;
                 }
-                for (int w = tid; w < nwords; w += T) s.tile[w] = 0u;
+                zero_words(s.tile, nwords);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = tid * 4 + q;
-                    if (k < nrows)
-                        my_total += (unsigned long long)(max(win[q].y - win[q].x + 1, 0) + max(win[q].w - win[q].z + 1, 0));
+                for (int q = 0; q < ROUNDS; ++q) {
+                    const int k = tid + q * T;
+                    if (k < nrows) my_total += (unsigned long long)cells[q];
+                    if (k == nrows && k < rows_try) s.next_w0 = wcnt[q];  // first row of the next pass
                 }
                 if (tid == 0) {
                     Target &t = s.tg[0];
@@ -681,7 +948,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 __syncthreads();
                 {
                     auto tgt = [&](int) { return 0; };
-                    raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH);
+                    raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH, nh, n_runs);
                 }
                 my_cov += (unsigned long long)count_words(s.tile, nwords);
                 __syncthreads();
@@ -708,8 +975,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
 
 int cover_point_capacity(int max_head)
 {
-    int pc = max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP;
-    return (pc + 255) / 256 * 256 + 16;
+    int pc = (max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP) + RCAP;  // + the runs' trapezoid entries
+    return (pc + 63) / 64 * 64 + 16;  // a multiple of 16 (carve_dyn)
 }
 
 }  // namespace
@@ -718,7 +985,7 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
 {
     if (b.n_cand == 0) return cudaSuccess;
     int pc = cover_point_capacity(h->cover_pcap);
-    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + 16) pc -= 256;
+    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + RCAP + 16) pc -= 64;
     const size_t bytes = cover_smem_bytes(pc);
     cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
@@ -757,7 +1024,7 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
             s.rwin[k] = make_int4(0, g - 1, 1, 0);
             s.rbias[k] = make_int2(k * rw, 0);
         }
-        for (int w = tid; w < nrows * rw; w += T) s.tile[w] = 0u;
+        zero_words(s.tile, nrows * rw);
         if (tid == 0) {
             Target &t = s.tg[0];
             t.j0 = j0;
