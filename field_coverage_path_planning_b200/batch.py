@@ -34,6 +34,62 @@ def _dev(device) -> torch.device:
     return d
 
 
+class _Staging:
+    """Grow-only pinned host buffers of one device: ONE packed host->device copy of a batch's inputs
+    and ONE packed device->host copy of its results, instead of a cudaHostAlloc + copy per array."""
+    _per_dev: Dict[int, "_Staging"] = {}
+
+    def __init__(self):
+        self.h_in = self.h_out = None
+        self.in_done = None          # event: the last packed H2D copy has left h_in
+
+    @classmethod
+    def get(cls, dev: torch.device) -> "_Staging":
+        st = cls._per_dev.get(dev.index)
+        if st is None:
+            st = cls._per_dev[dev.index] = cls()
+        return st
+
+    def host_in(self, nbytes: int) -> torch.Tensor:
+        if self.in_done is not None:
+            self.in_done.synchronize()           # the previous copy may still be reading the buffer
+        if self.h_in is None or self.h_in.numel() < nbytes:
+            self.h_in = torch.empty(max(nbytes * 2, 1 << 20), dtype=torch.uint8).pin_memory()
+        return self.h_in
+
+    def host_out(self, nbytes: int) -> torch.Tensor:
+        if self.h_out is None or self.h_out.numel() < nbytes:
+            self.h_out = torch.empty(max(nbytes * 2, 1 << 20), dtype=torch.uint8).pin_memory()
+        return self.h_out
+
+
+def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device) -> Dict[str, torch.Tensor]:
+    """All input arrays through one pinned staging buffer and one async copy; the device tensors
+    are typed views of one allocation (256-byte aligned slices)."""
+    offs, total = {}, 0
+    for k, a in arrays.items():
+        offs[k] = total
+        total += (a.nbytes + 255) & ~255
+    total = max(total, 256)
+    st = _Staging.get(dev)
+    h = st.host_in(total)
+    hv = h.numpy()
+    for k, a in arrays.items():
+        hv[offs[k]:offs[k] + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    with torch.cuda.device(dev):
+        d = torch.empty(total, dtype=torch.uint8, device=dev)
+        d.copy_(h[:total], non_blocking=True)
+        if st.in_done is None:
+            st.in_done = torch.cuda.Event()
+        st.in_done.record(torch.cuda.current_stream(dev))
+    out = {}
+    for k, a in arrays.items():
+        t = d[offs[k]:offs[k] + a.nbytes].view(torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype)
+        out[k] = t.view(a.shape) if a.nbytes else t
+    out["_packed"] = d
+    return out
+
+
 def _to_dev(a: np.ndarray, dev: torch.device, pin: bool = True) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a))
     if pin:
@@ -168,7 +224,7 @@ class DeviceBatch:
     def __init__(self, pb: PreparedBatch, dev: torch.device, pin: bool = True):
         self.pb = pb
         self.dev = dev
-        self.t = {k: _to_dev(v, dev, pin) for k, v in pb.arrays.items()}
+        self.t = _pack_to_dev(pb.arrays, dev) if pin else {k: _to_dev(v, dev, False) for k, v in pb.arrays.items()}
         v = pb.vehicle
         b = _lib.Batch()
         b.vehicle = _lib.Vehicle(v.working_width, v.max_work_speed_kmh, v.max_headland_speed_kmh,
@@ -286,14 +342,28 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
                                     buffers.d_best.data_ptr(), stream))
         if not fetch:
             return None
-        if copy_summary:
-            summary = buffers.d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE)[:B]
-        else:
-            summary = np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
-        best_cost = buffers.d_cost.cpu().numpy()[:F]
-        best_cand = buffers.d_best.cpu().numpy()[:F]
-        if outputs == "paths" and offsets is None:
-            offsets = buffers.d_off.cpu().numpy()
+        # one pinned staging buffer, async copies, ONE synchronisation
+        nb_sum = B * _lib.SUMMARY_DTYPE.itemsize if copy_summary else 0
+        need_off = outputs == "paths" and offsets is None
+        o_cost = (nb_sum + 255) & ~255
+        o_best = o_cost + ((F * 8 + 255) & ~255)
+        o_off = o_best + ((F * 8 + 255) & ~255)
+        total_out = o_off + ((B + 1) * 8 if need_off else 0)
+        ho = _Staging.get(dev).host_out(max(total_out, 256))
+        if nb_sum:
+            ho[:nb_sum].copy_(buffers.d_sum[:nb_sum], non_blocking=True)
+        if F:
+            ho[o_cost:o_cost + F * 8].view(torch.float64).copy_(buffers.d_cost[:F], non_blocking=True)
+            ho[o_best:o_best + F * 8].view(torch.int64).copy_(buffers.d_best[:F], non_blocking=True)
+        if need_off:
+            ho[o_off:o_off + (B + 1) * 8].view(torch.int64).copy_(buffers.d_off[:B + 1], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        hv = ho.numpy()
+        summary = hv[:nb_sum].copy().view(_lib.SUMMARY_DTYPE)[:B] if nb_sum else np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
+        best_cost = hv[o_cost:o_cost + F * 8].copy().view(np.float64)
+        best_cand = hv[o_best:o_best + F * 8].copy().view(np.int64)
+        if need_off:
+            offsets = hv[o_off:o_off + (B + 1) * 8].copy().view(np.int64)
     res = BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
                       d_path=buffers.d_path, d_speeds=buffers.d_spd, d_curvature=buffers.d_kap,
                       d_summary=buffers.d_sum, cand_base=cand_base)
