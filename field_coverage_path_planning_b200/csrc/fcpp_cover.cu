@@ -28,7 +28,7 @@ namespace {
 
 constexpr int T = FCPP_COVER_THREADS;
 constexpr int NWARP = T / 32;
-constexpr int TW = 7680;        // occupancy tile, 32-bit words (30 KB)
+constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
 constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
 constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fill), per corner
 constexpr int ICAP = 1024;      // item -> active-entry table
@@ -39,25 +39,6 @@ constexpr int EBATCH = EPT * T; // entries per scheduling batch
 // (relative error < 5e-7, i.e. < 5e-7 r units): at r = 1.6 m the margin is 0.078 units = 7.8e-6 m.
 constexpr double AMBIG_BASE = 0.03, AMBIG_REL = 3e-6;
 constexpr double AMBIG_Q = 1e-5;      // quad row intervals: margin in cells
-
-// Straight runs (>= RUN_MIN_SEGS collinear segments, e.g. a 20-point headland straight or a reverse
-// fill): inside the run's tangent zone the union of the sub-capsules is one trapezoid per row, known
-// up to the deviation RUN_DELTA of the snapped points from their chord.  The trapezoid is written
-// by ONE entry with two linear boundaries (no square roots); lattice points within the margin of a
-// boundary are decided afterwards by the exact predicate over the run's sub-segments.
-constexpr int RCAP = 64;            // runs per staging
-constexpr int QCAP = 128;           // deferred boundary points per raster batch
-constexpr int RUN_MIN_SEGS = 4;
-constexpr int RUN_MIN_ROWS = 8;
-constexpr double RUN_DELTA = 2.0;   // lattice units (2e-4 m)
-constexpr double RUN_MAX_MCELLS = 0.2;
-
-struct Run {
-    int i0, i1;    // sub-segment entries [i0, i1)
-    int j0, j1;    // lattice rows of the trapezoid zone (inclusive)
-    float mcells;  // boundary margin in cells: (RUN_DELTA + 0.05) * len / |dy| / H
-    int pad[3];
-};
 
 struct Target {
     int j0, nrows;  // lattice rows [j0, j0 + nrows) are resident
@@ -71,16 +52,14 @@ struct CoverFixed {
     int4 rwin[ROWCAP];   // per tile row: window 1 cells [x, y], window 2 cells [z, w] (empty: lo > hi)
     int2 rbias[ROWCAP];  // per tile row: tile word index of cell i in window w = bias.w + (i >> 5)
     int scan[32];
-    Run runs[RCAP];
-    int4 queue[QCAP];       // deferred boundary points: lattice column, tile row, cy, run
     double qedge[2][4][3];  // field / main quad edges: ax, ay, k = ex/ey (relative coordinates)
     int4 qtype[2][4];       // per edge: x = +1 upper bound / -1 lower bound / 0 horizontal, y = ay, z = sign(ex)
     int2 fq[4], mq[4];      // snapped field quad and R-inset, relative to the band lattice origin
     Target tg[4];
     int nrows, total_words;
     int next_item;
-    int n_runs, qn;
     int next_w0;
+    double rconst[2];  // raster_entries: r^2 and the certification margin in cells
     int cnt[8];
     unsigned long long acc[2];
     uint64_t bar;
@@ -93,7 +72,6 @@ struct CoverDyn {
     int4 *seg;        // [pc] entry e = pts[e] -> pts[e+1] with the lower end first: ax, ay, bx, by
     double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len; oy = +inf if dy == 0
     double *kk;       // [pc] dx/dy
-    uint8_t *runid;   // [pc] run of a sub-segment entry (0xff: none)
     int *apre;        // [EBATCH + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries
     uint16_t *act;    // [EBATCH] active entries (batch-local index)
     uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
@@ -104,8 +82,8 @@ __host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15);
 constexpr size_t DYN_TAIL = sizeof(int) * (EBATCH + 16) + sizeof(uint16_t) * EBATCH + sizeof(uint16_t) * ICAP;
 __host__ __device__ inline size_t cover_smem_bytes(int pc)
 {
-    return a16(sizeof(CoverFixed)) +
-           (size_t)pc * (sizeof(int2) + sizeof(int4) + sizeof(double2) + sizeof(double) + sizeof(uint8_t)) + DYN_TAIL;
+    return a16(sizeof(CoverFixed)) + (size_t)pc * (sizeof(int2) + sizeof(int4) + sizeof(double2) + sizeof(double)) +
+           DYN_TAIL;
 }
 __device__ __forceinline__ CoverDyn carve_dyn(unsigned char *base, int pc)
 {
@@ -116,8 +94,7 @@ __device__ __forceinline__ CoverDyn carve_dyn(unsigned char *base, int pc)
     d.seg = (int4 *)(p + (size_t)pc * 8);
     d.og = (double2 *)(p + (size_t)pc * 24);
     d.kk = (double *)(p + (size_t)pc * 40);
-    d.runid = (uint8_t *)(p + (size_t)pc * 48);
-    p += (size_t)pc * 49;
+    p += (size_t)pc * 48;
     d.apre = (int *)p;
     d.act = (uint16_t *)(p + sizeof(int) * (EBATCH + 16));
     d.item_first = d.act + EBATCH;
@@ -290,7 +267,6 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
             q = t;
         }
         d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
-        d.runid[e] = 0;
         const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
         if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
             d.og[e] = make_double2(0.0, INFINITY);
@@ -303,150 +279,24 @@ __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
     }
 }
 
-__device__ __forceinline__ bool straight_joint(const int2 *p, int i)  // joint at point i of a polyline
-{
-    const double ax = (double)(p[i].x - p[i - 1].x), ay = (double)(p[i].y - p[i - 1].y);
-    const double bx = (double)(p[i + 1].x - p[i].x), by = (double)(p[i + 1].y - p[i].y);
-    if ((ax == 0.0 && ay == 0.0) || (bx == 0.0 && by == 0.0)) return false;
-    if (ax * bx + ay * by <= 0.0) return false;
-    const double cr = ax * by - ay * bx, sx = ax + bx, sy = ay + by;
-    return cr * cr <= (RUN_DELTA * RUN_DELTA) * (sx * sx + sy * sy);
-}
-
-// Finds the straight runs of the polyline pts[p0 .. p0+np) (entries p0 .. p0+np-2), verifies each
-// against its chord and appends a trapezoid entry per run at tbase + slot.  Block-wide (every
-// thread must call it): one thread per joint / point / segment in every phase, so that nobody
-// waits on serial chord checks.  Call after the __syncthreads() that follows setup_entries and
-// before the first raster_entries (the staging points are still live).
-// d.runid[e]: bit 7 = joint at the segment's first point is straight (temporary), final value
-// 0x40 | slot for the sub-segments of a run, 0 otherwise.  d.apre is scratch here.
-template <class MergeFn>
-__device__ void build_runs(CoverFixed &s, const CoverDyn &d, int p0, int np, int tbase, int H, double invH, double rd,
-                           MergeFn mergeable)
-{
-    const int ns = np - 1;  // segments
-    if (ns > EBATCH || ns < RUN_MIN_SEGS) return;
-    const int2 *P = d.pts + p0;
-    uint8_t *F = d.runid + p0;
-    for (int i = threadIdx.x; i < ns; i += T) {
-        const bool st = i > 0 && mergeable(p0 + i - 1) && mergeable(p0 + i) && straight_joint(P, i);
-        F[i] = st ? 0x80 : 0;
-        d.apre[i] = 0;
-    }
-    __syncthreads();
-    // every interior point of a chain against the chain's chord
-    for (int j = threadIdx.x; j < ns; j += T) {
-        if (!(F[j] & 0x80)) continue;
-        int i = j - 1;
-        while (F[i] & 0x80) --i;  // F[0] is never set
-        int e = j + 1;
-        while (e < ns && (F[e] & 0x80)) ++e;
-        if (e - i < RUN_MIN_SEGS) continue;
-        const int2 a = P[i], b = P[e];
-        const double cx = (double)(b.x - a.x), cy = (double)(b.y - a.y), len2 = cx * cx + cy * cy;
-        const double wx = (double)(P[j].x - a.x), wy = (double)(P[j].y - a.y);
-        const double ux = (double)(P[j - 1].x - a.x), uy = (double)(P[j - 1].y - a.y);
-        const double cr = wx * cy - wy * cx, pj = wx * cx + wy * cy, pp = ux * cx + uy * cy;
-        if (!((cr * cr <= (RUN_DELTA * RUN_DELTA) * len2) && (pj > pp) && (pj < len2))) atomicOr(&d.apre[i], 1);
-    }
-    __syncthreads();
-    // chain heads: geometry of the trapezoid zone, slot, trapezoid entry
-    for (int i = threadIdx.x; i < ns; i += T) {
-        if ((F[i] & 0x80) || !mergeable(p0 + i) || i + 1 >= ns || !(F[i + 1] & 0x80)) continue;
-        int e = i + 1;
-        while (e < ns && (F[e] & 0x80)) ++e;
-        if (e - i < RUN_MIN_SEGS || (d.apre[i] & 1)) continue;
-        int2 a = P[i], b = P[e];
-        if (b.y < a.y) {
-            const int2 t = a;
-            a = b;
-            b = t;
-        }
-        const int dyi = b.y - a.y;
-        if (dyi <= 0) continue;  // horizontal chord: no tangent zone on rows
-        const double dx = (double)(b.x - a.x), dy = (double)dyi, len = sqrt(dx * dx + dy * dy);
-        const double m = (RUN_DELTA + 0.05) * len / dy;  // x shift of a tangent line moved by RUN_DELTA
-        if (m * invH > RUN_MAX_MCELLS) continue;
-        const double oy = fabs(rd * dx / len);
-        const double y0 = (double)a.y + oy + (RUN_DELTA + 1.0), y1 = (double)b.y - oy - (RUN_DELTA + 1.0);
-        if (!(y1 - y0 >= (double)(RUN_MIN_ROWS) * (double)H)) continue;
-        const int j0 = __double2int_ru(y0 * invH) + 1, j1 = __double2int_rd(y1 * invH) - 1;  // one row of slack
-        if (j1 - j0 + 1 < RUN_MIN_ROWS) continue;
-        const int slot = atomicAdd(&s.n_runs, 1);
-        if (slot >= RCAP) continue;
-        Run R;
-        R.i0 = p0 + i;
-        R.i1 = p0 + e;
-        R.j0 = j0;
-        R.j1 = j1;
-        R.mcells = (float)(m * invH);
-        R.pad[0] = R.pad[1] = R.pad[2] = 0;
-        s.runs[slot] = R;
-        d.seg[tbase + slot] = make_int4(a.x, a.y, b.x, b.y);
-        d.og[tbase + slot] = make_double2(rd * dy / len, rd * dx / len);
-        d.kk[tbase + slot] = dx / dy;
-        d.apre[i] = (slot + 1) << 8;
-    }
-    __syncthreads();
-    // every segment learns its run from its chain head
-    int rid[EPT];
-#pragma unroll
-    for (int q = 0; q < EPT; ++q) {
-        const int i = threadIdx.x + q * T;
-        rid[q] = 0;
-        if (i < ns) {
-            int h = i;
-            while (F[h] & 0x80) --h;
-            const int v = d.apre[h] >> 8;
-            if (v) rid[q] = 0x40 | (v - 1);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < EPT; ++q) {
-        const int i = threadIdx.x + q * T;
-        if (i < ns) F[i] = (uint8_t)rid[q];
-    }
-}
-
-// exact decision of one deferred boundary point of a run: inside iff within r of a sub-segment
-__device__ __noinline__ void resolve_run_point(CoverFixed &s, const CoverDyn &d, int4 q, int H, int64_t r2)
-{
-    const Run R = s.runs[q.w];
-    const int64_t px = (int64_t)q.x * H;
-    bool in = false;
-    for (int j = R.i0; j < R.i1 && !in; ++j) {
-        const int4 g = d.seg[j];
-        in = near_seg(px, q.z, g.x, g.y, g.z, g.w, r2);
-    }
-    if (!in) return;
-    const int4 w = s.rwin[q.y];
-    const int2 bias = s.rbias[q.y];
-    if (q.x >= w.x && q.x <= w.y)
-        atomicOr(s.tile + bias.x + (q.x >> 5), 1u << (q.x & 31));
-    else if (q.x >= w.z && q.x <= w.w)
-        atomicOr(s.tile + bias.y + (q.x >> 5), 1u << (q.x & 31));
-}
-
 // Rasterise the segments ("entries") e0 .. e0+n_ent-1 (entries that join two different polylines
 // are masked by `tgt(e) < 0`) into the resident tile rows of their targets.  All targets of one
 // call share the lattice pitch H.  Must be called after a __syncthreads() that follows
 // setup_entries (the staging points are overwritten by the per-pass row records).
-// Logical entries [0, n_ent) are the segments e0 + i, logical entries [n_ent, n_ent + n_t) the
-// trapezoids of the runs 0 .. n_t-1 (records at t0 + slot); a sub-segment of a run skips the rows
-// its run's trapezoid writes.
 template <class TgFn>
 __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_ent, TgFn tgt, int r, int H,
-                               double invH, int t0 = 0, int n_t = 0)
+                               double invH)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double r2d = (double)r * (double)r;
     const int64_t r2 = (int64_t)r * r;
-    const double amb = (AMBIG_BASE + AMBIG_REL * (double)r) * invH;
-    const int n_log = n_ent + n_t;
-    for (int eb = 0; eb < n_log; eb += EBATCH) {
-        const int nb = min(EBATCH, n_log - eb);
-        if (tid == 0) s.qn = 0;
+    // loop constants live in shared memory: under the 64-register cap the compiler would otherwise
+    // re-derive them (an int->double conversion and five FP64 operations) for every item
+    if (tid == 0) {
+        s.rconst[0] = (double)r * (double)r;
+        s.rconst[1] = (AMBIG_BASE + AMBIG_REL * (double)r) * invH;
+    }
+    for (int eb = 0; eb < n_ent; eb += EBATCH) {
+        const int nb = min(EBATCH, n_ent - eb);
         // ---- resident rows each entry's capsule can touch; packed (active << 21 | rows) ----
         int rows[EPT], inc[EPT];
 #pragma unroll
@@ -454,35 +304,13 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const int le = tid * EPT + q;
             rows[q] = 0;
             if (le < nb) {
-                const int lg = eb + le;
-                int e, ti, jlo, jhi;
-                if (lg < n_ent) {
-                    e = e0 + lg;
-                    ti = tgt(e);
-                    if (ti >= 0) {
-                        const int4 sg = d.seg[e];
-                        jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
-                        jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
-                        const int rid = d.runid[e];
-                        if (rid & 0x40) {  // the run's trapezoid owns rows [j0, j1]
-                            const int tj0 = s.runs[rid & 0x3f].j0, tj1 = s.runs[rid & 0x3f].j1;
-                            if (jlo >= tj0 && jhi <= tj1)
-                                jhi = jlo - 1;
-                            else if (jlo >= tj0)
-                                jlo = max(jlo, tj1 + 1);
-                            else if (jhi <= tj1)
-                                jhi = min(jhi, tj0 - 1);
-                        }
-                    }
-                } else {
-                    const Run R = s.runs[lg - n_ent];
-                    e = t0 + (lg - n_ent);
-                    ti = tgt(R.i0);
-                    jlo = R.j0;
-                    jhi = R.j1;
-                }
+                const int e = e0 + eb + le;
+                const int ti = tgt(e);
                 if (ti >= 0) {
+                    const int4 sg = d.seg[e];
                     const Target t = s.tg[ti];
+                    int jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
+                    int jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
                     jlo = max(jlo, t.j0);
                     jhi = min(jhi, t.j0 + t.nrows - 1);
                     if (jhi >= jlo) rows[q] = jhi - jlo + 1;
@@ -548,9 +376,7 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             item = next_item;
             if (p >= n_pairs) continue;
             const int ai = base_ai + __popc(bmask & ((2u << lane) - 1u));
-            const int lg = eb + d.act[ai];
-            const bool trap = lg >= n_ent;
-            const int e = trap ? t0 + (lg - n_ent) : e0 + lg;
+            const int e = e0 + eb + d.act[ai];
             const int qrow = p - d.apre[ai];
             const int4 sg = d.seg[e];
             const int2 er = d.erow[e];
@@ -560,36 +386,10 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const int cy = (er.x + qrow) * H;
             const double ax = (double)sg.x, bx = (double)sg.z;
             const double wa = (double)(cy - sg.y), wb = (double)(cy - sg.w);
-            int ia, ib;
-            if (trap) {
-                // tangent zone of a straight run: two lines; points within the run's margin of a
-                // line are decided later by the exact predicate over the sub-segments
-                const double mc = (double)s.runs[lg - n_ent].mcells;
-                const double tl = ((ax - og.x) + (wa - og.y) * kk) * invH, th = ((ax + og.x) + (wa + og.y) * kk) * invH;
-                ia = __double2int_ru(tl + mc);
-                ib = __double2int_rd(th - mc);
-                const int ja = __double2int_ru(tl - mc), jb = __double2int_rd(th + mc);
-                for (int i = ja; i < ia; ++i) {
-                    const int4 qe = make_int4(i, k, cy, lg - n_ent);
-                    const int slot = atomicAdd(&s.qn, 1);
-                    if (slot < QCAP)
-                        s.queue[slot] = qe;
-                    else
-                        resolve_run_point(s, d, qe, H, r2);
-                }
-                for (int i = max(ib, ia - 1) + 1; i <= jb; ++i) {
-                    const int4 qe = make_int4(i, k, cy, lg - n_ent);
-                    const int slot = atomicAdd(&s.qn, 1);
-                    if (slot < QCAP)
-                        s.queue[slot] = qe;
-                    else
-                        resolve_run_point(s, d, qe, H, r2);
-                }
-            } else {
             // half chords of the end discs: approximate FP32 sqrt of an exact integer
-            const double ta = r2d - wa * wa, tb = r2d - wb * wb;
-            const double hA = (double)sqrt_approx((float)(ta > 0.0 ? ta : 0.0));
-            const double hB = (double)sqrt_approx((float)(tb > 0.0 ? tb : 0.0));
+            const double r2d = s.rconst[0], amb = s.rconst[1];
+            const double hA = (double)sqrt_approx(fmaxf((float)(r2d - wa * wa), 0.0f));
+            const double hB = (double)sqrt_approx(fmaxf((float)(r2d - wb * wb), 0.0f));
             // left: arc A below yL0 = ay+oy | tangent line up to yL1 = by+oy | arc B;  right: -oy
             const double xl = (wa < og.y) ? ax - hA : ((wb <= og.y) ? (ax - og.x) + (wa - og.y) * kk : bx - hB);
             const double xr = (wa < -og.y) ? ax + hA : ((wb <= -og.y) ? (ax + og.x) + (wa + og.y) * kk : bx + hB);
@@ -598,12 +398,11 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             const double tl = xl * invH, th = xr * invH;
             const int rl = __double2int_rn(tl), rh = __double2int_rn(th);
             const double dl = tl - (double)rl, dh = th - (double)rh;
-            ia = rl + (dl >= 0.0 ? 1 : 0);  // smallest i > tl
-            ib = rh - (dh <= 0.0 ? 1 : 0);  // largest  i < th
+            int ia = rl + (dl >= 0.0 ? 1 : 0);  // smallest i > tl
+            int ib = rh - (dh <= 0.0 ? 1 : 0);  // largest  i < th
             if (fabs(dl) < amb || fabs(dh) < amb) {
                 if (fabs(dl) < amb) ia = near_seg((int64_t)rl * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rl : rl + 1;
                 if (fabs(dh) < amb) ib = near_seg((int64_t)rh * H, cy, sg.x, sg.y, sg.z, sg.w, r2) ? rh : rh - 1;
-            }
             }
             const int4 w = s.rwin[k];
             const int2 bias = s.rbias[k];
@@ -613,11 +412,6 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             if (s2 <= e2) or_span(s.tile + bias.y, s2, e2);
         }
         __syncthreads();
-        if (n_t > 0) {  // deferred boundary points of the trapezoids
-            const int nq = min(s.qn, QCAP);
-            for (int q = tid; q < nq; q += T) resolve_run_point(s, d, s.queue[q], H, r2);
-            __syncthreads();
-        }
     }
 }
 
@@ -689,7 +483,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         const int rw = (g + 31) >> 5;
         const int Hc = (int)qfix(FCPP_CORNER_GRID_H);
         const double invHc = 1.0 / (double)Hc;
-        const bool okc = (g >= 1) && (rw <= TW - 16) && (4 * VPOLY_CAP + RCAP <= pc);
+        const bool okc = (g >= 1) && (rw <= TW - 16) && (4 * VPOLY_CAP <= pc);
         if (!okc) grid_err = 1;
         const int rpt = okc ? min(ROWCAP, (TW - 16) / rw) : 1;                          // rows per tile
         const int group = (okc && 4 * g <= rpt) ? 4 : ((okc && 2 * g <= rpt) ? 2 : 1);  // corners per pass
@@ -719,24 +513,10 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 d.pts[ci * VPOLY_CAP + k] = make_int2((int)(qfix(x) - X0), (int)(qfix(y) - Y0));
             }
         }
-        if (tid == 0) s.n_runs = 0;
         __syncthreads();
-        int n_runs = 0;
         if (okc) {
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) setup_entries(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
-#ifdef FCPP_MERGE_RUNS
-            __syncthreads();
-            // straight runs (the reverse fills); entry 14 joins arc and fill and belongs to neither
-            auto mergeable = [&](int e) {
-                const int c = e / VPOLY_CAP, k = e - c * VPOLY_CAP;
-                return k != FCPP_CORNER_POINTS - 1 && k < FCPP_CORNER_POINTS + nv[c] - 1;
-            };
-            // (one call over the four staged polylines: the gaps between them are not mergeable)
-            build_runs(s, d, 0, 4 * VPOLY_CAP, 4 * VPOLY_CAP, Hc, invHc, rd, mergeable);
-            __syncthreads();
-            n_runs = min(s.n_runs, RCAP);
-#endif
         }
         int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < 4 && okc; c0 += group) {
@@ -764,7 +544,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                         return (k < FCPP_CORNER_POINTS - 1 && c >= c0 && c < c0 + group) ? c - c0 : -1;
                     };
                     raster_entries(s, d, c0 * VPOLY_CAP, (group - 1) * VPOLY_CAP + FCPP_CORNER_POINTS - 1, tgt, rq, Hc,
-                                   invHc, 4 * VPOLY_CAP, n_runs);
+                                   invHc);
                 }
                 for (int c = 0; c < group; ++c) {
                     const int n = count_words(s.tile + c * cstride, nrows * rw);
@@ -780,8 +560,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                                    ? c - c0
                                    : -1;
                     };
-                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq, Hc, invHc, 4 * VPOLY_CAP,
-                                   n_runs);
+                    raster_entries(s, d, c0 * VPOLY_CAP, group * VPOLY_CAP - 1, tgt, rq, Hc, invHc);
                 }
                 for (int c = 0; c < group; ++c) {
                     const int n = count_words(s.tile + c * cstride, nrows * rw);
@@ -825,7 +604,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         const double invH = 1.0 / (double)H;
         const int nh = r.n_head;
         // relative coordinates must fit int32 with headroom (extent + r < 2^30 units = 107 km)
-        const bool ok = (nh + RCAP <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
+        const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
                         H64 < (1 << 20);
         if (!ok) grid_err = 1;
         __syncthreads();
@@ -844,18 +623,8 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             __syncthreads();
             if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
             if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
-            if (tid == 0) s.n_runs = 0;
             setup_entries(d, 0, nh - 1, rd);
             __syncthreads();
-            int n_runs = 0;
-#ifdef FCPP_MERGE_RUNS
-            {
-                auto mergeable = [&](int) { return true; };
-                build_runs(s, d, 0, nh, nh, H, invH, rd, mergeable);
-                __syncthreads();
-                n_runs = min(s.n_runs, RCAP);
-            }
-#endif
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
             if (tid == 0) s.next_w0 = 0;
@@ -948,7 +717,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 __syncthreads();
                 {
                     auto tgt = [&](int) { return 0; };
-                    raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH, nh, n_runs);
+                    raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH);
                 }
                 my_cov += (unsigned long long)count_words(s.tile, nwords);
                 __syncthreads();
@@ -975,7 +744,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
 
 int cover_point_capacity(int max_head)
 {
-    int pc = (max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP) + RCAP;  // + the runs' trapezoid entries
+    const int pc = max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP;
     return (pc + 63) / 64 * 64 + 16;  // a multiple of 16 (carve_dyn)
 }
 
@@ -985,7 +754,7 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
 {
     if (b.n_cand == 0) return cudaSuccess;
     int pc = cover_point_capacity(h->cover_pcap);
-    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + RCAP + 16) pc -= 64;
+    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + 16) pc -= 64;
     const size_t bytes = cover_smem_bytes(pc);
     cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
