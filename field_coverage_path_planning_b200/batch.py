@@ -279,8 +279,11 @@ class BatchBuffers:
         self.dev = dev
         self.n_cand, self.n_fields, self.total_points = n_cand, n_fields, total_points
         self.d_sum = torch.empty(max(n_cand, 1) * _lib.SUMMARY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-        self.d_cost = torch.empty(max(n_fields, 1), dtype=torch.float64, device=dev)
-        self.d_best = torch.empty(max(n_fields, 1), dtype=torch.int64, device=dev)
+        # cost and candidate back to back in ONE allocation: the multi-GPU merge all-gathers both at once
+        nf = max(n_fields, 1)
+        self.d_cb = torch.empty(2 * nf, dtype=torch.int64, device=dev)
+        self.d_cost = self.d_cb[:nf].view(torch.float64)
+        self.d_best = self.d_cb[nf:]
         self.d_off = self.d_path = self.d_spd = self.d_kap = None
         if total_points > 0:
             self.d_off = torch.empty(n_cand + 1, dtype=torch.int64, device=dev)

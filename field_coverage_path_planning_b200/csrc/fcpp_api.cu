@@ -268,6 +268,19 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
     return FCPP_OK;
 }
 
+int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t world, int32_t n_fields,
+                            double *d_best_cost, int64_t *d_best_cand, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (world < 1 || n_fields < 0 || (n_fields > 0 && (!d_gathered || !d_best_cost || !d_best_cand)))
+        return fail(h, FCPP_ERR_INVALID, "fcpp_field_argmin_merge: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_argmin_merge(h, d_gathered, world, n_fields, d_best_cost, d_best_cand,
+                                             (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "argmin merge kernel");
+    return FCPP_OK;
+}
+
 int fcpp_speed_verify(fcpp_handle *h, const fcpp_vehicle *veh, const double *d_path_xy, const double *d_speeds_in,
                       const int64_t *d_offsets, int64_t n_paths, int64_t max_path_len, int do_speed_plan,
                       double *d_speeds_out, double *d_curvature, fcpp_summary *d_summary, void *stream)

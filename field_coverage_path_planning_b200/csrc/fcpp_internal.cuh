@@ -462,6 +462,8 @@ cudaError_t fcpp_launch_ga_rotate(fcpp_handle *h, const int32_t *d_route, int n,
 size_t fcpp_ga_state_bytes();
 void fcpp_ga_read_state(const void *host_copy, int &gen, int &stagnant, int &done, int &last_gen, double &best_fit,
                         double &best_len);
+cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int world, int32_t n_fields,
+                                     double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);
 cudaError_t fcpp_launch_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, cudaStream_t st);
 cudaError_t fcpp_launch_connection_matrix(fcpp_handle *h, const double *d_verts, int32_t n_fields, double depot_x,
                                           double depot_y, double *d_C, int32_t *d_arg, cudaStream_t st);

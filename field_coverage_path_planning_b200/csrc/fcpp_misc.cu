@@ -107,6 +107,28 @@ __global__ void argmin_final(unsigned long long *key, int64_t *cand, int n_field
     }
 }
 
+// multi-GPU: per-field merge of the ranks' local bests after ONE all-gather of (cost, candidate)
+// words; lowest cost wins, ties go to the lowest global candidate index, -1 = no candidate
+__global__ void argmin_merge_kernel(const long long *__restrict__ g, int world, int n_fields,
+                                    double *__restrict__ best_cost, long long *__restrict__ best_cand)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_fields) return;
+    double bc = INFINITY;
+    long long bi = -1;
+    for (int r = 0; r < world; ++r) {
+        const long long *row = g + (int64_t)r * 2 * n_fields;
+        const double c = __longlong_as_double(row[f]);
+        const long long i = row[n_fields + f];
+        if (i >= 0 && (bi < 0 || c < bc || (c == bc && i < bi))) {
+            bc = c;
+            bi = i;
+        }
+    }
+    best_cost[f] = bc;
+    best_cand[f] = bi;
+}
+
 // multi_field_planner.py:263-288 ("mfp"): D[i][j] = ||pos_i - pos_j||, 0 on the diagonal
 __global__ void distance_matrix_kernel(const double *__restrict__ pos, int n, double *__restrict__ D)
 {
@@ -151,6 +173,16 @@ __global__ void connection_matrix_kernel(const double *__restrict__ verts, int n
 }
 
 }  // namespace
+
+cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int world, int32_t n_fields,
+                                     double *d_best_cost, int64_t *d_best_cand, cudaStream_t st)
+{
+    if (n_fields == 0) return cudaSuccess;
+    argmin_merge_kernel<<<(n_fields + 255) / 256, 256, 0, st>>>((const long long *)d_gathered, world, n_fields,
+                                                                d_best_cost, (long long *)d_best_cand);
+    h->launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t fcpp_launch_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, cudaStream_t st)
 {

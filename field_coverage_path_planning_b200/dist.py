@@ -2,9 +2,9 @@
 NO data-path collective — the only exchange is the final per-field argmin.
 
 The reduction is exact and deterministic (ties go to the lowest global candidate index):
-    1. all_reduce(MIN) of the per-field best cost (float64);
-    2. all_reduce(MIN) of the candidate index where the local best equals the global minimum
-       (int64, "no candidate" = INT64_MAX);
+    1+2. CUDA: ONE all-gather of every rank's (best cost, best candidate) words and the library's
+       merge kernel (fcpp_field_argmin_merge).  CPU/gloo (tests): all_reduce(MIN) of the cost, then
+       all_reduce(MIN) of the candidate index where the local best equals the global minimum;
     3. the winner's 176-byte summary record is contributed by its owner and summed as int32
        words (every other rank contributes zeros), i.e. an all-gather of one record per field.
 Works on NCCL (CUDA tensors) and gloo (CPU tensors — used by the world_size-2 CPU tests).
@@ -37,7 +37,30 @@ def shard_candidates(cands: Dict[str, np.ndarray], world: int, rank: int) -> Tup
 
 def reduce_best(best_cost: torch.Tensor, best_cand: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Global per-field (cost, candidate) from the local ones.  ``best_cand`` holds GLOBAL
-    candidate indices (-1 = this rank has no valid candidate for the field).  In place."""
+    candidate indices (-1 = this rank has no valid candidate for the field).  In place.
+
+    CUDA tensors: ONE all-gather of the (cost, candidate) words of every rank + the library's merge
+    kernel (fcpp_field_argmin_merge).  CPU tensors (gloo tests): the same rule with torch ops."""
+    if best_cost.is_cuda:
+        import ctypes as C
+        F = best_cost.numel()
+        world = dist.get_world_size(group)
+        dev = best_cost.device
+        adjacent = (best_cost.dtype == torch.float64 and best_cand.dtype == torch.int64 and best_cost.is_contiguous()
+                    and best_cand.is_contiguous() and best_cand.data_ptr() == best_cost.data_ptr() + 8 * F
+                    and best_cost.untyped_storage().data_ptr() == best_cand.untyped_storage().data_ptr())
+        if adjacent:   # BatchBuffers lays them out back to back
+            send = torch.empty(0, dtype=torch.int64, device=dev).set_(
+                best_cost.untyped_storage(), best_cost.storage_offset(), (2 * F,))
+        else:
+            send = torch.cat([best_cost.view(torch.int64), best_cand])
+        gathered = torch.empty(world * 2 * F, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, send, group=group)
+        h = _lib.handle(dev.index)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        h.check(h.lib.fcpp_field_argmin_merge(h.h, gathered.data_ptr(), world, F, best_cost.data_ptr(),
+                                              best_cand.data_ptr(), st))
+        return best_cost, best_cand
     local_cost = best_cost.clone()
     dist.all_reduce(best_cost, op=dist.ReduceOp.MIN, group=group)
     mine = (local_cost == best_cost) & (best_cand >= 0)

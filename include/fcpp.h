@@ -190,6 +190,13 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
                       int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
                       double *d_best_cost, int64_t *d_best_cand, void *stream);
 
+/* Multi-GPU merge of the per-field argmin: d_gathered [world][2*F] 8-byte words =
+ * every rank's (best_cost[F] as double bits, best_cand[F] as int64 global indices, -1 = none), e.g.
+ * the result of ONE all-gather of the two arrays laid out back to back.  Lowest cost wins, ties go
+ * to the lowest candidate index; d_best_cost = +inf and d_best_cand = -1 when no rank has one. */
+int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t world, int32_t n_fields,
+                            double *d_best_cost, int64_t *d_best_cand, void *stream);
+
 /* Generic A7/A8/A13 on caller-supplied paths (ragged batch, path p = points offsets[p]..offsets[p+1]):
  * speed planning mlp3:467-589 (d_speeds_out may alias d_speeds_in), curvature verification
  * mlp3:1373-1424 and length/time mlp3:1290-1311 into d_summary (fields n_accel_viol, max_*,

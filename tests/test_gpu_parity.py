@@ -438,3 +438,63 @@ def test_clothoid_turn_model_vs_scipy_oracle(fc):
     assert len(r["main_work"]["path"]) == 1256
     with pytest.raises(ValueError):
         fc.plan_batch(fields, fc.VehicleParams(), cand, turn_model="bezier")
+
+
+def test_argmin_merge_kernel_vs_numpy_rule(fc):
+    """fcpp_field_argmin_merge (the multi-GPU merge after ONE all-gather): lowest cost wins, ties go
+    to the lowest global candidate index, ranks without a candidate (-1) are skipped."""
+    import ctypes as C
+    import torch
+    from field_coverage_path_planning_b200 import _lib
+    rng = np.random.default_rng(9)
+    h = _lib.handle(0)
+    for world, F in ((1, 1), (2, 7), (3, 1000), (8, 4096)):
+        cost = rng.integers(0, 6, size=(world, F)).astype(np.float64) * 0.5      # many ties
+        cand = rng.integers(0, 10 ** 6, size=(world, F)).astype(np.int64)
+        none = rng.random((world, F)) < 0.3
+        cand[none] = -1
+        cost[none] = np.inf
+        if F > 5:
+            cand[:, 3] = -1                                                        # nobody has field 3
+            cost[:, 3] = np.inf
+        g = np.concatenate([cost.view(np.int64), cand], axis=1)                    # [world][2F] words
+        dg = torch.from_numpy(np.ascontiguousarray(g)).cuda()
+        oc = torch.empty(F, dtype=torch.float64, device="cuda")
+        ob_ = torch.empty(F, dtype=torch.int64, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h.check(h.lib.fcpp_field_argmin_merge(h.h, dg.data_ptr(), world, F, oc.data_ptr(), ob_.data_ptr(), st))
+        want_c, want_i = np.full(F, np.inf), np.full(F, -1, dtype=np.int64)
+        for f in range(F):
+            for r in range(world):
+                if cand[r, f] >= 0 and (want_i[f] < 0 or cost[r, f] < want_c[f] or
+                                        (cost[r, f] == want_c[f] and cand[r, f] < want_i[f])):
+                    want_c[f], want_i[f] = cost[r, f], cand[r, f]
+        assert np.array_equal(oc.cpu().numpy(), want_c) and np.array_equal(ob_.cpu().numpy(), want_i)
+
+
+def test_distributed_plan_batch_world1_nccl(fc):
+    """plan_batch(distributed=True) through a world-size-1 NCCL group == the single-process result
+    (all-gather + merge kernel + winner-record exchange on the CUDA path)."""
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rect = [(0, 0), (500, 0), (500, 200), (0, 200)]
+        small = [(0, 0), (100, 0), (100, 80), (0, 80)]
+        tiny = [(0, 0), (12, 0), (12, 9), (0, 9)]                                  # no valid candidate
+        cand = fc.make_candidates(3, radii=[5.0, 8.0, 11.0], start_corners=[0, 1, 2, 3])
+        a = fc.plan_batch([rect, small, tiny], fc.VehicleParams(), cand, outputs="summary", device="cuda:0")
+        b = fc.plan_batch([rect, small, tiny], fc.VehicleParams(), cand, outputs="summary", device="cuda:0",
+                          distributed=True)
+        assert np.array_equal(a.best_cand, b.best_cand) and np.array_equal(a.best_cost, b.best_cost)
+        assert a.best_cand[2] == -1 and np.isinf(a.best_cost[2])
+        win = b.extras["winner_summary"]
+        for f in range(2):
+            assert win[f].tobytes() == a.summary[a.best_cand[f]].tobytes()
+    finally:
+        if created:
+            dist.destroy_process_group()
