@@ -202,6 +202,35 @@ __device__ __forceinline__ double cls_speed(const fcpp_vehicle &v, uint8_t c)
                                           : (c == CLS_HEAD ? v.max_headland_speed_kmh : v.reverse_speed_kmh));
 }
 
+// x / 3.6, correctly rounded, in three instructions instead of the generic FP64 division
+// (Markstein: with r = RN(1/y) and q0 = RN(x r), RN(q0 + r RN(x - y q0)) = RN(x / y) whenever the
+// significand of y is not all ones; checked here against the division on 1.5e9 random doubles).
+// The km/h <-> m/s conversions of the reference (mlp3:498, :564-566, :580-582, :1306, :1389) are
+// the most frequent divisions of this kernel; the result is bit-identical to `x / 3.6`.
+__device__ __forceinline__ double div36(double x)
+{
+    if (!(fabs(x) < 1e150)) return x / 3.6;  // inf / nan / absurd magnitudes: the generic path
+    const double r = 1.0 / 3.6;
+    const double q0 = x * r;
+    return fma(fma(-q0, 3.6, x), r, q0);
+}
+
+// FP64 sqrt and division take a ~70-instruction slow path when the radicand / numerator is zero,
+// and one zero lane (a zero-length segment, a straight joint) drags its whole warp through it.
+// The zero lanes are fed a harmless operand and get their exact result (0) by a select.
+__device__ __forceinline__ double sqrt_z(double q)
+{
+    const bool z = (q == 0.0);
+    const double r = sqrt(z ? 1.0 : q);
+    return z ? 0.0 : r;
+}
+__device__ __forceinline__ double div_z(double num, double den)  // den > 0
+{
+    const bool z = (num == 0.0);
+    const double r = (z ? 1.0 : num) / den;
+    return z ? 0.0 : r;
+}
+
 // mlp3:513-536 with the three atan2 folded into one: dtheta = atan2(d1 x d2, d1 . d2)
 __device__ __forceinline__ double curvature3(double dx1, double dy1, double ds1, double dx2, double dy2,
                                              double ds2)
@@ -209,8 +238,11 @@ __device__ __forceinline__ double curvature3(double dx1, double dy1, double ds1,
     if (ds1 < FCPP_ZERO_LEN || ds2 < FCPP_ZERO_LEN) return 0.0;
     const double cr = dx1 * dy2 - dy1 * dx2;
     const double dt = dx1 * dx2 + dy1 * dy2;
-    const double dth = atan2(cr, dt);
-    return fabs(2 * dth / (ds1 + ds2));
+    // collinear joints (cr == 0): atan2(+-0, dt) is 0 for dt > 0 and +-pi for dt < 0; only |dtheta| is used
+    const bool col = (cr == 0.0);
+    const double at = atan2(col ? 1.0 : cr, dt);
+    const double dth = col ? (dt < 0.0 ? 3.141592653589793 : 0.0) : at;
+    return fabs(div_z(2 * dth, ds1 + ds2));
 }
 
 // curvature speed limit in km/h (mlp3:496-503)
@@ -429,7 +461,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
         double px = hpx, py = hpy;
         double cx = s.X[cs], cy = s.Y[cs];
         double dx1 = cx - px, dy1 = cy - py;
-        double ds1 = (cs > 0) ? sqrt(dx1 * dx1 + dy1 * dy1) : 0.0;
+        double ds1 = (cs > 0) ? sqrt_z(dx1 * dx1 + dy1 * dy1) : 0.0;
         for (int i = cs; i < ce; ++i) {
             double nx, ny;
             if (i + 1 < ce) {
@@ -443,7 +475,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             if (i + 1 < N) {
                 dx2 = nx - cx;
                 dy2 = ny - cy;
-                ds2 = sqrt(dx2 * dx2 + dy2 * dy2);
+                ds2 = sqrt_z(dx2 * dx2 + dy2 * dy2);
             }
             double kap = 0.0;
             if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
@@ -456,13 +488,13 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
                 if (i + 1 < N) v1 = a.in_speeds[off + i + 1];
             }
             const double vl = (GEN || a.do_speed_plan) ? vlimit(v0, kap, veh) : v0;
-            const double vms = vl / 3.6;
+            const double vms = div36(vl);
             s.X[i] = ds2;
             s.Y[i] = kap;
             s.U[i] = vms * vms;
             // per-layer length and pre-adjustment time (mlp3:616-617, :882-883)
             if (i + 1 < N && i != n_main - 1) {
-                const double t = ds2 / fmax((v0 + v1) / 2 / 3.6, FCPP_MIN_SPEED_MS);
+                const double t = div_z(ds2, fmax(div36((v0 + v1) / 2), FCPP_MIN_SPEED_MS));
                 if (i < n_main) {
                     acc_len_m += ds2;
                     acc_tpre_m += t;
@@ -558,7 +590,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             double v;
             if (do_scan && N >= 3) {
                 const double vl = vlimit(v0, kap, veh);
-                const double vms = vl / 3.6;
+                const double vms = div36(vl);
                 const double u = s.U[i];
                 v = (u == vms * vms) ? vl : 3.6 * sqrt(u);
             } else {
@@ -567,7 +599,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             if (gs) gs[i] = v;
             if (gk) gk[i] = kap;
             if (i >= 1 && i + 1 < N) {
-                const double vm = v / 3.6;
+                const double vm = div36(v);
                 const double alat = vm * vm * kap;  // mlp3:1389-1390
                 n_aviol += (alat > veh.max_lateral_accel);
                 mx[0] = fmax(mx[0], kap);
@@ -584,7 +616,7 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
     double acc_t_m = 0.0, acc_t_h = 0.0;
     for (int i = tid; i + 1 < N; i += T) {
         if (i == n_main - 1) continue;
-        const double t = s.X[i] / fmax((s.U[i] + s.U[i + 1]) / 2 / 3.6, FCPP_MIN_SPEED_MS);
+        const double t = div_z(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
         if (i < n_main)
             acc_t_m += t;
         else
