@@ -218,17 +218,26 @@ __device__ __forceinline__ double div36(double x)
 // FP64 sqrt and division take a ~70-instruction slow path when the radicand / numerator is zero,
 // and one zero lane (a zero-length segment, a straight joint) drags its whole warp through it.
 // The zero lanes are fed a harmless operand and get their exact result (0) by a select.
+// (the substitution is opaque inline PTX: written as a C++ select the compiler proves
+// sqrt(0) == 0 and 0 / den == 0, folds the select away and the slow path is back)
+__device__ __forceinline__ double one_if_zero(double x)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %1, 0d0000000000000000;\n\t"
+        "selp.f64 %0, 0d3FF0000000000000, %1, p;\n\t}"
+        : "=d"(r)
+        : "d"(x));
+    return r;
+}
 __device__ __forceinline__ double sqrt_z(double q)
 {
-    const bool z = (q == 0.0);
-    const double r = sqrt(z ? 1.0 : q);
-    return z ? 0.0 : r;
+    const double r = sqrt(one_if_zero(q));
+    return (q == 0.0) ? 0.0 : r;
 }
 __device__ __forceinline__ double div_z(double num, double den)  // den > 0
 {
-    const bool z = (num == 0.0);
-    const double r = (z ? 1.0 : num) / den;
-    return z ? 0.0 : r;
+    const double r = one_if_zero(num) / den;
+    return (num == 0.0) ? 0.0 : r;
 }
 
 // mlp3:513-536 with the three atan2 folded into one: dtheta = atan2(d1 x d2, d1 . d2)
@@ -240,7 +249,7 @@ __device__ __forceinline__ double curvature3(double dx1, double dy1, double ds1,
     const double dt = dx1 * dx2 + dy1 * dy2;
     // collinear joints (cr == 0): atan2(+-0, dt) is 0 for dt > 0 and +-pi for dt < 0; only |dtheta| is used
     const bool col = (cr == 0.0);
-    const double at = atan2(col ? 1.0 : cr, dt);
+    const double at = atan2(one_if_zero(cr), dt);
     const double dth = col ? (dt < 0.0 ? 3.141592653589793 : 0.0) : at;
     return fabs(div_z(2 * dth, ds1 + ds2));
 }
