@@ -256,11 +256,39 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return y;
 }
 
-// segment records of entries [e0, e0 + n): lower end first, tangent offsets and slope; once per polyline
+// direction class of an exactly axis-aligned, non-degenerate segment: 1 +x, 2 -x, 3 +y, 4 -y; 0 otherwise
+__device__ __forceinline__ int axis_class(int2 p, int2 q)
+{
+    const int dx = q.x - p.x, dy = q.y - p.y;
+    if (dy == 0 && dx != 0) return dx > 0 ? 1 : 2;
+    if (dx == 0 && dy != 0) return dy > 0 ? 3 : 4;
+    return 0;
+}
+
+// segment records of entries [e0, e0 + n): lower end first, tangent offsets and slope; once per polyline.
+// MERGE: consecutive segments that run in the same direction along one axis-aligned line (the
+// 20-point straights of an unrotated rectangular field) are collapsed into their first entry — the
+// union of capsules along one straight line IS the capsule of the whole chain, exactly — and the
+// other entries of the chain get an empty row range.
+template <bool MERGE>
 __device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
 {
     for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
         int2 p = d.pts[e], q = d.pts[e + 1];
+        if (MERGE) {
+            const int c = axis_class(p, q);
+            if (c) {
+                if (e > e0 && axis_class(d.pts[e - 1], p) == c) {  // inside a chain: dead entry
+                    d.seg[e] = make_int4(0, 1 << 30, 0, -(1 << 30));
+                    d.og[e] = make_double2(0.0, INFINITY);
+                    d.kk[e] = 0.0;
+                    continue;
+                }
+                int j = e + 1;
+                while (j < e0 + n && axis_class(d.pts[j], d.pts[j + 1]) == c) ++j;
+                q = d.pts[j];
+            }
+        }
         if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
             const int2 t = p;
             p = q;
@@ -516,7 +544,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         __syncthreads();
         if (okc) {
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) setup_entries(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
+            for (int ci = 0; ci < 4; ++ci) setup_entries<false>(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
         }
         int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < 4 && okc; c0 += group) {
@@ -623,7 +651,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             __syncthreads();
             if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
             if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
-            setup_entries(d, 0, nh - 1, rd);
+            setup_entries<true>(d, 0, nh - 1, rd);
             __syncthreads();
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
@@ -812,7 +840,7 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
                 d.pts[k] = make_int2((int)x, (int)y);
             }
             __syncthreads();
-            setup_entries(d, 0, np - 1, (double)rq);
+            setup_entries<true>(d, 0, np - 1, (double)rq);
             __syncthreads();
             auto tgt = [&](int) { return 0; };
             raster_entries(s, d, 0, np - 1, tgt, rq, H, invH);
