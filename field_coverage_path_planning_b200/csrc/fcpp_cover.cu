@@ -57,7 +57,6 @@ struct CoverFixed {
     int2 fq[4], mq[4];      // snapped field quad and R-inset, relative to the band lattice origin
     Target tg[4];
     int nrows, total_words;
-    int next_item;
     int next_w0;
     double rconst[2];  // raster_entries: r^2 and the certification margin in cells
     int cnt[8];
@@ -362,22 +361,13 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                     for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
             }
         }
-        if (tid == 0) {
-            d.apre[n_act] = n_pairs;
-            s.next_item = NWARP;
-        }
+        if (tid == 0) d.apre[n_act] = n_pairs;
         __syncthreads();
-        // items are handed out dynamically (the first one statically): their cost varies with the
-        // span lengths, and the block barrier below waits for the slowest warp
+        // items go to the warps round-robin (handing them out through a shared counter was measured
+        // twice and lost 2.5-4.5 %: the atomic sits on every item's critical path)
         for (int item = warp; item < n_items;) {
             const int pbase = 32 * item;
-#ifdef FCPP_DYNAMIC_ITEMS
-            int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(&s.next_item, 1);
-            const int next_item = __shfl_sync(0xffffffffu, nxt, 0);
-#else
             const int next_item = item + NWARP;
-#endif
             // ---- pair -> active entry: the entry boundaries inside this item as a bit mask ----
             int base_ai;
             if (table) {
