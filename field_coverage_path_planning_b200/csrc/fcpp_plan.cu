@@ -664,7 +664,10 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
 }
 
 template <bool GEN>
-__global__ void __launch_bounds__(T, 3) plan_kernel(const PlanArgs a)
+#ifndef FCPP_PLAN_MIN_CTAS
+#define FCPP_PLAN_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(T, FCPP_PLAN_MIN_CTAS) plan_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
