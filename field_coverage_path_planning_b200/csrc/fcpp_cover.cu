@@ -34,6 +34,7 @@ constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fi
 constexpr int ICAP = 1024;      // item -> active-entry table
 constexpr int EPT = 2;          // entries per thread in a scheduling batch
 constexpr int EBATCH = EPT * T; // entries per scheduling batch
+constexpr int RECT_CAP = 64;    // vertical-chain rectangles per polyline (more: the chain stays one capsule)
 // capsule boundaries: certification margin in lattice units (1e-4 m) = 0.03 + 3e-6 r.  The FP64
 // tangent lines are good to 2e-7 units; the arcs use an approximate FP32 sqrt of an exact integer
 // (relative error < 5e-7, i.e. < 5e-7 r units): at r = 1.6 m the margin is 0.078 units = 7.8e-6 m.
@@ -62,6 +63,8 @@ struct CoverFixed {
     int cnt[8];
     unsigned long long acc[2];
     uint64_t bar;
+    int4 rects[RECT_CAP];  // vertical chains: lattice columns [x, y] on lattice rows [z, w] (see setup_entries)
+    int nrect;
 };
 
 // dynamic part, sized by the point capacity pc (>= longest polyline staged)
@@ -269,39 +272,95 @@ __device__ __forceinline__ int axis_class(int2 p, int2 q)
 // 20-point straights of an unrotated rectangular field) are collapsed into their first entry — the
 // union of capsules along one straight line IS the capsule of the whole chain, exactly — and the
 // other entries of the chain get an empty row range.
-template <bool MERGE>
-__device__ void setup_entries(const CoverDyn &d, int e0, int n, double rd)
+// RECT (band only): a VERTICAL chain of >= 2 entries is split, again exactly, into the two end
+// discs (point segments in the chain's first two entries) and the rectangle between them, which
+// needs no per-row geometry at all: on the lattice rows ay <= cy <= by the covered columns are
+// |i H - x| < r, two integers per chain.  The rectangles go to s.rects and are filled by
+// fill_rects, one row per thread, outside the (entry, row) pair scheduler.
+__device__ __forceinline__ void write_entry(const CoverDyn &d, int e, int2 p, int2 q, double rd)
+{
+    if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
+        const int2 t = p;
+        p = q;
+        q = t;
+    }
+    d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
+    const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
+    if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
+        d.og[e] = make_double2(0.0, INFINITY);
+        d.kk[e] = 0.0;
+    } else {
+        const double len = sqrt(dx * dx + dy * dy);
+        d.og[e] = make_double2(rd * dy / len, rd * dx / len);
+        d.kk[e] = dx / dy;
+    }
+}
+__device__ __forceinline__ void write_dead_entry(const CoverDyn &d, int e)
+{
+    d.seg[e] = make_int4(0, 1 << 30, 0, -(1 << 30));
+    d.og[e] = make_double2(0.0, INFINITY);
+    d.kk[e] = 0.0;
+}
+
+template <bool MERGE, bool RECT>
+__device__ void setup_entries(CoverFixed &s, const CoverDyn &d, int e0, int n, double rd, int r, int H, double invH)
 {
     for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
-        int2 p = d.pts[e], q = d.pts[e + 1];
+        const int2 p = d.pts[e];
+        int2 q = d.pts[e + 1];
         if (MERGE) {
             const int c = axis_class(p, q);
             if (c) {
-                if (e > e0 && axis_class(d.pts[e - 1], p) == c) {  // inside a chain: dead entry
-                    d.seg[e] = make_int4(0, 1 << 30, 0, -(1 << 30));
-                    d.og[e] = make_double2(0.0, INFINITY);
-                    d.kk[e] = 0.0;
+                if (e > e0 && axis_class(d.pts[e - 1], p) == c) {  // inside a chain
+                    // the chain's second entry is written by the thread of its first (RECT)
+                    const bool second = !(e - 1 > e0 && axis_class(d.pts[e - 2], d.pts[e - 1]) == c);
+                    if (!(RECT && second)) write_dead_entry(d, e);
                     continue;
                 }
                 int j = e + 1;
                 while (j < e0 + n && axis_class(d.pts[j], d.pts[j + 1]) == c) ++j;
                 q = d.pts[j];
+                if (RECT && j > e + 1) {
+                    int slot = -1;
+                    if (c >= 3) {
+                        slot = atomicAdd(&s.nrect, 1);
+                        if (slot >= RECT_CAP) slot = -1;  // (the counter is clamped by the reader)
+                    }
+                    if (slot >= 0) {
+                        const int ylo = min(p.y, q.y), yhi = max(p.y, q.y);
+                        const int ia = floor_div_i(p.x - r, H, invH) + 1;      // i H > x - r
+                        const int ib = -floor_div_i(-(p.x + r), H, invH) - 1;  // i H < x + r
+                        const int ja = -floor_div_i(-ylo, H, invH);            // j H >= ylo
+                        const int jb = floor_div_i(yhi, H, invH);              // j H <= yhi
+                        s.rects[slot] = make_int4(ia, ib, ja, jb);
+                        write_entry(d, e, make_int2(p.x, ylo), make_int2(p.x, ylo), rd);
+                        write_entry(d, e + 1, make_int2(p.x, yhi), make_int2(p.x, yhi), rd);
+                        continue;
+                    }
+                    write_dead_entry(d, e + 1);
+                }
             }
         }
-        if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
-            const int2 t = p;
-            p = q;
-            q = t;
-        }
-        d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
-        const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
-        if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
-            d.og[e] = make_double2(0.0, INFINITY);
-            d.kk[e] = 0.0;
-        } else {
-            const double len = sqrt(dx * dx + dy * dy);
-            d.og[e] = make_double2(rd * dy / len, rd * dx / len);
-            d.kk[e] = dx / dy;
+        write_entry(d, e, p, q, rd);
+    }
+}
+
+// the rectangles of the vertical chains on the resident rows [j0, j0 + nrows): one row per thread
+__device__ void fill_rects(CoverFixed &s, int j0, int nrows)
+{
+    const int nr = min(s.nrect, RECT_CAP);
+    for (int q = 0; q < nr; ++q) {
+        const int4 rc = s.rects[q];
+        if (rc.x > rc.y) continue;
+        const int lo = max(rc.z, j0), hi = min(rc.w, j0 + nrows - 1);
+        for (int j = lo + (int)threadIdx.x; j <= hi; j += T) {
+            const int k = j - j0;
+            const int4 w = s.rwin[k];
+            const int2 bias = s.rbias[k];
+            const int s1 = max(rc.x, w.x), e1 = min(rc.y, w.y);
+            if (s1 <= e1) or_span(s.tile + bias.x, s1, e1);
+            const int s2 = max(rc.x, w.z), e2 = min(rc.y, w.w);
+            if (s2 <= e2) or_span(s.tile + bias.y, s2, e2);
         }
     }
 }
@@ -534,7 +593,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         __syncthreads();
         if (okc) {
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) setup_entries<false>(d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd);
+            for (int ci = 0; ci < 4; ++ci) setup_entries<false, false>(s, d, ci * VPOLY_CAP, FCPP_CORNER_POINTS + nv[ci] - 1, rd, rq, Hc, invHc);
         }
         int before[4] = {0, 0, 0, 0}, after[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < 4 && okc; c0 += group) {
@@ -627,6 +686,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
         if (!ok) grid_err = 1;
         __syncthreads();
         if (ok) {
+            if (tid == 0) s.nrect = 0;
             if (tid < 4) {
                 s.fq[tid] = make_int2((int)(qfix(b.field_verts[(int64_t)r.field * 8 + 2 * tid]) - Xc0),
                                       (int)(qfix(b.field_verts[(int64_t)r.field * 8 + 2 * tid + 1]) - Yc0));
@@ -641,7 +701,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             __syncthreads();
             if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
             if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
-            setup_entries<true>(d, 0, nh - 1, rd);
+            setup_entries<true, FCPP_COVER_RECT != 0>(s, d, 0, nh - 1, rd, rq, H, invH);
             __syncthreads();
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
@@ -734,6 +794,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 }
                 __syncthreads();
                 {
+                    fill_rects(s, j0, nrows);
                     auto tgt = [&](int) { return 0; };
                     raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH);
                 }
@@ -830,7 +891,7 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
                 d.pts[k] = make_int2((int)x, (int)y);
             }
             __syncthreads();
-            setup_entries<true>(d, 0, np - 1, (double)rq);
+            setup_entries<true, false>(s, d, 0, np - 1, (double)rq, rq, H, invH);
             __syncthreads();
             auto tgt = [&](int) { return 0; };
             raster_entries(s, d, 0, np - 1, tgt, rq, H, invH);

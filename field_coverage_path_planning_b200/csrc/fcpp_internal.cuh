@@ -14,6 +14,9 @@
 
 #define FCPP_PLAN_THREADS 256
 #define FCPP_COVER_THREADS 512
+#ifndef FCPP_COVER_RECT
+#define FCPP_COVER_RECT 1  // vertical chains as rectangles + end discs (fcpp_cover.cu: setup_entries)
+#endif
 
 // speed classes of a path point (initial speeds)
 enum : uint8_t { CLS_WORK = 0, CLS_TURN = 1, CLS_HEAD = 2, CLS_REVERSE = 3 };
