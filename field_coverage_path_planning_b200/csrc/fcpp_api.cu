@@ -151,6 +151,13 @@ int64_t fcpp_launch_count(const fcpp_handle *h) { return h ? h->launches : 0; }
 int32_t fcpp_last_max_points(const fcpp_handle *h) { return h ? h->last_maxn : 0; }
 int32_t fcpp_last_max_head_points(const fcpp_handle *h) { return h ? h->last_maxhead : 0; }
 
+int fcpp_set_cover_mode(fcpp_handle *h, int mode)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    h->cover_mode = mode;
+    return FCPP_OK;
+}
+
 int fcpp_set_profiling(fcpp_handle *h, int on)
 {
     if (!h) return FCPP_ERR_INVALID;

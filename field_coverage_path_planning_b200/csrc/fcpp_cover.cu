@@ -23,6 +23,9 @@
 //  * every grid row has up to two windows of band cells ([field_lo, main_lo) and (main_hi,
 //    field_hi]); only their words are stored, zeroed, written and counted.
 #include "fcpp_internal.cuh"
+#ifdef FCPP_COVER_DEBUG
+#include <cstdio>
+#endif
 
 namespace {
 
@@ -63,8 +66,12 @@ struct CoverFixed {
     int cnt[8];
     unsigned long long acc[2];
     uint64_t bar;
-    int4 rects[RECT_CAP];  // vertical chains: lattice columns [x, y] on lattice rows [z, w] (see setup_entries)
+    int4 rects[RECT_CAP];  // axis-aligned chains: lattice columns [x, y] on lattice rows [z, w] (see setup_entries)
     int nrect;
+    // zoned band evaluation (see band_zoned): boxes around the general entries, one per field quadrant
+    int4 zbox[4];      // lattice columns [x, y], rows [z, w]; empty: x > y
+    int ztarget[4];    // zone -> target index of the current pass, -1 = not resident
+    int4 zt[4];        // per target of the current pass: zone, first tile word, words per row, unused
 };
 
 // dynamic part, sized by the point capacity pc (>= longest polyline staged)
@@ -272,11 +279,12 @@ __device__ __forceinline__ int axis_class(int2 p, int2 q)
 // 20-point straights of an unrotated rectangular field) are collapsed into their first entry — the
 // union of capsules along one straight line IS the capsule of the whole chain, exactly — and the
 // other entries of the chain get an empty row range.
-// RECT (band only): a VERTICAL chain of >= 2 entries is split, again exactly, into the two end
+// RECT (band only): an axis-aligned chain of >= 2 entries is split, again exactly, into the two end
 // discs (point segments in the chain's first two entries) and the rectangle between them, which
-// needs no per-row geometry at all: on the lattice rows ay <= cy <= by the covered columns are
-// |i H - x| < r, two integers per chain.  The rectangles go to s.rects and are filled by
-// fill_rects, one row per thread, outside the (entry, row) pair scheduler.
+// needs no per-row geometry at all: for a vertical chain the covered columns on the lattice rows
+// ay <= cy <= by are |i H - x| < r (a horizontal chain likewise with rows and columns swapped), four
+// integers per chain.  The rectangles go to s.rects; they are filled by fill_rects, one row per
+// thread, outside the (entry, row) pair scheduler, or counted without any bitmap (band_zoned).
 __device__ __forceinline__ void write_entry(const CoverDyn &d, int e, int2 p, int2 q, double rd)
 {
     if (q.y < p.y || (q.y == p.y && q.x < p.x)) {
@@ -321,20 +329,22 @@ __device__ void setup_entries(CoverFixed &s, const CoverDyn &d, int e0, int n, d
                 while (j < e0 + n && axis_class(d.pts[j], d.pts[j + 1]) == c) ++j;
                 q = d.pts[j];
                 if (RECT && j > e + 1) {
-                    int slot = -1;
-                    if (c >= 3) {
-                        slot = atomicAdd(&s.nrect, 1);
-                        if (slot >= RECT_CAP) slot = -1;  // (the counter is clamped by the reader)
-                    }
+                    int slot = atomicAdd(&s.nrect, 1);
+                    if (slot >= RECT_CAP) slot = -1;  // (the counter is clamped by the readers)
                     if (slot >= 0) {
-                        const int ylo = min(p.y, q.y), yhi = max(p.y, q.y);
-                        const int ia = floor_div_i(p.x - r, H, invH) + 1;      // i H > x - r
-                        const int ib = -floor_div_i(-(p.x + r), H, invH) - 1;  // i H < x + r
-                        const int ja = -floor_div_i(-ylo, H, invH);            // j H >= ylo
-                        const int jb = floor_div_i(yhi, H, invH);              // j H <= yhi
-                        s.rects[slot] = make_int4(ia, ib, ja, jb);
-                        write_entry(d, e, make_int2(p.x, ylo), make_int2(p.x, ylo), rd);
-                        write_entry(d, e + 1, make_int2(p.x, yhi), make_int2(p.x, yhi), rd);
+                        if (c >= 3) {  // vertical: columns |i H - x| < r on the rows ylo <= j H <= yhi
+                            const int ylo = min(p.y, q.y), yhi = max(p.y, q.y);
+                            s.rects[slot] = make_int4(floor_div_i(p.x - r, H, invH) + 1, -floor_div_i(-(p.x + r), H, invH) - 1,
+                                                      -floor_div_i(-ylo, H, invH), floor_div_i(yhi, H, invH));
+                            write_entry(d, e, make_int2(p.x, ylo), make_int2(p.x, ylo), rd);
+                            write_entry(d, e + 1, make_int2(p.x, yhi), make_int2(p.x, yhi), rd);
+                        } else {  // horizontal: rows |j H - y| < r on the columns xlo <= i H <= xhi
+                            const int xlo = min(p.x, q.x), xhi = max(p.x, q.x);
+                            s.rects[slot] = make_int4(-floor_div_i(-xlo, H, invH), floor_div_i(xhi, H, invH),
+                                                      floor_div_i(p.y - r, H, invH) + 1, -floor_div_i(-(p.y + r), H, invH) - 1);
+                            write_entry(d, e, make_int2(xlo, p.y), make_int2(xlo, p.y), rd);
+                            write_entry(d, e + 1, make_int2(xhi, p.y), make_int2(xhi, p.y), rd);
+                        }
                         continue;
                     }
                     write_dead_entry(d, e + 1);
@@ -345,18 +355,19 @@ __device__ void setup_entries(CoverFixed &s, const CoverDyn &d, int e0, int n, d
     }
 }
 
-// the rectangles of the vertical chains on the resident rows [j0, j0 + nrows): one row per thread
-__device__ void fill_rects(CoverFixed &s, int j0, int nrows)
+// the rectangles of the axis-aligned chains on the resident rows [j0, j0 + nrows), which start at
+// tile row koff: one row per thread (columns are clipped by the row's windows)
+__device__ void fill_rects(CoverFixed &s, int j0, int nrows, int koff)
 {
     const int nr = min(s.nrect, RECT_CAP);
-    for (int q = 0; q < nr; ++q) {
-        const int4 rc = s.rects[q];
-        if (rc.x > rc.y) continue;
-        const int lo = max(rc.z, j0), hi = min(rc.w, j0 + nrows - 1);
-        for (int j = lo + (int)threadIdx.x; j <= hi; j += T) {
-            const int k = j - j0;
-            const int4 w = s.rwin[k];
-            const int2 bias = s.rbias[k];
+    for (int k = threadIdx.x; k < nrows; k += T) {
+        const int j = j0 + k;
+        const int4 w = s.rwin[k + koff];
+        const int2 bias = s.rbias[k + koff];
+        if (w.x > w.y && w.z > w.w) continue;
+        for (int q = 0; q < nr; ++q) {
+            const int4 rc = s.rects[q];
+            if (j < rc.z || j > rc.w) continue;
             const int s1 = max(rc.x, w.x), e1 = min(rc.y, w.y);
             if (s1 <= e1) or_span(s.tile + bias.x, s1, e1);
             const int s2 = max(rc.x, w.z), e2 = min(rc.y, w.w);
@@ -387,7 +398,7 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
         int rows[EPT], inc[EPT];
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
-            const int le = tid * EPT + q;
+            const int le = q * T + tid;  // interleaved: the entries of a short polyline spread over all warps
             rows[q] = 0;
             if (le < nb) {
                 const int e = e0 + eb + le;
@@ -414,7 +425,7 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             if (rows[q]) {
                 const int ai = (int)((unsigned)inc[q] >> 21) - 1;
                 const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
-                d.act[ai] = (uint16_t)(tid * EPT + q);
+                d.act[ai] = (uint16_t)(q * T + tid);
                 d.apre[ai] = first;
                 if (table)
                     for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
@@ -512,9 +523,301 @@ __device__ __forceinline__ void zero_words(uint32_t *w, int n)  // rounds n up t
 
 __device__ __forceinline__ int words_of(int lo, int hi) { return hi >= lo ? (hi >> 5) - (lo >> 5) + 1 : 0; }
 
+// lattice-index intervals of row cy inside the closed field quad [x, y] and the closed R-inset
+// [z, w] (empty: lo > hi, normalised to (0, -1))
+__device__ __forceinline__ int4 band_row_raw(const CoverFixed &s, int cy, int H, double invH, int nx)
+{
+    int4 v;
+    quad_row_interval(s.fq, s.qedge[0], s.qtype[0], cy, H, invH, nx, v.x, v.y);
+    quad_row_interval(s.mq, s.qedge[1], s.qtype[1], cy, H, invH, nx, v.z, v.w);
+    return v;
+}
+// band cells of a row: window 1 = [x, y], window 2 = [z, w] (empty: lo > hi) — the cells whose
+// centre lies in the closed field quad and not in the closed R-inset
+__device__ __forceinline__ int4 band_windows_of(int4 v)
+{
+    int4 win = make_int4(1, 0, 1, 0);
+    if (v.x <= v.y) {
+        if (v.z <= v.w) {  // the inset lies inside the field: clamp defensively
+            const int ma = max(v.z, v.x), mb = min(v.w, v.y);
+            win = make_int4(v.x, ma - 1, mb + 1, v.y);
+        } else {
+            win = make_int4(v.x, v.y, 1, 0);
+        }
+    }
+    return win;
+}
+__device__ __forceinline__ int4 band_row_windows(const CoverFixed &s, int cy, int H, double invH, int nx)
+{
+    return band_windows_of(band_row_raw(s, cy, H, invH, nx));
+}
+
+// rows [ylo, yhi] (lattice coordinates) lie entirely below or entirely above the quad
+__device__ __forceinline__ bool outside_rows(const int2 *q, int ylo, int yhi)
+{
+    const int ymin = min(min(q[0].y, q[1].y), min(q[2].y, q[3].y));
+    const int ymax = max(max(q[0].y, q[1].y), max(q[2].y, q[3].y));
+    return yhi < ymin || ylo > ymax;
+}
+
+// quadrant of a live entry: by the midpoint of its segment against the middle of the lattice
+__device__ __forceinline__ int seg_quadrant(const int4 sg, int midx2, int midy2)
+{
+    return ((sg.y + sg.w) >= midy2 ? 2 : 0) | ((sg.x + sg.z) >= midx2 ? 1 : 0);
+}
+
+// number of lattice columns of [a, b] on row j covered by the chain rectangles (sorted by their
+// first column): the classic sweep over sorted intervals
+__device__ __forceinline__ int rect_cover(const CoverFixed &s, int nr, int j, int a, int b)
+{
+    int cur = a - 1, len = 0;
+    for (int q = 0; q < nr; ++q) {
+        const int4 rc = s.rects[q];
+        if (rc.x > b) break;
+        if (j < rc.z || j > rc.w) continue;
+        const int lo = max(rc.x, cur + 1), hi = min(rc.y, b);
+        if (lo <= hi) {
+            len += hi - lo + 1;
+            cur = hi;
+        }
+    }
+    return len;
+}
+
+// Zoned evaluation of the headland band for fields whose straights are axis-aligned chains.
+// Everything that is not a chain rectangle (turn arcs, reverse fills, the joins between loops, the
+// end discs of the chains) sits near the field's corners: these "general" entries are boxed per
+// field quadrant into at most four ZONES, and only the zones get a bitmap (rectangles + general
+// entries, a few thousand words in total instead of the whole band).  Outside the zones a band
+// cell can only be covered by a rectangle, so each row is counted in closed form:
+//     covered(row) = |U ∩ W| - Σ_zones |U ∩ W ∩ Z|   (U = union of the rectangles' column intervals,
+// W = the row's band windows, Z = the zones' column intervals; the zones are pairwise disjoint).
+// Returns false (nothing counted) when the zones overlap or are too large; the caller then runs
+// the row-tiled evaluation of the whole band.
+__device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_ent, int rq, int H, double invH, int nx, int ny,
+                           unsigned long long &my_total, unsigned long long &my_cov)
+{
+    const int tid = threadIdx.x;
+    const int nr = min(s.nrect, RECT_CAP);
+    const int midx2 = (nx - 1) * H, midy2 = (ny - 1) * H;
+    // ---- sort the rectangles by first column (rank by counting), box the general entries ----
+    int4 mine = make_int4(0, 0, 0, 0);
+    int rank = 0;
+    if (tid < nr) {
+        mine = s.rects[tid];
+        for (int q = 0; q < nr; ++q) {
+            const int x = s.rects[q].x;
+            rank += (x < mine.x || (x == mine.x && q < tid)) ? 1 : 0;
+        }
+    }
+    if (tid < 4) s.zbox[tid] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
+    __syncthreads();
+    if (tid < nr) s.rects[rank] = mine;
+    for (int e = tid; e < n_ent; e += T) {
+        const int4 sg = d.seg[e];
+        if (sg.y > sg.w) continue;  // dead entry of a chain
+        const int jlo = max(floor_div_i(sg.y - rq, H, invH) + 1, 0);
+        const int jhi = min(-floor_div_i(-(sg.w + rq), H, invH) - 1, ny - 1);
+        const int cl = max(floor_div_i(min(sg.x, sg.z) - rq, H, invH), 0);
+        const int ch = min(-floor_div_i(-(max(sg.x, sg.z) + rq), H, invH), nx - 1);
+        if (jlo > jhi || cl > ch) continue;  // cannot touch the lattice
+        int4 *zb = &s.zbox[seg_quadrant(sg, midx2, midy2)];
+        atomicMin(&zb->x, cl);
+        atomicMax(&zb->y, ch);
+        atomicMin(&zb->z, jlo);
+        atomicMax(&zb->w, jhi);
+    }
+    __syncthreads();
+    // ---- the zones must be pairwise disjoint and small (uniform decision) ----
+    {
+        bool okz = true;
+        long long words = 0;
+        for (int z = 0; z < 4; ++z) {
+            const int4 a = s.zbox[z];
+            if (a.x > a.y) continue;
+            const int rw = (a.y >> 5) - (a.x >> 5) + 1;
+            words += (long long)rw * (a.w - a.z + 1);
+            if (rw > TW - 16) okz = false;
+            for (int y = z + 1; y < 4; ++y) {
+                const int4 c = s.zbox[y];
+                if (c.x <= c.y && a.x <= c.y && c.x <= a.y && a.z <= c.w && c.z <= a.w) okz = false;
+            }
+        }
+        if (words > 12ll * TW) okz = false;
+#ifdef FCPP_COVER_DEBUG
+        if (tid == 0 && (blockIdx.x % 512) == 0) {
+            printf("cand %d nrect %d okz %d words %lld\n", (int)blockIdx.x, nr, (int)okz, words);
+            for (int z = 0; z < 4; ++z) printf("  zone %d cols [%d,%d] rows [%d,%d]\n", z, s.zbox[z].x, s.zbox[z].y, s.zbox[z].z, s.zbox[z].w);
+        }
+#endif
+        if (!okz) return false;
+    }
+
+    // ---- bitmap passes over the zones: whole zones are packed into one tile while they fit, a
+    // zone larger than the tile is cut into row ranges (every thread derives the same packing) ----
+    int z = 0, zrow = 0;
+    while (true) {
+        int nt = 0, used_w = 0, used_r = 0;
+        __syncthreads();  // the previous pass is done with s.tg / s.zt / s.ztarget
+        if (tid < 4) s.ztarget[tid] = -1;
+        __syncthreads();
+        while (z < 4 && nt < 4) {
+            const int4 box = s.zbox[z];
+            if (box.x > box.y) {
+                ++z;
+                zrow = 0;
+                continue;
+            }
+            const int rw = (box.y >> 5) - (box.x >> 5) + 1;
+            const int zrows = box.w - box.z + 1;
+            const int n = min(zrows - zrow, min((TW - used_w) / rw, ROWCAP - used_r));
+            if (n <= 0) break;
+            if (tid == 0) {
+                Target &t = s.tg[nt];
+                t.j0 = box.z + zrow;
+                t.nrows = n;
+                t.koff = used_r;
+                s.zt[nt] = make_int4(z, used_w, rw, 0);
+                s.ztarget[z] = nt;
+            }
+            used_w += (n * rw + 3) & ~3;
+            used_r += n;
+            ++nt;
+            zrow += n;
+            if (zrow < zrows) break;  // a cut zone ends the pass
+            ++z;
+            zrow = 0;
+        }
+        if (nt == 0) break;
+        __syncthreads();
+        // row windows of the resident rows, clipped to their zone's columns
+        for (int k = tid; k < used_r; k += T) {
+            int t = 0;
+            while (t + 1 < nt && k >= s.tg[t + 1].koff) ++t;
+            const Target tg = s.tg[t];
+            const int4 zt = s.zt[t];
+            const int4 box = s.zbox[zt.x];
+            int4 win = band_row_windows(s, (tg.j0 + (k - tg.koff)) * H, H, invH, nx);
+            win.x = max(win.x, box.x);
+            win.y = min(win.y, box.y);
+            win.z = max(win.z, box.x);
+            win.w = min(win.w, box.y);
+            const int base = zt.y + (k - tg.koff) * zt.z - (box.x >> 5);
+            s.rwin[k] = win;
+            s.rbias[k] = make_int2(base, base);
+        }
+        zero_words(s.tile, used_w);
+        __syncthreads();
+        for (int t = 0; t < nt; ++t) fill_rects(s, s.tg[t].j0, s.tg[t].nrows, s.tg[t].koff);
+        {
+            auto tgt = [&](int e) {
+                const int4 sg = d.seg[e];
+                return (sg.y > sg.w) ? -1 : s.ztarget[seg_quadrant(sg, midx2, midy2)];
+            };
+            raster_entries(s, d, 0, n_ent, tgt, rq, H, invH);
+        }
+        my_cov += (unsigned long long)count_words(s.tile, used_w);
+    }
+    // ---- every row in closed form: band cells, rectangle cover outside the zones.  Rows are
+    // grouped into runs between BREAKPOINTS (rows where a rectangle or a zone starts or ends, and
+    // the rows of the quads' vertices): inside a run the rectangles and zones are the same and each
+    // of the four window boundaries follows ONE quad edge, i.e. is monotone in the row — if it has
+    // the same lattice index on the first and the last row of the run it has it on every row, and
+    // the run is counted once and multiplied.  Runs with slanted boundaries go row by row. ----
+    __syncthreads();  // the last pass is done with the tile: reuse it for the breakpoints
+    int *bp = reinterpret_cast<int *>(s.tile);  // [nb] sorted breakpoints, then [nb] slow runs (lo, hi)
+    const int nb = 10 + 2 * nr + 8;
+    {
+        int v = -1;
+        if (tid == 0) v = 0;
+        else if (tid == 1) v = ny;
+        else if (tid < 10) {
+            const int y = (tid < 6) ? s.fq[tid - 2].y : s.mq[tid - 6].y;
+            v = -floor_div_i(-y, H, invH);  // first row at or above the vertex
+        } else if (tid < 10 + 2 * nr) {
+            const int4 rc = s.rects[(tid - 10) >> 1];
+            v = (tid & 1) ? rc.w + 1 : rc.z;
+        } else if (tid < nb) {
+            const int4 box = s.zbox[(tid - 10 - 2 * nr) >> 1];
+            v = (box.x > box.y) ? 0 : ((tid & 1) ? box.w + 1 : box.z);
+        }
+        v = min(max(v, 0), ny);
+        int *raw = bp + 2 * nb + 2;
+        if (tid < nb) raw[tid] = v;
+        __syncthreads();
+        if (tid < nb) {
+            int rk = 0;
+            for (int q = 0; q < nb; ++q) {
+                const int x = raw[q];
+                rk += (x < v || (x == v && q < tid)) ? 1 : 0;
+            }
+            bp[rk] = v;
+        }
+        if (tid == 0) s.cnt[0] = 0;
+        __syncthreads();
+    }
+    // one thread per (run, end): the raw row intervals of the run's first and last row
+    int4 *rraw = reinterpret_cast<int4 *>(bp + 4 * nb);  // [2 nb], 16-byte aligned (nb is even)
+    if (tid < 2 * (nb - 1)) {
+        const int i = tid >> 1;
+        const int lo = bp[i], hi = bp[i + 1] - 1;
+        if (lo <= hi) rraw[tid] = band_row_raw(s, ((tid & 1) ? hi : lo) * H, H, invH, nx);
+    }
+    __syncthreads();
+    // part p of a row's count: p = 0 the whole window pair, p = 1 + q what lies in zone q (subtracted)
+    auto row_part = [&](int j, int4 win, int p, unsigned long long mult) {
+        int4 box = make_int4(INT_MIN, INT_MAX, INT_MIN, INT_MAX);
+        if (p > 0) {
+            box = s.zbox[p - 1];
+            if (box.x > box.y || j < box.z || j > box.w) return;
+        }
+        int cov = 0, cells = 0;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int a = max(w ? win.z : win.x, box.x), b = min(w ? win.w : win.y, box.y);
+            if (a > b) continue;
+            cells += b - a + 1;
+            cov += rect_cover(s, nr, j, a, b);
+        }
+        if (p == 0) {
+            my_total += mult * (unsigned long long)cells;
+            my_cov += mult * (unsigned long long)cov;
+        } else {
+            my_cov -= mult * (unsigned long long)cov;
+        }
+    };
+    int2 *slow = reinterpret_cast<int2 *>(bp + nb);
+    for (int u = tid; u < 5 * (nb - 1); u += T) {
+        const int i = u / 5, p = u - 5 * i;
+        const int lo = bp[i], hi = bp[i + 1] - 1;
+        if (lo > hi) continue;
+        const int4 v0 = rraw[2 * i], v1 = rraw[2 * i + 1];
+        bool same = v0.x == v1.x && v0.y == v1.y && v0.z == v1.z && v0.w == v1.w;
+        // an EMPTY interval at both ends proves nothing about the rows between (a sliver thinner
+        // than a cell) unless the whole run lies below or above the quad
+        if (hi > lo && v0.x > v0.y) same = same && outside_rows(s.fq, lo * H, hi * H);
+        if (hi > lo && v0.z > v0.w) same = same && outside_rows(s.mq, lo * H, hi * H);
+        if (same)
+            row_part(lo, band_windows_of(v0), p, (unsigned long long)(hi - lo + 1));
+        else if (p == 0)
+            slow[atomicAdd(&s.cnt[0], 1)] = make_int2(lo, hi);
+    }
+    __syncthreads();
+    const int nslow = s.cnt[0];
+    for (int q = 0; q < nslow; ++q) {
+        const int2 run = slow[q];
+        for (int j = run.x + tid; j <= run.y; j += T) {
+            const int4 win = band_row_windows(s, j * H, H, invH, nx);
+            for (int p = 0; p < 5; ++p) row_part(j, win, p, 1ull);
+        }
+    }
+    __syncthreads();  // the caller may reuse the tile
+    return true;
+}
+
 __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
                                                      const TrigTables *__restrict__ trig,
-                                                     fcpp_summary *__restrict__ summary, int pc)
+                                                     fcpp_summary *__restrict__ summary, int pc, int mode)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
@@ -706,6 +1009,10 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
             if (tid == 0) s.next_w0 = 0;
+            // axis-aligned straights: bitmap only around the corners, the rest in closed form
+            if (FCPP_COVER_RECT && !(mode & 1) && s.nrect > 0 &&
+                band_zoned(s, d, nh - 1, rq, H, invH, nx, ny, my_total, my_cov))
+                j0 = ny;
             while (j0 < ny) {
                 // --- how many rows to try: from the word count of the first row.  The previous pass
                 // has usually computed it already (its first row that did not fit) ---
@@ -738,19 +1045,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     int4 win = make_int4(1, 0, 1, 0);
                     int n1 = 0;
                     if (k < rows_try) {
-                        int fa, fb, ma, mb;
-                        const int cy = (j0 + k) * H;
-                        quad_row_interval(s.fq, s.qedge[0], s.qtype[0], cy, H, invH, nx, fa, fb);
-                        quad_row_interval(s.mq, s.qedge[1], s.qtype[1], cy, H, invH, nx, ma, mb);
-                        if (fa <= fb) {
-                            if (ma <= mb) {  // the inset lies inside the field: clamp defensively
-                                ma = max(ma, fa);
-                                mb = min(mb, fb);
-                                win = make_int4(fa, ma - 1, mb + 1, fb);
-                            } else {
-                                win = make_int4(fa, fb, 1, 0);
-                            }
-                        }
+                        win = band_row_windows(s, (j0 + k) * H, H, invH, nx);
                         n1 = words_of(win.x, win.y);
                         wcnt[q] = n1 + words_of(win.z, win.w);
                         cells[q] = max(win.y - win.x + 1, 0) + max(win.w - win.z + 1, 0);
@@ -794,7 +1089,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 }
                 __syncthreads();
                 {
-                    fill_rects(s, j0, nrows);
+                    fill_rects(s, j0, nrows, 0);
                     auto tgt = [&](int) { return 0; };
                     raster_entries(s, d, 0, nh - 1, tgt, rq, H, invH);
                 }
@@ -837,7 +1132,7 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
     const size_t bytes = cover_smem_bytes(pc);
     cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc);
+    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc, h->cover_mode);
     h->launches++;
     return cudaGetLastError();
 }

@@ -76,6 +76,7 @@ struct fcpp_handle {
     int last_maxn;
     int last_maxhead;
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
+    int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation
     int64_t layout_ncand;
     void *d_ga;              // GA workspace (two populations, lengths, fitness, ranks, state, best route)
     size_t ga_bytes;

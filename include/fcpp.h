@@ -305,6 +305,12 @@ int32_t fcpp_last_max_head_points(const fcpp_handle *h);
 int fcpp_set_profiling(fcpp_handle *h, int on);
 int fcpp_kernel_times(fcpp_handle *h, float *ms3);
 
+/* Diagnostics: coverage-kernel evaluation mode of the following fcpp_plan_batch calls.  0 = automatic
+ * (default): the headland band of a field whose straights are axis-aligned is evaluated "zoned"
+ * (bitmap around the corners, closed form elsewhere), any other field row-tiled.  Bit 0 set = always
+ * row-tiled.  Both give identical counts (tests/test_gpu_parity.py compares them). */
+int fcpp_set_cover_mode(fcpp_handle *h, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -352,6 +352,57 @@ def test_config5_large_field_fine_grid(fc):
     _summary_vs_oracle(s[0], o)
 
 
+def test_band_zoned_equals_row_tiled_and_oracle(fc):
+    """The coverage kernel evaluates the headland band of fields with axis-aligned straights "zoned"
+    (bitmap around the corners + closed-form rows) and every other field row-tiled.
+    Both must give the same integers: compared here on BASELINE config 2 at full size, config 5
+    geometry, small / offset / sheared / mixed fields and several grid pitches, with a sample of every
+    case against the brute-force oracle."""
+    from field_coverage_path_planning_b200 import _lib
+    from oracle import batch as ob, ref_planner as rp
+    h = _lib.handle(0)
+
+    def both(fields, veh, cand, **kw):
+        try:
+            h.check(h.lib.fcpp_set_cover_mode(h.h, 1))
+            tiled = fc.plan_batch(fields, veh, cand, **kw).summary
+        finally:
+            h.check(h.lib.fcpp_set_cover_mode(h.h, 0))
+        auto = fc.plan_batch(fields, veh, cand, **kw).summary
+        assert auto.tobytes() == tiled.tobytes()
+        return auto
+
+    veh = fc.VehicleParams()
+    cand = fc.make_candidates(1, radii=np.linspace(5.0, 12.0, 1024), start_corners=[0, 1, 2, 3])
+    s = both([RECT], veh, cand, obstacles=[OBST2])
+    assert (s["status"] == 0).all() and (s["cov_cells"] > 0).all()
+    # config 5 geometry, radii across the range (zones larger than one tile at R = 12)
+    big = [(0, 0), (2000, 0), (2000, 1000), (0, 1000)]
+    both([big], veh, fc.make_candidates(1, radii=[5.0, 7.3, 9.6, 12.0], start_corners=[0, 1, 2, 3]), grid_h=0.05)
+    # small, offset, sheared (horizontal chains only), tilted (no chains) and non-origin fields in one batch
+    fields = [
+        [(0, 0), (60, 0), (60, 45), (0, 45)],
+        [(1000.3, 2000.7), (1180.3, 2000.7), (1180.3, 2075.7), (1000.3, 2075.7)],
+        [(0, 0), (500, 0), (580, 200), (80, 200)],
+        [(0, 0), (300, 40), (280, 190), (-20, 150)],
+        [(-250.05, -100.02), (249.95, -100.02), (249.95, 99.98), (-250.05, 99.98)],
+        [(0, 0), (45, 0), (45, 300), (0, 300)],
+    ]
+    cand = fc.make_candidates(len(fields), radii=[5.0, 6.4, 8.0, 11.0], start_corners=[0, 1, 2, 3])
+    for gh in (0.1, 0.05, 0.25):
+        s = both(fields, veh, cand, grid_h=gh)
+    for wv in (2.0, 4.5):
+        both(fields, fc.VehicleParams(working_width=wv), cand)
+    # the oracle (brute force per cell) on a sample of the last batch set-up
+    s = both(fields, veh, cand)
+    for b in range(0, len(s), 7):
+        if s["status"][b]:
+            continue
+        o = ob.evaluate_candidate(fields[int(cand["field_id"][b])], rp.VehicleParams(), R=cand["R"][b],
+                                  start_corner=int(cand["start_corner"][b]))
+        assert int(s["cov_total"][b]) == o["cov_total"] and int(s["cov_cells"][b]) == o["cov_cells"], b
+
+
 def test_integration_md_ctypes_stub_runs(fc):
     """The reference-side ctypes stub printed in INTEGRATION.md is executed verbatim (only the
     library path is made absolute) and must reproduce the drop-in planner's result."""
