@@ -31,9 +31,16 @@ namespace {
 
 constexpr int T = FCPP_COVER_THREADS;
 constexpr int NWARP = T / 32;
-constexpr int TW = 8192;        // occupancy tile, 32-bit words (32 KB)
-constexpr int ROWCAP = 1024;    // grid rows per tile (4 per thread)
-constexpr int VPOLY_CAP = 192;  // verification polyline (15-pt arc + reverse fill), per corner
+#ifndef FCPP_COVER_TW
+#define FCPP_COVER_TW 8192
+#define FCPP_COVER_ROWCAP 1024
+#define FCPP_COVER_VPOLY 192
+#define FCPP_COVER_MINBLOCKS 2
+#endif
+constexpr int TW = FCPP_COVER_TW;          // occupancy tile, 32-bit words (32 KB)
+constexpr int ROWCAP = FCPP_COVER_ROWCAP;  // grid rows per tile (a multiple of T)
+constexpr int VPOLY_CAP = FCPP_COVER_VPOLY;  // verification polyline (15-pt arc + reverse fill), per corner
+static_assert(ROWCAP % T == 0, "row windows are computed ROWCAP / T rows per thread");
 constexpr int ICAP = 1024;      // item -> active-entry table
 constexpr int EPT = 2;          // entries per thread in a scheduling batch
 constexpr int EBATCH = EPT * T; // entries per scheduling batch
@@ -74,41 +81,35 @@ struct CoverFixed {
     int4 zt[4];        // per target of the current pass: zone, first tile word, words per row, unused
 };
 
-// dynamic part, sized by the point capacity pc (>= longest polyline staged)
-struct CoverDyn {
-    int2 *pts;        // [pc] snapped points relative to their lattice origin (staging; aliased by erow)
-    int2 *erow;       // [pc] per pass: first resident lattice row of the entry, its tile row
-    int4 *seg;        // [pc] entry e = pts[e] -> pts[e+1] with the lower end first: ax, ay, bx, by
-    double2 *og;      // [pc] (ox, oy) = r*(dy, dx)/len; oy = +inf if dy == 0
-    double *kk;       // [pc] dx/dy
-    int *apre;        // [EBATCH + 1] exclusive (entry,row)-pair prefix over the ACTIVE entries
-    uint16_t *act;    // [EBATCH] active entries (batch-local index)
-    uint16_t *item_first;  // [ICAP] active index holding the first pair of an item
+// Dynamic part, behind CoverFixed in the same dynamic shared-memory allocation: the scheduling
+// tables (fixed size) and one 48-byte record per polyline segment ("entry"; capacity pc >= longest
+// polyline staged).  Everything is addressed from the extern shared array itself, i.e. with
+// compile-time offsets: no pointer lives in a register (a struct of eight pointers handed to the
+// rasteriser by reference ended up in LOCAL memory and cost eight L1-missing loads per item).
+struct Entry {
+    int4 seg;     // pts[e] -> pts[e+1] with the lower end first: ax, ay, bx, by
+    double2 og;   // (ox, oy) = r*(dy, dx)/len; oy = +inf if dy == 0
+    double kk;    // dx/dy
+    int2 erow;    // staging: the snapped point e relative to its lattice origin; per raster pass: first
+                  // resident lattice row of the entry, its tile row (the points are dead by then)
 };
+static_assert(sizeof(Entry) == 48, "Entry layout");
 
-__host__ __device__ inline size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
-// pc is a multiple of 16, so every array below starts 16-byte aligned without further rounding
-constexpr size_t DYN_TAIL = sizeof(int) * (EBATCH + 16) + sizeof(uint16_t) * EBATCH + sizeof(uint16_t) * ICAP;
-__host__ __device__ inline size_t cover_smem_bytes(int pc)
-{
-    return a16(sizeof(CoverFixed)) + (size_t)pc * (sizeof(int2) + sizeof(int4) + sizeof(double2) + sizeof(double)) +
-           DYN_TAIL;
-}
-__device__ __forceinline__ CoverDyn carve_dyn(unsigned char *base, int pc)
-{
-    CoverDyn d;
-    unsigned char *p = base + a16(sizeof(CoverFixed));
-    d.pts = (int2 *)p;
-    d.erow = d.pts;  // the points are dead once setup_entries has built the segment records
-    d.seg = (int4 *)(p + (size_t)pc * 8);
-    d.og = (double2 *)(p + (size_t)pc * 24);
-    d.kk = (double *)(p + (size_t)pc * 40);
-    p += (size_t)pc * 48;
-    d.apre = (int *)p;
-    d.act = (uint16_t *)(p + sizeof(int) * (EBATCH + 16));
-    d.item_first = d.act + EBATCH;
-    return d;
-}
+extern __shared__ __align__(16) unsigned char cover_smem[];
+
+__host__ __device__ constexpr size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
+constexpr size_t OFF_APRE = a16(sizeof(CoverFixed));                 // int [EBATCH + 16]: exclusive (entry,row)-pair
+                                                                     // prefix over the ACTIVE entries
+constexpr size_t OFF_ACT = OFF_APRE + sizeof(int) * (EBATCH + 16);   // uint16 [EBATCH]: active entries (batch-local)
+constexpr size_t OFF_ITEM = OFF_ACT + sizeof(uint16_t) * EBATCH;     // uint16 [ICAP]: active index holding an item's first pair
+constexpr size_t OFF_ENT = a16(OFF_ITEM + sizeof(uint16_t) * ICAP);  // Entry [pc]
+struct CoverDyn {
+    __device__ __forceinline__ Entry &ent(int e) const { return reinterpret_cast<Entry *>(cover_smem + OFF_ENT)[e]; }
+    __device__ __forceinline__ int *apre() const { return reinterpret_cast<int *>(cover_smem + OFF_APRE); }
+    __device__ __forceinline__ uint16_t *act() const { return reinterpret_cast<uint16_t *>(cover_smem + OFF_ACT); }
+    __device__ __forceinline__ uint16_t *item_first() const { return reinterpret_cast<uint16_t *>(cover_smem + OFF_ITEM); }
+};
+__host__ __device__ inline size_t cover_smem_bytes(int pc) { return OFF_ENT + (size_t)pc * sizeof(Entry); }
 
 // exact floor(a / H) for |a| < 2^31, 0 < H < 2^20 through FP64 + integer correction
 __device__ __forceinline__ int floor_div_i(int a, int H, double invH)
@@ -292,42 +293,42 @@ __device__ __forceinline__ void write_entry(const CoverDyn &d, int e, int2 p, in
         p = q;
         q = t;
     }
-    d.seg[e] = make_int4(p.x, p.y, q.x, q.y);
+    d.ent(e).seg = make_int4(p.x, p.y, q.x, q.y);
     const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y);
     if (dy == 0.0) {  // horizontal segment or point: the general formula with oy = +inf
-        d.og[e] = make_double2(0.0, INFINITY);
-        d.kk[e] = 0.0;
+        d.ent(e).og = make_double2(0.0, INFINITY);
+        d.ent(e).kk = 0.0;
     } else {
         const double len = sqrt(dx * dx + dy * dy);
-        d.og[e] = make_double2(rd * dy / len, rd * dx / len);
-        d.kk[e] = dx / dy;
+        d.ent(e).og = make_double2(rd * dy / len, rd * dx / len);
+        d.ent(e).kk = dx / dy;
     }
 }
 __device__ __forceinline__ void write_dead_entry(const CoverDyn &d, int e)
 {
-    d.seg[e] = make_int4(0, 1 << 30, 0, -(1 << 30));
-    d.og[e] = make_double2(0.0, INFINITY);
-    d.kk[e] = 0.0;
+    d.ent(e).seg = make_int4(0, 1 << 30, 0, -(1 << 30));
+    d.ent(e).og = make_double2(0.0, INFINITY);
+    d.ent(e).kk = 0.0;
 }
 
 template <bool MERGE, bool RECT>
 __device__ void setup_entries(CoverFixed &s, const CoverDyn &d, int e0, int n, double rd, int r, int H, double invH)
 {
     for (int e = e0 + threadIdx.x; e < e0 + n; e += T) {
-        const int2 p = d.pts[e];
-        int2 q = d.pts[e + 1];
+        const int2 p = d.ent(e).erow;
+        int2 q = d.ent(e + 1).erow;
         if (MERGE) {
             const int c = axis_class(p, q);
             if (c) {
-                if (e > e0 && axis_class(d.pts[e - 1], p) == c) {  // inside a chain
+                if (e > e0 && axis_class(d.ent(e - 1).erow, p) == c) {  // inside a chain
                     // the chain's second entry is written by the thread of its first (RECT)
-                    const bool second = !(e - 1 > e0 && axis_class(d.pts[e - 2], d.pts[e - 1]) == c);
+                    const bool second = !(e - 1 > e0 && axis_class(d.ent(e - 2).erow, d.ent(e - 1).erow) == c);
                     if (!(RECT && second)) write_dead_entry(d, e);
                     continue;
                 }
                 int j = e + 1;
-                while (j < e0 + n && axis_class(d.pts[j], d.pts[j + 1]) == c) ++j;
-                q = d.pts[j];
+                while (j < e0 + n && axis_class(d.ent(j).erow, d.ent(j + 1).erow) == c) ++j;
+                q = d.ent(j).erow;
                 if (RECT && j > e + 1) {
                     int slot = atomicAdd(&s.nrect, 1);
                     if (slot >= RECT_CAP) slot = -1;  // (the counter is clamped by the readers)
@@ -404,14 +405,14 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                 const int e = e0 + eb + le;
                 const int ti = tgt(e);
                 if (ti >= 0) {
-                    const int4 sg = d.seg[e];
+                    const int4 sg = d.ent(e).seg;
                     const Target t = s.tg[ti];
                     int jlo = floor_div_i(sg.y - r, H, invH) + 1;      // cy > ymin - r
                     int jhi = -floor_div_i(-(sg.w + r), H, invH) - 1;  // cy < ymax + r
                     jlo = max(jlo, t.j0);
                     jhi = min(jhi, t.j0 + t.nrows - 1);
                     if (jhi >= jlo) rows[q] = jhi - jlo + 1;
-                    d.erow[e] = make_int2(jlo, jlo - t.j0 + t.koff);
+                    d.ent(e).erow = make_int2(jlo, jlo - t.j0 + t.koff);
                 }
             }
             inc[q] = rows[q] ? ((1 << 21) | rows[q]) : 0;
@@ -425,13 +426,13 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             if (rows[q]) {
                 const int ai = (int)((unsigned)inc[q] >> 21) - 1;
                 const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
-                d.act[ai] = (uint16_t)(q * T + tid);
-                d.apre[ai] = first;
+                d.act()[ai] = (uint16_t)(q * T + tid);
+                d.apre()[ai] = first;
                 if (table)
-                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first[i] = (uint16_t)ai;
+                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first()[i] = (uint16_t)ai;
             }
         }
-        if (tid == 0) d.apre[n_act] = n_pairs;
+        if (tid == 0) d.apre()[n_act] = n_pairs;
         __syncthreads();
         // items go to the warps round-robin (handing them out through a shared counter was measured
         // twice and lost 2.5-4.5 %: the atomic sits on every item's critical path)
@@ -441,14 +442,14 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             // ---- pair -> active entry: the entry boundaries inside this item as a bit mask ----
             int base_ai;
             if (table) {
-                base_ai = d.item_first[item];
+                base_ai = d.item_first()[item];
             } else {  // upper_bound over the pair prefix (one lane), then broadcast
                 int lo = 0;
                 if (lane == 0) {
                     int hi = n_act - 1;
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if (d.apre[mid] <= pbase)
+                        if (d.apre()[mid] <= pbase)
                             lo = mid;
                         else
                             hi = mid - 1;
@@ -457,19 +458,19 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
                 base_ai = __shfl_sync(0xffffffffu, lo, 0);
             }
             const int bidx = base_ai + 1 + lane;
-            const int bnd = (bidx <= n_act) ? d.apre[bidx] : 0x7fffffff;  // > pbase: entry base_ai holds pair pbase
+            const int bnd = (bidx <= n_act) ? d.apre()[bidx] : 0x7fffffff;  // > pbase: entry base_ai holds pair pbase
             const unsigned mbit = (bnd < pbase + 32) ? (1u << ((bnd - pbase) & 31)) : 0u;
             const unsigned bmask = __reduce_or_sync(0xffffffffu, mbit);
             const int p = pbase + lane;
             item = next_item;
             if (p >= n_pairs) continue;
             const int ai = base_ai + __popc(bmask & ((2u << lane) - 1u));
-            const int e = e0 + eb + d.act[ai];
-            const int qrow = p - d.apre[ai];
-            const int4 sg = d.seg[e];
-            const int2 er = d.erow[e];
-            const double2 og = d.og[e];
-            const double kk = d.kk[e];
+            const int e = e0 + eb + d.act()[ai];
+            const int qrow = p - d.apre()[ai];
+            const int4 sg = d.ent(e).seg;
+            const int2 er = d.ent(e).erow;
+            const double2 og = d.ent(e).og;
+            const double kk = d.ent(e).kk;
             const int k = er.y + qrow;
             const int cy = (er.x + qrow) * H;
             const double ax = (double)sg.x, bx = (double)sg.z;
@@ -614,7 +615,7 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
     __syncthreads();
     if (tid < nr) s.rects[rank] = mine;
     for (int e = tid; e < n_ent; e += T) {
-        const int4 sg = d.seg[e];
+        const int4 sg = d.ent(e).seg;
         if (sg.y > sg.w) continue;  // dead entry of a chain
         const int jlo = max(floor_div_i(sg.y - rq, H, invH) + 1, 0);
         const int jhi = min(-floor_div_i(-(sg.w + rq), H, invH) - 1, ny - 1);
@@ -711,7 +712,7 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
         for (int t = 0; t < nt; ++t) fill_rects(s, s.tg[t].j0, s.tg[t].nrows, s.tg[t].koff);
         {
             auto tgt = [&](int e) {
-                const int4 sg = d.seg[e];
+                const int4 sg = d.ent(e).seg;
                 return (sg.y > sg.w) ? -1 : s.ztarget[seg_quadrant(sg, midx2, midy2)];
             };
             raster_entries(s, d, 0, n_ent, tgt, rq, H, invH);
@@ -815,13 +816,12 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
     return true;
 }
 
-__global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
+__global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
                                                      const TrigTables *__restrict__ trig,
                                                      fcpp_summary *__restrict__ summary, int pc, int mode)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
-    const CoverDyn d = carve_dyn(smem_raw, pc);
+    CoverFixed &s = *reinterpret_cast<CoverFixed *>(cover_smem);
+    const CoverDyn d;
     const int tid = threadIdx.x;
     const int64_t cand = blockIdx.x;
     fcpp_summary *sum = summary + cand;
@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                     x = r.vrev[ci][0] + tt_ * r.vrev[ci][2];
                     y = r.vrev[ci][1] + tt_ * r.vrev[ci][3];
                 }
-                d.pts[ci * VPOLY_CAP + k] = make_int2((int)(qfix(x) - X0), (int)(qfix(y) - Y0));
+                d.ent(ci * VPOLY_CAP + k).erow = make_int2((int)(qfix(x) - X0), (int)(qfix(y) - Y0));
             }
         }
         __syncthreads();
@@ -999,7 +999,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
                 double x, y;
                 uint8_t c;
                 gen_point(r, s.tt, tm, W, r.n_main + k, x, y, c);
-                d.pts[k] = make_int2((int)(qfix(x) - Xc0), (int)(qfix(y) - Yc0));
+                d.ent(k).erow = make_int2((int)(qfix(x) - Xc0), (int)(qfix(y) - Yc0));
             }
             __syncthreads();
             if (tid < 4) quad_edges_setup(s.fq, s.qedge[0], s.qtype[0], tid);
@@ -1119,7 +1119,7 @@ __global__ void __launch_bounds__(T, 2) cover_kernel(const fcpp_batch b, const C
 int cover_point_capacity(int max_head)
 {
     const int pc = max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP;
-    return (pc + 63) / 64 * 64 + 16;  // a multiple of 16 (carve_dyn)
+    return (pc + 63) / 64 * 64 + 16;  // a multiple of 16
 }
 
 }  // namespace
@@ -1150,9 +1150,8 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
 {
     // one CTA; rows are processed in tiles of the shared occupancy buffer, then merged into the
     // caller's row-major g x g bit grid (bit j*g+i)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoverFixed &s = *reinterpret_cast<CoverFixed *>(smem_raw);
-    const CoverDyn d = carve_dyn(smem_raw, WIN_PC);
+    CoverFixed &s = *reinterpret_cast<CoverFixed *>(cover_smem);
+    const CoverDyn d;
     const int tid = threadIdx.x;
     const int64_t X0 = qfix(ox), Y0 = qfix(oy);
     const int H = (int)qfix(hc);
@@ -1183,7 +1182,7 @@ __global__ void __launch_bounds__(T) window_kernel(const double *__restrict__ pa
                 int64_t x = qfix(path[2 * (p0 + k)]) - X0, y = qfix(path[2 * (p0 + k) + 1]) - Y0;
                 x = x < -lim ? -lim : (x > lim ? lim : x);
                 y = y < -lim ? -lim : (y > lim ? lim : y);
-                d.pts[k] = make_int2((int)x, (int)y);
+                d.ent(k).erow = make_int2((int)x, (int)y);
             }
             __syncthreads();
             setup_entries<true, false>(s, d, 0, np - 1, (double)rq, rq, H, invH);

@@ -13,7 +13,9 @@
 #include "../../include/fcpp.h"
 
 #define FCPP_PLAN_THREADS 256
+#ifndef FCPP_COVER_THREADS
 #define FCPP_COVER_THREADS 512
+#endif
 #ifndef FCPP_COVER_RECT
 #define FCPP_COVER_RECT 1  // vertical chains as rectangles + end discs (fcpp_cover.cu: setup_entries)
 #endif
