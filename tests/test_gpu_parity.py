@@ -393,6 +393,12 @@ def test_band_zoned_equals_row_tiled_and_oracle(fc):
         s = both(fields, veh, cand, grid_h=gh)
     for wv in (2.0, 4.5):
         both(fields, fc.VehicleParams(working_width=wv), cand)
+    # many narrow loops: K = 12, 15 and 16 headland loops (48-64 chain rectangles = the cap)
+    narrow = [[(0, 0), (120, 0), (120, 90), (0, 90)]]
+    s = both(narrow, fc.VehicleParams(working_width=0.8), fc.make_candidates(1, radii=[9.6, 12.0, 12.8], start_corners=[0, 3]))
+    assert (s["status"] == 0).all() and list(s["n_loops"][::2]) == [12, 15, 16]
+    o = ob.evaluate_candidate(narrow[0], rp.VehicleParams(working_width=0.8), R=12.8, start_corner=3)
+    assert int(s["cov_total"][5]) == o["cov_total"] and int(s["cov_cells"][5]) == o["cov_cells"]
     # the oracle (brute force per cell) on a sample of the last batch set-up
     s = both(fields, veh, cand)
     for b in range(0, len(s), 7):
