@@ -79,6 +79,16 @@ def batch_case(fc, name, fields, cand, obstacles, grid_h, outputs, cpu_n):
     total = int(first.offsets[-1]) if outputs == "paths" else 0
     bufs = BatchBuffers(dev, pb.n_cand, pb.n_fields, total)
     ms = time_gpu(lambda: run_device_batch(db, outputs, buffers=bufs, fetch=False))
+    # per-kernel CUDA-event times of one more step (layout+scan, plan, coverage)
+    import ctypes as C
+    from field_coverage_path_planning_b200 import _lib
+    h = _lib.handle(0)
+    h.check(h.lib.fcpp_set_profiling(h.h, 1))
+    run_device_batch(db, outputs, buffers=bufs, fetch=False)
+    torch.cuda.synchronize()
+    ms3 = (C.c_float * 3)()
+    h.check(h.lib.fcpp_kernel_times(h.h, C.byref(ms3)))
+    h.check(h.lib.fcpp_set_profiling(h.h, 0))
     t0 = time.perf_counter()
     for _ in range(3):
         fc.plan_batch(fields, veh, cand, obstacles=obstacles, outputs=outputs, grid_h=grid_h)
@@ -95,7 +105,8 @@ def batch_case(fc, name, fields, cand, obstacles, grid_h, outputs, cpu_n):
     return {"config": name, "candidates": B, "outputs": outputs, "grid_h": grid_h,
             "points_per_plan_mean": float((s["n_main"] + s["n_head"]).mean()),
             "band_cells_mean": float(s["cov_total"].mean()),
-            "gpu_ms": ms, "gpu_plans_per_s": B / (ms / 1e3), "e2e_s": e2e, "e2e_plans_per_s": B / e2e,
+            "gpu_ms": ms, "kernel_ms": {"layout": ms3[0], "plan": ms3[1], "cover": ms3[2]},
+            "gpu_plans_per_s": B / (ms / 1e3), "e2e_s": e2e, "e2e_plans_per_s": B / e2e,
             "cpu_plans_per_s": cr, "cpu_cores": cores, "cpu_sample": cpu_n,
             "n_boundary_viol_mean": float(s["n_boundary_viol"].mean()),
             "coverage_rate_mean": float((s["cov_cells"] / np.maximum(s["cov_total"], 1)).mean())}

@@ -112,6 +112,7 @@ int fcpp_create(int device, fcpp_handle **out)
     h->device = device;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     TrigTables t;
     host_tables(t);
     cudaError_t e = cudaMalloc((void **)&h->d_trig, sizeof(TrigTables));

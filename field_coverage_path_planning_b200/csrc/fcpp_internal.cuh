@@ -71,6 +71,7 @@ struct fcpp_handle {
     int *d_maxn;             // device: [max n_total, max n_head] of the last layout pass
     int *h_maxn;             // pinned host mirror
     int max_smem_optin;
+    int max_smem_sm;         // shared memory per SM
     int sm_count;
     bool layout_valid;
     bool profiling;

@@ -17,8 +17,7 @@
 
 namespace {
 
-constexpr int T = FCPP_PLAN_THREADS;
-constexpr int NWARP = T / 32;
+constexpr int T0 = FCPP_PLAN_THREADS;  // threads per CTA of the smallest variant; plan_kernel also runs at 2x and 4x
 
 struct PlanArgs {
     // GEN
@@ -52,12 +51,13 @@ struct Smem {
     double *obs_xy;    // [obs_cap_verts][2]
     int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
     double *obs_bb;    // [obs_cap_polys][4] bbox of each obstacle grown by W/2 + 1e-6 (early reject)
-    double *scratch;   // [128]
+    double *scratch;   // [SCRATCH]
     uint64_t *bar;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+constexpr int SCRATCH = 320;  // block reductions: 9 values x 32 warps
 __host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int obs_polys)
 {
     size_t s = 0;
@@ -68,7 +68,7 @@ __host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int o
     s += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
     s += align16(sizeof(int32_t) * (obs_polys + 1));
     s += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
-    s += align16(sizeof(double) * 128);
+    s += align16(sizeof(double) * SCRATCH);
     s += 16;
     return s;
 }
@@ -96,7 +96,7 @@ __device__ inline Smem carve(unsigned char *base, int ncap, int obs_verts, int o
     s.obs_bb = (double *)(base + o);
     o += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
     s.scratch = (double *)(base + o);
-    o += align16(sizeof(double) * 128);
+    o += align16(sizeof(double) * SCRATCH);
     s.bar = (uint64_t *)(base + o);
     return s;
 }
@@ -173,7 +173,7 @@ __device__ __forceinline__ double warp_max(double v)
 }
 
 // reduce NV sums / maxes across the block (deterministic order); result valid in thread 0
-template <int NV, bool IS_MAX>
+template <int NV, bool IS_MAX, int NWARP>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double *sh)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -266,7 +266,7 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
 
 // One plan (GEN) or one caller-supplied path (!GEN).  `s` points at the staging arrays (shared
 // memory in plan_kernel, an HBM/L2 scratch slice in plan_big_kernel), `cap` is their capacity.
-template <bool GEN, bool BIG>
+template <bool GEN, bool BIG, int T>
 __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
                                           const uint32_t phase)
 {
@@ -633,8 +633,8 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
     }
     double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
                       acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
-    block_reduce<9, false>(sums, s.scratch);
-    block_reduce<3, true>(mx, s.scratch);
+    block_reduce<9, false, T / 32>(sums, s.scratch);
+    block_reduce<3, true, T / 32>(mx, s.scratch);
     if (tid == 0 && sum) {
         sum->status = 0;
         if (!GEN) {
@@ -663,24 +663,27 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
     }
 }
 
-template <bool GEN>
 #ifndef FCPP_PLAN_MIN_CTAS
 #define FCPP_PLAN_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(T, FCPP_PLAN_MIN_CTAS) plan_kernel(const PlanArgs a)
+// T threads per CTA: T0 (256) when four or more CTAs fit an SM, 2*T0 / 4*T0 when the staging of long
+// plans leaves room for only two / one (a 2 km x 1 km plan has 7 191 points = 180 KB): the SM keeps
+// ~32 resident warps either way
+template <bool GEN, int T>
+__global__ void __launch_bounds__(T, (T0 * FCPP_PLAN_MIN_CTAS) / T) plan_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
     if (threadIdx.x == 0) mbar_init(s.bar, 1);
     __syncthreads();
-    plan_body<GEN, false>(a, s, blockIdx.x, a.ncap, 0);
+    plan_body<GEN, false, T>(a, s, blockIdx.x, a.ncap, 0);
 }
 
 // Plans that do not fit the shared-memory staging (N > ~9000 points, e.g. a 5 km x 3 km field):
 // a few persistent CTAs walk the batch and run the same body with x/y/u/class staged in a
 // per-CTA slice of library-owned HBM (L2-resident in practice).
 template <bool GEN>
-__global__ void __launch_bounds__(T, 3) plan_big_kernel(const PlanArgs a)
+__global__ void __launch_bounds__(T0, 3) plan_big_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s = carve(smem_raw, 0, a.obs_cap_verts, a.obs_cap_polys);
@@ -696,17 +699,31 @@ __global__ void __launch_bounds__(T, 3) plan_big_kernel(const PlanArgs a)
     for (int64_t c = blockIdx.x; c < a.n_items; c += gridDim.x) {
         const int n = GEN ? a.recs[c].n_total : (int)(a.in_offsets[c + 1] - a.in_offsets[c]);
         if (n <= a.ncap) continue;  // handled by plan_kernel
-        plan_body<GEN, true>(a, s, c, a.big_ncap, phase);
+        plan_body<GEN, true, T0>(a, s, c, a.big_ncap, phase);
         if (GEN) phase ^= 1u;
         __syncthreads();
     }
 }
 
+// configure + launch plan_kernel with the thread count that keeps ~32 warps resident per SM
+template <bool GEN, int T>
+cudaError_t launch_variant(const PlanArgs &a, int64_t n, size_t bytes, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(plan_kernel<GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    plan_kernel<GEN, T><<<(unsigned)n, T, bytes, st>>>(a);
+    return cudaGetLastError();
+}
 template <bool GEN>
-cudaError_t configure(fcpp_handle *h, size_t bytes)
+cudaError_t launch_plan_kernel(fcpp_handle *h, const PlanArgs &a, int64_t n, size_t bytes, cudaStream_t st)
 {
     if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
-    return cudaFuncSetAttribute(plan_kernel<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const size_t per_sm = (size_t)h->max_smem_sm;
+    const int fit = (int)(per_sm / (bytes + 1024));  // CTAs per SM by shared memory (1 KB reserved each)
+    h->launches++;
+    if (fit >= 4) return launch_variant<GEN, T0>(a, n, bytes, st);
+    if (fit >= 2) return launch_variant<GEN, 2 * T0>(a, n, bytes, st);
+    return launch_variant<GEN, 4 * T0>(a, n, bytes, st);
 }
 
 // launch plan_big_kernel when the longest plan exceeds the shared-memory capacity
@@ -730,7 +747,7 @@ cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_poi
     a.big_stride = stride;
     a.n_items = n_items;
     const size_t bytes = plan_smem_bytes(0, a.obs_cap_verts, a.obs_cap_polys);
-    plan_big_kernel<GEN><<<(unsigned)ctas, T, bytes, st>>>(a);
+    plan_big_kernel<GEN><<<(unsigned)ctas, T0, bytes, st>>>(a);
     h->launches++;
     return cudaGetLastError();
 }
@@ -769,11 +786,7 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     a.big_enabled = big ? 1 : 0;
     a.n_items = b.n_cand;
     const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
-    cudaError_t e = configure<true>(h, bytes);
-    if (e != cudaSuccess) return e;
-    plan_kernel<true><<<(unsigned)b.n_cand, T, bytes, st>>>(a);
-    h->launches++;
-    e = cudaGetLastError();
+    cudaError_t e = launch_plan_kernel<true>(h, a, b.n_cand, bytes, st);
     if (e == cudaSuccess && big) e = launch_big<true>(h, a, b.n_cand, h->plan_ncap_hint, st);
     return e;
 }
@@ -799,11 +812,7 @@ cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, co
     a.big_enabled = big ? 1 : 0;
     a.n_items = n_paths;
     const size_t bytes = plan_smem_bytes(a.ncap, 0, 0);
-    cudaError_t e = configure<false>(h, bytes);
-    if (e != cudaSuccess) return e;
-    plan_kernel<false><<<(unsigned)n_paths, T, bytes, st>>>(a);
-    h->launches++;
-    e = cudaGetLastError();
+    cudaError_t e = launch_plan_kernel<false>(h, a, n_paths, bytes, st);
     if (e == cudaSuccess && big) e = launch_big<false>(h, a, n_paths, want, st);
     return e;
 }
