@@ -65,7 +65,7 @@ class Batch(C.Structure):
         ("max_points_hint", C.c_int32),
         ("max_head_points_hint", C.c_int32),
         ("turn_model", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("cover_dedupe", C.c_int32),
         ("clothoid_share", C.c_double),
     ]
 

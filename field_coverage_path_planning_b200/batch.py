@@ -135,6 +135,7 @@ class PreparedBatch:
     coverage: bool
     turn_model: str = "arc"
     clothoid_share: float = 0.5
+    dedupe: bool = False
 
     def h2d_bytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays.values()))
@@ -215,7 +216,7 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
     if turn_model not in ("arc", "clothoid"):
         raise ValueError("turn_model must be 'arc' (the reference's sampled arcs) or 'clothoid'")
     return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage), turn_model,
-                         float(clothoid_share))
+                         float(clothoid_share), dedupe="heading" in candidates and B > F)
 
 
 class DeviceBatch:
@@ -241,6 +242,8 @@ class DeviceBatch:
         b.grid_h = pb.grid_h
         b.do_coverage = 1 if pb.coverage else 0
         b.turn_model = 1 if pb.turn_model == "clothoid" else 0
+        # a heading search repeats the headland (hence the coverage) of a field for every heading
+        b.cover_dedupe = 1 if pb.dedupe else 0
         b.clothoid_share = pb.clothoid_share
         self.c = b
 

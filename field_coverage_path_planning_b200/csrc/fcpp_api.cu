@@ -138,6 +138,7 @@ void fcpp_destroy(fcpp_handle *h)
     if (h->d_maxn) cudaFree(h->d_maxn);
     if (h->h_maxn) cudaFreeHost(h->h_maxn);
     if (h->d_ga) cudaFree(h->d_ga);
+    if (h->d_dedupe) cudaFree(h->d_dedupe);
     if (h->h_ga_state) cudaFreeHost(h->h_ga_state);
     if (h->ga_stream) cudaStreamDestroy(h->ga_stream);
     for (int k = 0; k < 4; ++k)

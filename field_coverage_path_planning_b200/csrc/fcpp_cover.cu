@@ -818,8 +818,12 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
 
 __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
                                                      const TrigTables *__restrict__ trig,
-                                                     fcpp_summary *__restrict__ summary, int pc, int mode)
+                                                     fcpp_summary *__restrict__ summary, int pc, int mode,
+                                                     const int32_t *__restrict__ rep)
 {
+    // candidates whose coverage inputs equal those of an earlier candidate (heading search: the
+    // headland does not depend on the heading) take its counts afterwards (cover_copy_kernel)
+    if (rep && rep[blockIdx.x] != (int32_t)blockIdx.x) return;
     CoverFixed &s = *reinterpret_cast<CoverFixed *>(cover_smem);
     const CoverDyn d;
     const int tid = threadIdx.x;
@@ -1124,6 +1128,100 @@ int cover_point_capacity(int max_head)
 
 }  // namespace
 
+
+// ---------------------------------------------------------------------------------------------
+// Coverage de-duplication.  A10 / A11 depend on the field, R, W, the start corner and the turn
+// model only — not on the heading or the pass order — so in a heading search (BASELINE config 3:
+// 180 headings per field) 179 of 180 candidates repeat the coverage of another one.  Candidates
+// are grouped by a 64-bit hash of every CandRec field the coverage kernel reads (open-addressing
+// table, lowest candidate index per key), the group's first candidate is VERIFIED field by field
+// (a hash collision only costs the saving, never correctness), the kernel runs for one
+// representative per group and the others copy its integers.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__device__ bool cover_same(const CandRec &a, const CandRec &b)
+{
+    const bool da = a.status != 0 || a.n_total == 0, db = b.status != 0 || b.n_total == 0;
+    if (a.status != b.status || a.field != b.field || da != db) return false;
+    if (da) return true;
+    bool same = a.K == b.K && a.n_head == b.n_head && a.corner_g == b.corner_g &&
+                (a.flags & COVER_FLAG_MASK) == (b.flags & COVER_FLAG_MASK) && dbits(a.R) == dbits(b.R);
+    for (int k = 0; k < 3; ++k) same = same && a.n_rev[k] == b.n_rev[k];
+    for (int k = 0; k < 4; ++k) same = same && a.vn_rev[k] == b.vn_rev[k];
+    for (int k = 0; k < 8; ++k) same = same && dbits((&a.main_quad[0][0])[k]) == dbits((&b.main_quad[0][0])[k]);
+    for (int k = 0; k < 15; ++k) same = same && dbits((&a.rev[0][0])[k]) == dbits((&b.rev[0][0])[k]);
+    for (int k = 0; k < 20; ++k) same = same && dbits((&a.vrev[0][0])[k]) == dbits((&b.vrev[0][0])[k]);
+    for (int k = 0; same && k < 8 * a.K; ++k)
+        same = dbits((&a.corners[0][0][0])[k]) == dbits((&b.corners[0][0][0])[k]);
+    return same;
+}
+
+// table slot: key (0 = empty) and 0x7fffffff - (lowest candidate index) kept with atomicMax.  The
+// table is zeroed when it is allocated and every batch clears the slots it used (cover_copy_kernel),
+// so the steady state has no memset
+__global__ void __launch_bounds__(128) cover_key_kernel(const CandRec *__restrict__ recs, int64_t n,
+                                                        unsigned long long *__restrict__ keys,
+                                                        unsigned int *__restrict__ vals, uint32_t cap_mask,
+                                                        unsigned long long *__restrict__ hash)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const unsigned long long h = recs[c].cover_key;  // hashed by the layout kernel
+    hash[c] = h;
+    uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&keys[slot], 0ull, h);
+        if (prev == 0ull || prev == h) {
+            atomicMax(&vals[slot], 0x7fffffffu - (unsigned int)c);
+            return;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+}
+
+__global__ void __launch_bounds__(128) cover_rep_kernel(const CandRec *__restrict__ recs, int64_t n,
+                                                        const unsigned long long *__restrict__ keys,
+                                                        const unsigned int *__restrict__ vals, uint32_t cap_mask,
+                                                        unsigned long long *__restrict__ hash,
+                                                        int32_t *__restrict__ rep)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const unsigned long long h = hash[c];
+    uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
+    while (keys[slot] != h) slot = (slot + 1) & cap_mask;
+    hash[c] = slot;  // remembered for the clean-up
+    const int64_t first = (int64_t)(0x7fffffffu - vals[slot]);
+    rep[c] = (first < c && cover_same(recs[c], recs[first])) ? (int32_t)first : (int32_t)c;
+}
+
+__global__ void __launch_bounds__(128) cover_copy_kernel(fcpp_summary *__restrict__ summary, int64_t n,
+                                                         const int32_t *__restrict__ rep,
+                                                         unsigned long long *__restrict__ keys,
+                                                         unsigned int *__restrict__ vals,
+                                                         const unsigned long long *__restrict__ slot_of)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t slot = (uint32_t)slot_of[c];  // leave the table empty for the next batch
+    keys[slot] = 0ull;
+    vals[slot] = 0u;
+    const int32_t q = rep[c];
+    if (q == (int32_t)c) return;
+    const fcpp_summary &src = summary[q];
+    fcpp_summary &dst = summary[c];
+    dst.cov_cells = src.cov_cells;
+    dst.cov_total = src.cov_total;
+    for (int k = 0; k < 4; ++k) {
+        dst.corner_before[k] = src.corner_before[k];
+        dst.corner_after[k] = src.corner_after[k];
+    }
+    if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+}
+
+}  // namespace
+
 cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st)
 {
     if (b.n_cand == 0) return cudaSuccess;
@@ -1132,8 +1230,46 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
     const size_t bytes = cover_smem_bytes(pc);
     cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc, h->cover_mode);
+    // de-duplication (asked for by the batch, unless switched off by cover mode bit 1)
+    int32_t *d_rep = nullptr;
+    unsigned long long *keys = nullptr, *hash = nullptr;
+    unsigned int *vals = nullptr;
+    const int64_t n = b.n_cand;
+    if (b.cover_dedupe && n > 1 && !(h->cover_mode & 2) && n < (1ll << 30)) {
+        uint32_t cap = 1024;
+        while ((int64_t)cap < 2 * n) cap <<= 1;
+        const size_t need = (size_t)cap * 12 + (size_t)n * 12 + 64;
+        if (need > h->dedupe_bytes) {
+            if (h->d_dedupe) cudaFree(h->d_dedupe);
+            h->d_dedupe = nullptr;
+            h->dedupe_bytes = 0;
+            e = cudaMalloc(&h->d_dedupe, need);
+            if (e != cudaSuccess) return e;
+            h->dedupe_bytes = need;
+            h->dedupe_cap = 0;
+        }
+        // layout: keys [cap] | vals [cap] | hash / slot [n] | rep [n]; a different capacity moves the
+        // arrays, so the table is zeroed again
+        keys = (unsigned long long *)h->d_dedupe;
+        vals = (unsigned int *)(keys + cap);
+        hash = (unsigned long long *)(vals + cap);
+        d_rep = (int32_t *)(hash + n);
+        if (h->dedupe_cap != cap) {
+            e = cudaMemsetAsync(h->d_dedupe, 0, (size_t)cap * 12, st);
+            if (e != cudaSuccess) return e;
+            h->dedupe_cap = cap;
+        }
+        const unsigned g = (unsigned)((n + 127) / 128);
+        cover_key_kernel<<<g, 128, 0, st>>>(h->d_rec, n, keys, vals, cap - 1, hash);
+        cover_rep_kernel<<<g, 128, 0, st>>>(h->d_rec, n, keys, vals, cap - 1, hash, d_rep);
+        h->launches += 2;
+    }
+    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc, h->cover_mode, d_rep);
     h->launches++;
+    if (d_rep) {
+        cover_copy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(o.summary, n, d_rep, keys, vals, hash);
+        h->launches++;
+    }
     return cudaGetLastError();
 }
 

@@ -49,7 +49,7 @@ struct __align__(16) CandRec {
     double min_x, min_y, max_x, max_y;  // swath-frame bounds of the work area (mlp3:731-732)
     double cx, cy;                      // rotation centre (work-area centroid, mlp3:690, :710)
     double cos_a, sin_a;                // rotate-back (mlp3:709-714)
-    double pad0;
+    uint64_t cover_key;                 // hash of every field the coverage kernel reads (de-duplication)
     double main_quad[4][2];             // R-inset of the field (mlp3:594-595), D1
     double rev[3][5];                   // loop-0 reverse fills: ex, ey, dx, dy, length (mlp3:1154-1218)
     double vrev[4][5];                  // verification corners (mlp3:1531-1554)
@@ -79,7 +79,11 @@ struct fcpp_handle {
     int last_maxn;
     int last_maxhead;
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
-    int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation
+    int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation,
+                             // bit 1 = no coverage de-duplication
+    void *d_dedupe;          // coverage de-duplication: hash table, hashes, representatives
+    size_t dedupe_bytes;
+    uint32_t dedupe_cap;     // slots of the (currently zeroed) table inside d_dedupe; 0 = not initialised
     int64_t layout_ncand;
     void *d_ga;              // GA workspace (two populations, lengths, fitness, ranks, state, best route)
     size_t ga_bytes;
@@ -87,6 +91,36 @@ struct fcpp_handle {
     cudaStream_t ga_stream;  // capture stream of the generation graph
     char err[512];
 };
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t w)
+{
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+__device__ __forceinline__ uint64_t dbits(double x) { return (uint64_t)__double_as_longlong(x); }
+
+constexpr int COVER_FLAG_MASK = FCPP_FLAG_CORNER_MASK | FCPP_FLAG_GAP_GATE;
+
+// hash of every CandRec field the coverage kernel reads (fcpp_cover.cu: coverage de-duplication)
+__device__ __forceinline__ uint64_t cover_key(const CandRec &r)
+{
+    uint64_t h = 0x243F6A8885A308D3ull;
+    const bool dead = r.status != 0 || r.n_total == 0;
+    h = mix64(h, ((uint64_t)(uint32_t)r.status << 32) | (uint32_t)r.field);
+    h = mix64(h, dead ? 1u : 0u);
+    if (dead) return h | 1ull;  // all dead candidates of a field share zero counts
+    h = mix64(h, ((uint64_t)(uint32_t)r.K << 32) | (uint32_t)r.n_head);
+    h = mix64(h, ((uint64_t)(uint32_t)(r.flags & COVER_FLAG_MASK) << 32) | (uint32_t)r.corner_g);
+    for (int k = 0; k < 3; ++k) h = mix64(h, (uint32_t)r.n_rev[k]);
+    for (int k = 0; k < 4; ++k) h = mix64(h, (uint32_t)r.vn_rev[k]);
+    h = mix64(h, dbits(r.R));
+    for (int k = 0; k < 8; ++k) h = mix64(h, dbits((&r.main_quad[0][0])[k]));
+    for (int k = 0; k < 15; ++k) h = mix64(h, dbits((&r.rev[0][0])[k]));
+    for (int k = 0; k < 20; ++k) h = mix64(h, dbits((&r.vrev[0][0])[k]));
+    for (int k = 0; k < 8 * r.K; ++k) h = mix64(h, dbits((&r.corners[0][0][0])[k]));
+    return h | 1ull;  // 0 marks an empty slot
+}
+
 
 // ---------------------------------------------------------------------------------------
 // small helpers

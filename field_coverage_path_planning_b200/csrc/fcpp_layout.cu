@@ -213,12 +213,12 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
     r.cy = cy;
     r.cos_a = b.cand_rot[4 * c + 2];
     r.sin_a = b.cand_rot[4 * c + 3];
-    r.pad0 = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         r.main_quad[k][0] = mq[k][0];
         r.main_quad[k][1] = mq[k][1];
     }
+    r.cover_key = cover_key(r);
     if (n_pts) n_pts[c] = r.n_total;
     return r.n_total;
 }

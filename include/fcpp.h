@@ -107,7 +107,9 @@ typedef struct {
     int32_t turn_model;            /* 0: the reference's sampled circular arcs (mlp3:807-830, :1046-1062);
                                       1: clothoid -> arc -> clothoid turns with Fresnel integrals evaluated
                                       per sample point on the device (same sample counts, same layout) */
-    int32_t reserved0;
+    int32_t cover_dedupe;     /* 1: candidates whose coverage inputs are identical (same field, R, start corner — e.g.
+                               * the headings of a heading search) are rasterised once and share the counts; 0: every
+                               * candidate is rasterised.  Same integers either way. */
     double clothoid_share;         /* share of a turn's deflection spent on the two clothoids, (0, 1] */
 } fcpp_batch;
 
@@ -308,7 +310,9 @@ int fcpp_kernel_times(fcpp_handle *h, float *ms3);
 /* Diagnostics: coverage-kernel evaluation mode of the following fcpp_plan_batch calls.  0 = automatic
  * (default): the headland band of a field whose straights are axis-aligned is evaluated "zoned"
  * (bitmap around the corners, closed form elsewhere), any other field row-tiled.  Bit 0 set = always
- * row-tiled.  Both give identical counts (tests/test_gpu_parity.py compares them). */
+ * row-tiled.  Bit 1 set = no coverage de-duplication (by default candidates whose coverage inputs are
+ * identical — same field, R, start corner; e.g. the headings of a heading search — are rasterised once
+ * and share the counts).  All modes give identical counts (tests/test_gpu_parity.py compares them). */
 int fcpp_set_cover_mode(fcpp_handle *h, int mode);
 
 #ifdef __cplusplus

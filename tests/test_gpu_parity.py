@@ -362,14 +362,16 @@ def test_band_zoned_equals_row_tiled_and_oracle(fc):
     from oracle import batch as ob, ref_planner as rp
     h = _lib.handle(0)
 
-    def both(fields, veh, cand, **kw):
-        try:
-            h.check(h.lib.fcpp_set_cover_mode(h.h, 1))
-            tiled = fc.plan_batch(fields, veh, cand, **kw).summary
-        finally:
-            h.check(h.lib.fcpp_set_cover_mode(h.h, 0))
+    def both(fields, veh, cand, modes=(1,), **kw):
+        """mode bit 0: row-tiled band only; bit 1: no coverage de-duplication"""
         auto = fc.plan_batch(fields, veh, cand, **kw).summary
-        assert auto.tobytes() == tiled.tobytes()
+        for mode in modes:
+            try:
+                h.check(h.lib.fcpp_set_cover_mode(h.h, mode))
+                other = fc.plan_batch(fields, veh, cand, **kw).summary
+            finally:
+                h.check(h.lib.fcpp_set_cover_mode(h.h, 0))
+            assert auto.tobytes() == other.tobytes(), mode
         return auto
 
     veh = fc.VehicleParams()
@@ -393,6 +395,18 @@ def test_band_zoned_equals_row_tiled_and_oracle(fc):
         s = both(fields, veh, cand, grid_h=gh)
     for wv in (2.0, 4.5):
         both(fields, fc.VehicleParams(working_width=wv), cand)
+    # heading search (BASELINE config 3 in small): the coverage of a field does not depend on the
+    # heading, so it is rasterised once per (field, R, start corner) and shared — same integers as
+    # rasterising every candidate (mode 2), also with duplicated and dead candidates in the batch
+    hc = fc.make_candidates(len(fields), headings=np.deg2rad(np.arange(0.0, 180.0, 15.0)), radii=[6.0, 8.0],
+                            start_corners=[0, 2])
+    s = both(fields, veh, hc, modes=(1, 2, 3))
+    per = s["cov_cells"].reshape(len(fields), 12, 4)
+    assert (per == per[:, :1, :]).all() and (s["cov_cells"] > 0).all()
+    tiny = [[(0, 0), (30, 0), (30, 15), (0, 15)]] + fields[:2]       # field 0: inset empty -> dead candidates
+    tc = fc.make_candidates(3, headings=[0.0, 0.3], radii=[8.0, 8.0], start_corners=[1])
+    s = both(tiny, veh, tc, modes=(2,))
+    assert (s["status"][:4] != 0).all() and (s["cov_total"][:4] == 0).all() and (s["cov_total"][4:] > 0).all()
     # many narrow loops: K = 12, 15 and 16 headland loops (48-64 chain rectangles = the cap)
     narrow = [[(0, 0), (120, 0), (120, 90), (0, 90)]]
     s = both(narrow, fc.VehicleParams(working_width=0.8), fc.make_candidates(1, radii=[9.6, 12.0, 12.8], start_corners=[0, 3]))
