@@ -33,6 +33,8 @@ struct PlanArgs {
     int do_speed_plan;
     // both
     int ncap;          // smem capacity in points
+    int nmin;          // this launch handles nmin < N <= ncap (tiers by plan length, see launch_tiers)
+    int defer;         // 1: a later launch with a larger staging handles N > ncap
     int obs_cap_verts; // smem capacity for obstacle vertices
     int obs_cap_polys;
     // plans longer than the shared-memory staging go through plan_big_kernel (HBM/L2 staging)
@@ -673,6 +675,10 @@ template <bool GEN, int T>
 __global__ void __launch_bounds__(T, (T0 * FCPP_PLAN_MIN_CTAS) / T) plan_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.nmin >= 0 || a.defer) {  // tiered launch: is this plan in this tier's length range?
+        const int n = GEN ? a.recs[blockIdx.x].n_total : (int)(a.in_offsets[blockIdx.x + 1] - a.in_offsets[blockIdx.x]);
+        if (n <= a.nmin || (a.defer && n > a.ncap)) return;
+    }
     const Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
     if (threadIdx.x == 0) mbar_init(s.bar, 1);
     __syncthreads();
@@ -714,16 +720,54 @@ cudaError_t launch_variant(const PlanArgs &a, int64_t n, size_t bytes, cudaStrea
     plan_kernel<GEN, T><<<(unsigned)n, T, bytes, st>>>(a);
     return cudaGetLastError();
 }
-template <bool GEN>
-cudaError_t launch_plan_kernel(fcpp_handle *h, const PlanArgs &a, int64_t n, size_t bytes, cudaStream_t st)
+// largest point capacity whose staging lets `ctas` CTAs share one SM (1 KB reserved per CTA)
+int capacity_for_ctas(fcpp_handle *h, int obs_verts, int obs_polys, int ctas)
 {
-    if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
-    const size_t per_sm = (size_t)h->max_smem_sm;
-    const int fit = (int)(per_sm / (bytes + 1024));  // CTAs per SM by shared memory (1 KB reserved each)
-    h->launches++;
-    if (fit >= 4) return launch_variant<GEN, T0>(a, n, bytes, st);
-    if (fit >= 2) return launch_variant<GEN, 2 * T0>(a, n, bytes, st);
-    return launch_variant<GEN, 4 * T0>(a, n, bytes, st);
+    const size_t budget = (size_t)h->max_smem_sm / ctas - 1024;
+    int lo = 0, hi = 1 << 20;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        const size_t b = plan_smem_bytes(mid, obs_verts, obs_polys);
+        if (b <= budget && b <= (size_t)h->max_smem_optin)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo / 64 * 64;
+}
+
+// One launch when the longest plan of the batch leaves room for four CTAs per SM (BASELINE config 2).
+// A batch of mixed lengths (config 3: the plan length follows the heading) is cut into up to three
+// TIERS by plan length — N <= cap4 at T0 threads and four CTAs per SM, cap4 < N <= cap2 at 2*T0 and
+// two, longer at 4*T0 and one — so that short plans do not inherit the occupancy of the longest.
+// Every tier launches one CTA per candidate; CTAs outside the tier's range exit on one 4-byte read.
+template <bool GEN>
+cudaError_t launch_tiers(fcpp_handle *h, PlanArgs &a, int64_t n, int want, int cap_max, bool big, cudaStream_t st)
+{
+    const int cap4 = capacity_for_ctas(h, a.obs_cap_verts, a.obs_cap_polys, 4);
+    const int cap2 = capacity_for_ctas(h, a.obs_cap_verts, a.obs_cap_polys, 2);
+    const int last = (want > 0 && want < cap_max) ? want : cap_max;
+    int caps[3], nt = 0;
+    if (last > cap4 && cap4 >= 256) caps[nt++] = cap4;
+    if (last > cap2 && cap2 > cap4) caps[nt++] = cap2;
+    caps[nt++] = last;
+    int prev = -1;
+    for (int t = 0; t < nt; ++t) {
+        a.ncap = caps[t];
+        a.nmin = prev;
+        a.defer = (t + 1 < nt) ? 1 : 0;
+        a.big_enabled = (t + 1 == nt && big) ? 1 : 0;
+        const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+        if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
+        const int fit = (int)((size_t)h->max_smem_sm / (bytes + 1024));
+        h->launches++;
+        cudaError_t e = fit >= 4   ? launch_variant<GEN, T0>(a, n, bytes, st)
+                        : fit >= 2 ? launch_variant<GEN, 2 * T0>(a, n, bytes, st)
+                                   : launch_variant<GEN, 4 * T0>(a, n, bytes, st);
+        if (e != cudaSuccess) return e;
+        prev = caps[t];
+    }
+    return cudaSuccess;
 }
 
 // launch plan_big_kernel when the longest plan exceeds the shared-memory capacity
@@ -785,8 +829,7 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     const bool big = h->plan_ncap_hint > a.ncap;
     a.big_enabled = big ? 1 : 0;
     a.n_items = b.n_cand;
-    const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
-    cudaError_t e = launch_plan_kernel<true>(h, a, b.n_cand, bytes, st);
+    cudaError_t e = launch_tiers<true>(h, a, b.n_cand, h->plan_ncap_hint, a.ncap, big, st);
     if (e == cudaSuccess && big) e = launch_big<true>(h, a, b.n_cand, h->plan_ncap_hint, st);
     return e;
 }
@@ -811,8 +854,7 @@ cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, co
     const bool big = want > a.ncap;
     a.big_enabled = big ? 1 : 0;
     a.n_items = n_paths;
-    const size_t bytes = plan_smem_bytes(a.ncap, 0, 0);
-    cudaError_t e = launch_plan_kernel<false>(h, a, n_paths, bytes, st);
+    cudaError_t e = launch_tiers<false>(h, a, n_paths, want > 0 ? want : a.ncap, a.ncap, big, st);
     if (e == cudaSuccess && big) e = launch_big<false>(h, a, n_paths, want, st);
     return e;
 }
