@@ -166,20 +166,27 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
     R = np.ascontiguousarray(candidates.get("R", np.full(B, vehicle.min_turn_radius)), dtype=np.float64)
     if "heading" in candidates:
         ang_c = np.ascontiguousarray(candidates["heading"], dtype=np.float64)
+        rot = np.stack([np.cos(-ang_c), np.sin(-ang_c), np.cos(ang_c), np.sin(ang_c)], axis=1)
+        rotated = np.abs(ang_c) > ROT_THRESHOLD
     else:
+        # the reference's heading is a property of the field (mlp3:244-263): trig per field, gathered
         e0 = fv[:, 1, :] - fv[:, 0, :]
-        ang_c = np.arctan2(e0[:, 1], e0[:, 0])[fid]  # mlp3:244-263
-    rot = np.stack([np.cos(-ang_c), np.sin(-ang_c), np.cos(ang_c), np.sin(ang_c)], axis=1)
-    flags = np.zeros(B, dtype=np.int32)
+        ang_f = np.arctan2(e0[:, 1], e0[:, 0])
+        rot = np.take(np.stack([np.cos(-ang_f), np.sin(-ang_f), np.cos(ang_f), np.sin(ang_f)], axis=1), fid, axis=0)
+        rotated = np.take(np.abs(ang_f) > ROT_THRESHOLD, fid)
     if "start_corner" in candidates:
         c = np.asarray(candidates["start_corner"], dtype=np.int32)
         if B and (c.min() < 0 or c.max() > 3):
             raise ValueError("start_corner must be 0..3")
-        flags |= c
-        flags |= np.where((c == 2) | (c == 3), _lib.FLAG_REVERSE_ORDER, 0).astype(np.int32)
-        flags |= np.where((c == 1) | (c == 2), _lib.FLAG_START_FROM_RIGHT, 0).astype(np.int32)
-    flags |= np.where(np.abs(ang_c) > ROT_THRESHOLD, _lib.FLAG_ROTATED, 0).astype(np.int32)
-    flags |= np.where(G.gap_gate(R, W), _lib.FLAG_GAP_GATE, 0).astype(np.int32)
+        # corner c in {0: LB, 1: RB, 2: RT, 3: LT}: reverse order iff c in {2, 3}, start from the right
+        # iff c in {1, 2} (mlp3:650-658)
+        hi = c >> 1
+        flags = c | (hi * _lib.FLAG_REVERSE_ORDER) | (((c ^ hi) & 1) * _lib.FLAG_START_FROM_RIGHT)
+        flags = flags.astype(np.int32, copy=False)
+    else:
+        flags = np.zeros(B, dtype=np.int32)
+    flags |= rotated.astype(np.int32) * _lib.FLAG_ROTATED
+    flags |= G.gap_gate(R, W).astype(np.int32) * _lib.FLAG_GAP_GATE
     arrays = {
         "field_verts": fv, "field_extent": np.ascontiguousarray(ext), "field_flags": fflags,
         "cand_field": fid, "cand_R": R, "cand_rot": np.ascontiguousarray(rot), "cand_flags": flags,
