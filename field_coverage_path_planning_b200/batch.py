@@ -223,7 +223,8 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
     if turn_model not in ("arc", "clothoid"):
         raise ValueError("turn_model must be 'arc' (the reference's sampled arcs) or 'clothoid'")
     return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage), turn_model,
-                         float(clothoid_share), dedupe="heading" in candidates and B > F)
+                         float(clothoid_share),
+                         dedupe=B > F and ("heading" in candidates or "start_corner" in candidates))
 
 
 class DeviceBatch:
@@ -249,7 +250,8 @@ class DeviceBatch:
         b.grid_h = pb.grid_h
         b.do_coverage = 1 if pb.coverage else 0
         b.turn_model = 1 if pb.turn_model == "clothoid" else 0
-        # a heading search repeats the headland (hence the coverage) of a field for every heading
+        # the headings of a field repeat its headland (hence its coverage), its start corners repeat the
+        # corner-window verification: identical coverage work is done once per group on the device
         b.cover_dedupe = 1 if pb.dedupe else 0
         b.clothoid_share = pb.clothoid_share
         self.c = b

@@ -819,11 +819,14 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
 __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
                                                      const TrigTables *__restrict__ trig,
                                                      fcpp_summary *__restrict__ summary, int pc, int mode,
-                                                     const int32_t *__restrict__ rep)
+                                                     const int32_t *__restrict__ rep /*[2][n_cand]*/)
 {
-    // candidates whose coverage inputs equal those of an earlier candidate (heading search: the
-    // headland does not depend on the heading) take its counts afterwards (cover_copy_kernel)
-    if (rep && rep[blockIdx.x] != (int32_t)blockIdx.x) return;
+    // a part (A10 corner windows / A11 band) whose inputs equal those of an earlier candidate is
+    // skipped: the candidate takes that one's counts afterwards (cover_copy_kernel).  A10 does not
+    // depend on the start corner or the heading, A11 not on the heading.
+    const bool do10 = !rep || rep[blockIdx.x] == (int32_t)blockIdx.x;
+    const bool do11 = !rep || rep[b.n_cand + blockIdx.x] == (int32_t)blockIdx.x;
+    if (!do10 && !do11) return;
     CoverFixed &s = *reinterpret_cast<CoverFixed *>(cover_smem);
     const CoverDyn d;
     const int tid = threadIdx.x;
@@ -845,8 +848,9 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
     const CandRec &r = s.rec;
     if (r.status != 0 || r.n_total == 0) {
         if (tid == 0) {
-            sum->cov_cells = sum->cov_total = 0;
-            for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
+            if (do11) sum->cov_cells = sum->cov_total = 0;
+            if (do10)
+                for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
         }
         return;
     }
@@ -856,19 +860,19 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
     TurnModel tm;
     tm.model = b.turn_model;
     tm.lam = b.clothoid_share;
-    int grid_err = 0;
+    int err10 = 0, err11 = 0;  // a grid that does not fit: per part (the parts may run in different CTAs)
 
     // =====================================================================================
     // A10: four verification corner windows (lattice POINTS, h = 0.1 m)
     // =====================================================================================
-    {
+    if (do10) {
         const double fl = b.field_extent[2 * r.field], fw = b.field_extent[2 * r.field + 1];
         const int g = r.corner_g;
         const int rw = (g + 31) >> 5;
         const int Hc = (int)qfix(FCPP_CORNER_GRID_H);
         const double invHc = 1.0 / (double)Hc;
         const bool okc = (g >= 1) && (rw <= TW - 16) && (4 * VPOLY_CAP <= pc);
-        if (!okc) grid_err = 1;
+        if (!okc) err10 = 1;
         const int rpt = okc ? min(ROWCAP, (TW - 16) / rw) : 1;                          // rows per tile
         const int group = (okc && 4 * g <= rpt) ? 4 : ((okc && 2 * g <= rpt) ? 2 : 1);  // corners per pass
         // snapped polylines of the four corners: 15-pt arc + reverse fill (mlp3:1531-1554), relative
@@ -877,7 +881,7 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
             nv[ci] = min(r.vn_rev[ci], VPOLY_CAP - FCPP_CORNER_POINTS);
-            if (r.vn_rev[ci] > VPOLY_CAP - FCPP_CORNER_POINTS) grid_err = 1;
+            if (r.vn_rev[ci] > VPOLY_CAP - FCPP_CORNER_POINTS) err10 = 1;
             if (!okc) continue;
             const double qx = (ci == 0 || ci == 3) ? r.R : fl - r.R;  // mlp3:1531-1536
             const double qy = (ci == 0 || ci == 1) ? r.R : fw - r.R;
@@ -969,7 +973,7 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
     // =====================================================================================
     // A11: headland band (lattice of cell CENTRES anchored at the field bbox minimum)
     // =====================================================================================
-    {
+    if (do11) {
         double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -990,7 +994,7 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
         // relative coordinates must fit int32 with headroom (extent + r < 2^30 units = 107 km)
         const bool ok = (nh <= pc) && nx64 > 0 && ny64 > 0 && nx64 * H64 < (1ll << 30) && ny64 * H64 < (1ll << 30) &&
                         H64 < (1 << 20);
-        if (!ok) grid_err = 1;
+        if (!ok) err11 = 1;
         __syncthreads();
         if (ok) {
             if (tid == 0) s.nrect = 0;
@@ -1075,7 +1079,7 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
                 __syncthreads();
                 const int nrows = s.nrows, nwords = s.total_words;
                 if (nrows == 0) {  // a single row does not fit the tile
-                    grid_err = 1;
+                    err11 = 1;
                     break;
                 }
                 zero_words(s.tile, nwords);
@@ -1113,11 +1117,11 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
             __syncthreads();
         }
         if (tid == 0) {
-            sum->cov_total = (ok && !grid_err) ? (int64_t)s.acc[0] : 0;
-            sum->cov_cells = (ok && !grid_err) ? (int64_t)s.acc[1] : 0;
-            if (grid_err) sum->status |= FCPP_CAND_GRID_TOO_LARGE;
+            sum->cov_total = (ok && !err11) ? (int64_t)s.acc[0] : 0;
+            sum->cov_cells = (ok && !err11) ? (int64_t)s.acc[1] : 0;
         }
     }
+    if (tid == 0 && (err10 | err11)) sum->status |= FCPP_CAND_GRID_TOO_LARGE;
 }
 
 int cover_point_capacity(int max_head)
@@ -1140,84 +1144,82 @@ int cover_point_capacity(int max_head)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-__device__ bool cover_same(const CandRec &a, const CandRec &b)
-{
-    const bool da = a.status != 0 || a.n_total == 0, db = b.status != 0 || b.n_total == 0;
-    if (a.status != b.status || a.field != b.field || da != db) return false;
-    if (da) return true;
-    bool same = a.K == b.K && a.n_head == b.n_head && a.corner_g == b.corner_g &&
-                (a.flags & COVER_FLAG_MASK) == (b.flags & COVER_FLAG_MASK) && dbits(a.R) == dbits(b.R);
-    for (int k = 0; k < 3; ++k) same = same && a.n_rev[k] == b.n_rev[k];
-    for (int k = 0; k < 4; ++k) same = same && a.vn_rev[k] == b.vn_rev[k];
-    for (int k = 0; k < 8; ++k) same = same && dbits((&a.main_quad[0][0])[k]) == dbits((&b.main_quad[0][0])[k]);
-    for (int k = 0; k < 15; ++k) same = same && dbits((&a.rev[0][0])[k]) == dbits((&b.rev[0][0])[k]);
-    for (int k = 0; k < 20; ++k) same = same && dbits((&a.vrev[0][0])[k]) == dbits((&b.vrev[0][0])[k]);
-    for (int k = 0; same && k < 8 * a.K; ++k)
-        same = dbits((&a.corners[0][0][0])[k]) == dbits((&b.corners[0][0][0])[k]);
-    return same;
-}
-
 // table slot: key (0 = empty) and 0x7fffffff - (lowest candidate index) kept with atomicMax.  The
 // table is zeroed when it is allocated and every batch clears the slots it used (cover_copy_kernel),
-// so the steady state has no memset
+// so the steady state has no memset.  Both parts share the table (different hash seeds; a cross-part
+// collision is caught by the verification like any other).
 __global__ void __launch_bounds__(128) cover_key_kernel(const CandRec *__restrict__ recs, int64_t n,
                                                         unsigned long long *__restrict__ keys,
                                                         unsigned int *__restrict__ vals, uint32_t cap_mask,
-                                                        unsigned long long *__restrict__ hash)
+                                                        unsigned long long *__restrict__ hash /*[2][n]*/)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    const unsigned long long h = recs[c].cover_key;  // hashed by the layout kernel
-    hash[c] = h;
-    uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
-    while (true) {
-        const unsigned long long prev = atomicCAS(&keys[slot], 0ull, h);
-        if (prev == 0ull || prev == h) {
-            atomicMax(&vals[slot], 0x7fffffffu - (unsigned int)c);
-            return;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const unsigned long long h = recs[c].cover_key[part];  // hashed by the layout kernel
+        hash[part * n + c] = h;
+        uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&keys[slot], 0ull, h);
+            if (prev == 0ull || prev == h) {
+                atomicMax(&vals[slot], 0x7fffffffu - (unsigned int)c);
+                break;
+            }
+            slot = (slot + 1) & cap_mask;
         }
-        slot = (slot + 1) & cap_mask;
     }
 }
 
 __global__ void __launch_bounds__(128) cover_rep_kernel(const CandRec *__restrict__ recs, int64_t n,
                                                         const unsigned long long *__restrict__ keys,
                                                         const unsigned int *__restrict__ vals, uint32_t cap_mask,
-                                                        unsigned long long *__restrict__ hash,
-                                                        int32_t *__restrict__ rep)
+                                                        unsigned long long *__restrict__ hash /*[2][n]*/,
+                                                        int32_t *__restrict__ rep /*[2][n]*/)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    const unsigned long long h = hash[c];
-    uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
-    while (keys[slot] != h) slot = (slot + 1) & cap_mask;
-    hash[c] = slot;  // remembered for the clean-up
-    const int64_t first = (int64_t)(0x7fffffffu - vals[slot]);
-    rep[c] = (first < c && cover_same(recs[c], recs[first])) ? (int32_t)first : (int32_t)c;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const unsigned long long h = hash[part * n + c];
+        uint32_t slot = (uint32_t)(h >> 17) & cap_mask;
+        while (keys[slot] != h) slot = (slot + 1) & cap_mask;
+        hash[part * n + c] = slot;  // remembered for the clean-up
+        const int64_t first = (int64_t)(0x7fffffffu - vals[slot]);
+        rep[part * n + c] = (first < c && cover_same(recs[c], recs[first], part)) ? (int32_t)first : (int32_t)c;
+    }
 }
 
 __global__ void __launch_bounds__(128) cover_copy_kernel(fcpp_summary *__restrict__ summary, int64_t n,
-                                                         const int32_t *__restrict__ rep,
+                                                         const int32_t *__restrict__ rep /*[2][n]*/,
                                                          unsigned long long *__restrict__ keys,
                                                          unsigned int *__restrict__ vals,
-                                                         const unsigned long long *__restrict__ slot_of)
+                                                         const unsigned long long *__restrict__ slot_of /*[2][n]*/)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    const uint32_t slot = (uint32_t)slot_of[c];  // leave the table empty for the next batch
-    keys[slot] = 0ull;
-    vals[slot] = 0u;
-    const int32_t q = rep[c];
-    if (q == (int32_t)c) return;
-    const fcpp_summary &src = summary[q];
-    fcpp_summary &dst = summary[c];
-    dst.cov_cells = src.cov_cells;
-    dst.cov_total = src.cov_total;
-    for (int k = 0; k < 4; ++k) {
-        dst.corner_before[k] = src.corner_before[k];
-        dst.corner_after[k] = src.corner_after[k];
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {  // leave the table empty for the next batch
+        const uint32_t slot = (uint32_t)slot_of[part * n + c];
+        keys[slot] = 0ull;
+        vals[slot] = 0u;
     }
-    if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+    fcpp_summary &dst = summary[c];
+    const int32_t q0 = rep[c], q1 = rep[n + c];
+    if (q0 != (int32_t)c) {
+        const fcpp_summary &src = summary[q0];
+        for (int k = 0; k < 4; ++k) {
+            dst.corner_before[k] = src.corner_before[k];
+            dst.corner_after[k] = src.corner_after[k];
+        }
+        if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+    }
+    if (q1 != (int32_t)c) {
+        const fcpp_summary &src = summary[q1];
+        dst.cov_cells = src.cov_cells;
+        dst.cov_total = src.cov_total;
+        if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+    }
 }
 
 }  // namespace
@@ -1235,10 +1237,10 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
     unsigned long long *keys = nullptr, *hash = nullptr;
     unsigned int *vals = nullptr;
     const int64_t n = b.n_cand;
-    if (b.cover_dedupe && n > 1 && !(h->cover_mode & 2) && n < (1ll << 30)) {
+    if (b.cover_dedupe && n > 1 && !(h->cover_mode & 2) && n < (1ll << 28)) {
         uint32_t cap = 1024;
-        while ((int64_t)cap < 2 * n) cap <<= 1;
-        const size_t need = (size_t)cap * 12 + (size_t)n * 12 + 64;
+        while ((int64_t)cap < 4 * n) cap <<= 1;  // two keys per candidate, load factor <= 1/2
+        const size_t need = (size_t)cap * 12 + (size_t)n * 24 + 64;
         if (need > h->dedupe_bytes) {
             if (h->d_dedupe) cudaFree(h->d_dedupe);
             h->d_dedupe = nullptr;
@@ -1248,12 +1250,12 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
             h->dedupe_bytes = need;
             h->dedupe_cap = 0;
         }
-        // layout: keys [cap] | vals [cap] | hash / slot [n] | rep [n]; a different capacity moves the
+        // layout: keys [cap] | vals [cap] | hash / slot [2][n] | rep [2][n]; a different capacity moves the
         // arrays, so the table is zeroed again
         keys = (unsigned long long *)h->d_dedupe;
         vals = (unsigned int *)(keys + cap);
         hash = (unsigned long long *)(vals + cap);
-        d_rep = (int32_t *)(hash + n);
+        d_rep = (int32_t *)(hash + 2 * n);
         if (h->dedupe_cap != cap) {
             e = cudaMemsetAsync(h->d_dedupe, 0, (size_t)cap * 12, st);
             if (e != cudaSuccess) return e;

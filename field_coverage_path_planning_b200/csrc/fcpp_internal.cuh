@@ -49,7 +49,8 @@ struct __align__(16) CandRec {
     double min_x, min_y, max_x, max_y;  // swath-frame bounds of the work area (mlp3:731-732)
     double cx, cy;                      // rotation centre (work-area centroid, mlp3:690, :710)
     double cos_a, sin_a;                // rotate-back (mlp3:709-714)
-    uint64_t cover_key;                 // hash of every field the coverage kernel reads (de-duplication)
+    uint64_t cover_key[2];              // hashes of the fields A10 (corner windows) / A11 (band) read (de-duplication)
+    uint64_t pad1;
     double main_quad[4][2];             // R-inset of the field (mlp3:594-595), D1
     double rev[3][5];                   // loop-0 reverse fills: ex, ey, dx, dy, length (mlp3:1154-1218)
     double vrev[4][5];                  // verification corners (mlp3:1531-1554)
@@ -101,26 +102,52 @@ __device__ __forceinline__ uint64_t dbits(double x) { return (uint64_t)__double_
 
 constexpr int COVER_FLAG_MASK = FCPP_FLAG_CORNER_MASK | FCPP_FLAG_GAP_GATE;
 
-// hash of every CandRec field the coverage kernel reads (fcpp_cover.cu: coverage de-duplication)
-__device__ __forceinline__ uint64_t cover_key(const CandRec &r)
+// hashes of the CandRec fields the coverage kernel reads (fcpp_cover.cu: coverage de-duplication).
+// part 0 = A10, the four corner windows: field, R, window size, verification reverse fills — NOT the
+// start corner; part 1 = A11, the headland band: field, R, loops, start corner, rings, reverse fills
+__device__ __forceinline__ bool cover_dead(const CandRec &r) { return r.status != 0 || r.n_total == 0; }
+__device__ __forceinline__ uint64_t cover_key(const CandRec &r, int part)
 {
-    uint64_t h = 0x243F6A8885A308D3ull;
-    const bool dead = r.status != 0 || r.n_total == 0;
+    uint64_t h = part ? 0x243F6A8885A308D3ull : 0x13198A2E03707344ull;
+    const bool dead = cover_dead(r);
     h = mix64(h, ((uint64_t)(uint32_t)r.status << 32) | (uint32_t)r.field);
     h = mix64(h, dead ? 1u : 0u);
     if (dead) return h | 1ull;  // all dead candidates of a field share zero counts
-    h = mix64(h, ((uint64_t)(uint32_t)r.K << 32) | (uint32_t)r.n_head);
-    h = mix64(h, ((uint64_t)(uint32_t)(r.flags & COVER_FLAG_MASK) << 32) | (uint32_t)r.corner_g);
-    for (int k = 0; k < 3; ++k) h = mix64(h, (uint32_t)r.n_rev[k]);
-    for (int k = 0; k < 4; ++k) h = mix64(h, (uint32_t)r.vn_rev[k]);
     h = mix64(h, dbits(r.R));
-    for (int k = 0; k < 8; ++k) h = mix64(h, dbits((&r.main_quad[0][0])[k]));
-    for (int k = 0; k < 15; ++k) h = mix64(h, dbits((&r.rev[0][0])[k]));
-    for (int k = 0; k < 20; ++k) h = mix64(h, dbits((&r.vrev[0][0])[k]));
-    for (int k = 0; k < 8 * r.K; ++k) h = mix64(h, dbits((&r.corners[0][0][0])[k]));
+    if (part == 0) {
+        h = mix64(h, (uint32_t)r.corner_g);
+        for (int k = 0; k < 4; ++k) h = mix64(h, (uint32_t)r.vn_rev[k]);
+        for (int k = 0; k < 20; ++k) h = mix64(h, dbits((&r.vrev[0][0])[k]));
+    } else {
+        h = mix64(h, ((uint64_t)(uint32_t)r.K << 32) | (uint32_t)r.n_head);
+        h = mix64(h, (uint32_t)(r.flags & COVER_FLAG_MASK));
+        for (int k = 0; k < 3; ++k) h = mix64(h, (uint32_t)r.n_rev[k]);
+        for (int k = 0; k < 8; ++k) h = mix64(h, dbits((&r.main_quad[0][0])[k]));
+        for (int k = 0; k < 15; ++k) h = mix64(h, dbits((&r.rev[0][0])[k]));
+        for (int k = 0; k < 8 * r.K; ++k) h = mix64(h, dbits((&r.corners[0][0][0])[k]));
+    }
     return h | 1ull;  // 0 marks an empty slot
 }
-
+__device__ __forceinline__ bool cover_same(const CandRec &a, const CandRec &b, int part)
+{
+    const bool da = cover_dead(a), db = cover_dead(b);
+    if (a.status != b.status || a.field != b.field || da != db) return false;
+    if (da) return true;
+    bool same = dbits(a.R) == dbits(b.R);
+    if (part == 0) {
+        same = same && a.corner_g == b.corner_g;
+        for (int k = 0; k < 4; ++k) same = same && a.vn_rev[k] == b.vn_rev[k];
+        for (int k = 0; k < 20; ++k) same = same && dbits((&a.vrev[0][0])[k]) == dbits((&b.vrev[0][0])[k]);
+    } else {
+        same = same && a.K == b.K && a.n_head == b.n_head && (a.flags & COVER_FLAG_MASK) == (b.flags & COVER_FLAG_MASK);
+        for (int k = 0; k < 3; ++k) same = same && a.n_rev[k] == b.n_rev[k];
+        for (int k = 0; k < 8; ++k) same = same && dbits((&a.main_quad[0][0])[k]) == dbits((&b.main_quad[0][0])[k]);
+        for (int k = 0; k < 15; ++k) same = same && dbits((&a.rev[0][0])[k]) == dbits((&b.rev[0][0])[k]);
+        for (int k = 0; same && k < 8 * a.K; ++k)
+            same = dbits((&a.corners[0][0][0])[k]) == dbits((&b.corners[0][0][0])[k]);
+    }
+    return same;
+}
 
 // ---------------------------------------------------------------------------------------
 // small helpers

@@ -218,7 +218,10 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
         r.main_quad[k][0] = mq[k][0];
         r.main_quad[k][1] = mq[k][1];
     }
-    r.cover_key = (b.cover_dedupe && b.do_coverage) ? cover_key(r) : 0ull;
+    const bool dd = b.cover_dedupe && b.do_coverage;
+    r.cover_key[0] = dd ? cover_key(r, 0) : 0ull;
+    r.cover_key[1] = dd ? cover_key(r, 1) : 0ull;
+    r.pad1 = 0ull;
     if (n_pts) n_pts[c] = r.n_total;
     return r.n_total;
 }

@@ -107,9 +107,10 @@ typedef struct {
     int32_t turn_model;            /* 0: the reference's sampled circular arcs (mlp3:807-830, :1046-1062);
                                       1: clothoid -> arc -> clothoid turns with Fresnel integrals evaluated
                                       per sample point on the device (same sample counts, same layout) */
-    int32_t cover_dedupe;     /* 1: candidates whose coverage inputs are identical (same field, R, start corner — e.g.
-                               * the headings of a heading search) are rasterised once and share the counts; 0: every
-                               * candidate is rasterised.  Same integers either way. */
+    int32_t cover_dedupe;     /* 1: coverage work with identical inputs is done once and shared — the corner windows
+                               * (A10) of candidates with the same field and R (any start corner, any heading), the
+                               * headland band (A11) of candidates with the same field, R and start corner (any
+                               * heading); 0: every candidate is rasterised.  Same integers either way. */
     double clothoid_share;         /* share of a turn's deflection spent on the two clothoids, (0, 1] */
 } fcpp_batch;
 

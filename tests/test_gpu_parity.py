@@ -362,8 +362,9 @@ def test_band_zoned_equals_row_tiled_and_oracle(fc):
     from oracle import batch as ob, ref_planner as rp
     h = _lib.handle(0)
 
-    def both(fields, veh, cand, modes=(1,), **kw):
-        """mode bit 0: row-tiled band only; bit 1: no coverage de-duplication"""
+    def both(fields, veh, cand, modes=(1, 2, 3), **kw):
+        """mode bit 0: row-tiled band only; bit 1: no coverage de-duplication (on by default in batches with a
+        heading or start-corner axis: corner windows shared per (field, R), bands per (field, R, corner))"""
         auto = fc.plan_batch(fields, veh, cand, **kw).summary
         for mode in modes:
             try:
