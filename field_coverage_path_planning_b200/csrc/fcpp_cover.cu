@@ -1014,6 +1014,16 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
             if (tid >= 4 && tid < 8) quad_edges_setup(s.mq, s.qedge[1], s.qtype[1], tid - 4);
             setup_entries<true, FCPP_COVER_RECT != 0>(s, d, 0, nh - 1, rd, rq, H, invH);
             __syncthreads();
+            // entries whose whole capsule (bounding box grown by r) lies in the closed R-inset cannot
+            // cover a band cell — the inner ends of the inner loops' turn arcs, most of the joins
+            for (int e = tid; e < nh - 1; e += T) {
+                const int4 sg = d.ent(e).seg;
+                if (sg.y > sg.w) continue;
+                const int x0 = min(sg.x, sg.z) - rq, x1 = max(sg.x, sg.z) + rq, y0 = sg.y - rq, y1 = sg.w + rq;
+                if (in_quad(s.mq, x0, y0) && in_quad(s.mq, x1, y0) && in_quad(s.mq, x1, y1) && in_quad(s.mq, x0, y1))
+                    write_dead_entry(d, e);
+            }
+            __syncthreads();
             unsigned long long my_total = 0ull, my_cov = 0ull;
             int j0 = 0;
             if (tid == 0) s.next_w0 = 0;
