@@ -122,7 +122,7 @@ EXPORTS = [
 ]
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()   # re-entrant: handle() creates a Handle, whose constructor calls load()
 _handles = {}
 
 
@@ -238,11 +238,13 @@ class Handle:
             pass
 
 
-def handle(device_index: int = 0) -> Handle:
+def handle(device_index: int = 0, slot: int = 0) -> Handle:
+    """The fcpp_handle of a device.  ``slot`` > 0 gives further independent handles (own workspace) for
+    work that overlaps slot 0 on another stream (each handle owns its workspace and is not re-entrant)."""
+    key = device_index if slot == 0 else (device_index, slot)
     with _lock:
-        pass
-    h = _handles.get(device_index)
-    if h is None:
-        h = Handle(device_index)
-        _handles[device_index] = h
+        h = _handles.get(key)
+        if h is None:
+            h = Handle(device_index)
+            _handles[key] = h
     return h

@@ -37,17 +37,17 @@ def _dev(device) -> torch.device:
 class _Staging:
     """Grow-only pinned host buffers of one device: ONE packed host->device copy of a batch's inputs
     and ONE packed device->host copy of its results, instead of a cudaHostAlloc + copy per array."""
-    _per_dev: Dict[int, "_Staging"] = {}
+    _per_dev: Dict[tuple, "_Staging"] = {}
 
     def __init__(self):
         self.h_in = self.h_out = None
         self.in_done = None          # event: the last packed H2D copy has left h_in
 
     @classmethod
-    def get(cls, dev: torch.device) -> "_Staging":
-        st = cls._per_dev.get(dev.index)
+    def get(cls, dev: torch.device, slot: int = 0) -> "_Staging":
+        st = cls._per_dev.get((dev.index, slot))
         if st is None:
-            st = cls._per_dev[dev.index] = cls()
+            st = cls._per_dev[(dev.index, slot)] = cls()
         return st
 
     def host_in(self, nbytes: int) -> torch.Tensor:
@@ -63,7 +63,7 @@ class _Staging:
         return self.h_out
 
 
-def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device) -> Dict[str, torch.Tensor]:
+def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device, slot: int = 0) -> Dict[str, torch.Tensor]:
     """All input arrays through one pinned staging buffer and one async copy; the device tensors
     are typed views of one allocation (256-byte aligned slices)."""
     offs, total = {}, 0
@@ -71,7 +71,7 @@ def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device) -> Dict[str, 
         offs[k] = total
         total += (a.nbytes + 255) & ~255
     total = max(total, 256)
-    st = _Staging.get(dev)
+    st = _Staging.get(dev, slot)
     h = st.host_in(total)
     hv = h.numpy()
     for k, a in arrays.items():
@@ -230,10 +230,12 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
 class DeviceBatch:
     """A PreparedBatch resident in HBM + its ctypes descriptor."""
 
-    def __init__(self, pb: PreparedBatch, dev: torch.device, pin: bool = True):
+    def __init__(self, pb: PreparedBatch, dev: torch.device, pin: bool = True, slot: int = 0):
         self.pb = pb
         self.dev = dev
-        self.t = _pack_to_dev(pb.arrays, dev) if pin else {k: _to_dev(v, dev, False) for k, v in pb.arrays.items()}
+        self.slot = slot   # which handle / staging buffers / (by convention) stream this batch uses
+        self.t = (_pack_to_dev(pb.arrays, dev, slot) if pin
+                  else {k: _to_dev(v, dev, False) for k, v in pb.arrays.items()})
         v = pb.vehicle
         b = _lib.Batch()
         b.vehicle = _lib.Vehicle(v.working_width, v.max_work_speed_kmh, v.max_headland_speed_kmh,
@@ -287,7 +289,9 @@ class BatchBuffers:
     no allocation, no readback, no synchronisation inside the step)."""
 
     def __init__(self, dev: torch.device, n_cand: int, n_fields: int, total_points: int = 0,
-                 want_curvature: bool = False):
+                 want_curvature: bool = False, path_storage=None):
+        """``path_storage`` = (d_path [total, 2], d_spd [total], d_kap [total] | None): views of a larger
+        allocation to use instead of new tensors."""
         self.dev = dev
         self.n_cand, self.n_fields, self.total_points = n_cand, n_fields, total_points
         self.d_sum = torch.empty(max(n_cand, 1) * _lib.SUMMARY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -299,23 +303,25 @@ class BatchBuffers:
         self.d_off = self.d_path = self.d_spd = self.d_kap = None
         if total_points > 0:
             self.d_off = torch.empty(n_cand + 1, dtype=torch.int64, device=dev)
-            self.d_path = torch.empty((total_points, 2), dtype=torch.float64, device=dev)
-            self.d_spd = torch.empty(total_points, dtype=torch.float64, device=dev)
-            if want_curvature:
-                self.d_kap = torch.empty(total_points, dtype=torch.float64, device=dev)
+            if path_storage is not None:
+                self.d_path, self.d_spd, self.d_kap = path_storage
+            else:
+                self.d_path = torch.empty((total_points, 2), dtype=torch.float64, device=dev)
+                self.d_spd = torch.empty(total_points, dtype=torch.float64, device=dev)
+                if want_curvature:
+                    self.d_kap = torch.empty(total_points, dtype=torch.float64, device=dev)
 
 
-def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
-                     cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
-                     buffers: Optional[BatchBuffers] = None, fetch: bool = True) -> Optional[BatchResult]:
-    """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
-
-    With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
-    whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only."""
+def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, cost: str, cand_base: int,
+                         buffers: Optional["BatchBuffers"], path_alloc=None):
+    """Enqueue layout, prefix sum, plan, coverage and argmin kernels of one batch on torch's current
+    stream.  Returns (buffers, offsets or None).  Without ``buffers`` the path storage is sized from
+    the layout pass (one small synchronous read-back); ``path_alloc(total) -> BatchBuffers | None``
+    lets the caller provide it."""
     if outputs not in ("summary", "paths"):
         raise ValueError("outputs must be 'summary' or 'paths'")
     dev = db.dev
-    h = _lib.handle(dev.index)
+    h = _lib.handle(dev.index, db.slot)
     L = h.lib
     B, F = db.pb.n_cand, db.pb.n_fields
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -331,7 +337,9 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
                 h.check(L.fcpp_layout(h.h, C.byref(db.c), None, d_off.data_ptr(), stream))
                 offsets = d_off.cpu().numpy()
                 total = max(int(offsets[-1]), 1)
-            buffers = BatchBuffers(dev, B, F, total, want_curvature)
+            buffers = path_alloc(total) if path_alloc is not None else None
+            if buffers is None:
+                buffers = BatchBuffers(dev, B, F, total, want_curvature)
             if outputs == "paths":
                 buffers.d_off = d_off
         else:
@@ -355,16 +363,23 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
         h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
                                     0 if cost == "length" else 1, cand_base, buffers.d_cost.data_ptr(),
                                     buffers.d_best.data_ptr(), stream))
-        if not fetch:
-            return None
-        # one pinned staging buffer, async copies, ONE synchronisation
+    return buffers, offsets
+
+
+def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, offsets, copy_summary: bool,
+                        cand_base: int) -> "BatchResult":
+    """Copy summaries + argmin (+ offsets) of a launched batch back: one pinned staging buffer, async
+    copies on torch's current stream, ONE synchronisation."""
+    dev = db.dev
+    B, F = db.pb.n_cand, db.pb.n_fields
+    with torch.cuda.device(dev):
         nb_sum = B * _lib.SUMMARY_DTYPE.itemsize if copy_summary else 0
         need_off = outputs == "paths" and offsets is None
         o_cost = (nb_sum + 255) & ~255
         o_best = o_cost + ((F * 8 + 255) & ~255)
         o_off = o_best + ((F * 8 + 255) & ~255)
         total_out = o_off + ((B + 1) * 8 if need_off else 0)
-        ho = _Staging.get(dev).host_out(max(total_out, 256))
+        ho = _Staging.get(dev, db.slot).host_out(max(total_out, 256))
         if nb_sum:
             ho[:nb_sum].copy_(buffers.d_sum[:nb_sum], non_blocking=True)
         if F:
@@ -384,6 +399,19 @@ def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: 
                       d_summary=buffers.d_sum, cand_base=cand_base)
     res.extras["buffers"] = buffers
     return res
+
+
+def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
+                     cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
+                     buffers: Optional[BatchBuffers] = None, fetch: bool = True) -> Optional[BatchResult]:
+    """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
+
+    With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
+    whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only."""
+    buffers, offsets = _launch_device_batch(db, outputs, want_curvature, cost, cand_base, buffers)
+    if not fetch:
+        return None
+    return _fetch_device_batch(db, buffers, outputs, offsets, copy_summary, cand_base)
 
 
 def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,
@@ -415,3 +443,4 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
                        clothoid_share)
     db = DeviceBatch(pb, dev)
     return run_device_batch(db, outputs, want_curvature, cost)
+

@@ -143,3 +143,17 @@ def test_prepare_batch_host_setup(built):
     with pytest.raises(ValueError):
         fc.prepare_batch([rect], fc.VehicleParams(), {"field_id": np.array([0], dtype=np.int32),
                                                       "start_corner": np.array([4], dtype=np.int32)})
+
+
+def test_first_handle_call_in_a_fresh_process_returns():
+    """_lib.handle() as the FIRST library call of a process (bench.py does that): the library load inside the
+    Handle constructor must not dead-lock on the module lock.  Without a GPU it fails loudly instead."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from field_coverage_path_planning_b200 import _lib\n"
+            "try:\n    _lib.handle(0); _lib.handle(0, 1); print('HANDLES')\n"
+            "except _lib.FcppError as e:\n    print('RAISED', e)\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RAISED" in out.stdout or "HANDLES" in out.stdout, out.stdout + out.stderr
