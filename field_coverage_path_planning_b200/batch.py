@@ -63,6 +63,10 @@ class _Staging:
         return self.h_out
 
 
+_TORCH_DTYPE = {np.dtype(np.float64).str: torch.float64, np.dtype(np.int32).str: torch.int32,
+                np.dtype(np.int64).str: torch.int64, np.dtype(np.uint8).str: torch.uint8}
+
+
 def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device, slot: int = 0) -> Dict[str, torch.Tensor]:
     """All input arrays through one pinned staging buffer and one async copy; the device tensors
     are typed views of one allocation (256-byte aligned slices)."""
@@ -84,7 +88,7 @@ def _pack_to_dev(arrays: Dict[str, np.ndarray], dev: torch.device, slot: int = 0
         st.in_done.record(torch.cuda.current_stream(dev))
     out = {}
     for k, a in arrays.items():
-        t = d[offs[k]:offs[k] + a.nbytes].view(torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype)
+        t = d[offs[k]:offs[k] + a.nbytes].view(_TORCH_DTYPE[a.dtype.str])
         out[k] = t.view(a.shape) if a.nbytes else t
     out["_packed"] = d
     return out
@@ -335,8 +339,12 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
             if outputs == "paths":
                 d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
                 h.check(L.fcpp_layout(h.h, C.byref(db.c), None, d_off.data_ptr(), stream))
-                offsets = d_off.cpu().numpy()
-                total = max(int(offsets[-1]), 1)
+                # the layout pass's own read-back carries the total; the offsets come back with the summaries
+                total = int(L.fcpp_last_total_points(h.h))
+                if total < 0:
+                    offsets = d_off.cpu().numpy()
+                    total = int(offsets[-1])
+                total = max(total, 1)
             buffers = path_alloc(total) if path_alloc is not None else None
             if buffers is None:
                 buffers = BatchBuffers(dev, B, F, total, want_curvature)

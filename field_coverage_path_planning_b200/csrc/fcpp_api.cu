@@ -118,7 +118,7 @@ int fcpp_create(int device, fcpp_handle **out)
     cudaError_t e = cudaMalloc((void **)&h->d_trig, sizeof(TrigTables));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_trig, &t, sizeof(t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_maxn, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_maxn, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_maxn, 4 * sizeof(int));  // + int64 total points
     if (e != cudaSuccess) {
         fcpp_destroy(h);
         return FCPP_ERR_CUDA;
@@ -152,6 +152,7 @@ int64_t fcpp_launch_count(const fcpp_handle *h) { return h ? h->launches : 0; }
 
 int32_t fcpp_last_max_points(const fcpp_handle *h) { return h ? h->last_maxn : 0; }
 int32_t fcpp_last_max_head_points(const fcpp_handle *h) { return h ? h->last_maxhead : 0; }
+int64_t fcpp_last_total_points(const fcpp_handle *h) { return h ? h->last_total : -1; }
 
 int fcpp_set_cover_mode(fcpp_handle *h, int mode)
 {
@@ -213,6 +214,9 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
         h->h_maxn[0] = h->h_maxn[1] = 0;
         if (batch->n_cand > 0) {
             e = cudaMemcpyAsync(h->h_maxn, h->d_maxn, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+            // the same synchronisation also brings back the total number of points (sizes the path buffers)
+            if (e == cudaSuccess && d_offsets)
+                e = cudaMemcpyAsync(h->h_maxn + 2, d_offsets + batch->n_cand, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return cuda_fail(h, e, "layout readback");
         }
@@ -220,6 +224,10 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
         maxhead = h->h_maxn[1];
         h->last_maxn = maxn;
         h->last_maxhead = maxhead;
+        h->last_total = -1;
+        if (d_offsets && batch->n_cand > 0) memcpy(&h->last_total, h->h_maxn + 2, sizeof(int64_t));
+    } else {
+        h->last_total = -1;  // asynchronous pass: nothing was read back
     }
     h->cover_pcap = maxhead;
     int want = (maxn + 63) / 64 * 64;

@@ -79,6 +79,7 @@ struct fcpp_handle {
     cudaEvent_t ev[4];       // layout start, plan start, cover start, end
     int last_maxn;
     int last_maxhead;
+    int64_t last_total;      // total points of the last synchronous layout pass with offsets (-1: unknown)
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
     int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation,
                              // bit 1 = no coverage de-duplication

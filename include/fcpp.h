@@ -301,6 +301,9 @@ int64_t fcpp_launch_count(const fcpp_handle *h);
  * (feed max_points_hint / max_head_points_hint). */
 int32_t fcpp_last_max_points(const fcpp_handle *h);
 int32_t fcpp_last_max_head_points(const fcpp_handle *h);
+/* offsets[n_cand] of the last fcpp_layout that wrote offsets without size hints (it is read back in the
+ * same synchronisation as the two maxima); -1 if unknown.  Sizes the path buffers without a second copy. */
+int64_t fcpp_last_total_points(const fcpp_handle *h);
 
 /* Per-kernel device times.  With profiling on, every fcpp_plan_batch brackets its kernels with
  * CUDA events on the launching stream; fcpp_kernel_times (call after synchronising the stream)
