@@ -278,7 +278,8 @@ __device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *sh, 
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const CandRec *__restrict__ recs, int64_t n,
                                                                    int64_t *__restrict__ offsets,
-                                                                   int64_t *__restrict__ tile_sums)
+                                                                   int64_t *__restrict__ tile_sums,
+                                                                   int64_t *__restrict__ single_total)
 {
     __shared__ int64_t sh[64];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -298,7 +299,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const CandRec 
         const int64_t i = base + k;
         if (i < n) offsets[i] = off + loc[k];
     }
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) {
+        tile_sums[blockIdx.x] = total;
+        if (single_total) *single_total = total;  // one tile: the scan is complete, offsets[n] = total
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int64_t *tile_sums, int64_t n_tiles,
@@ -349,10 +353,14 @@ cudaError_t fcpp_launch_layout(fcpp_handle *h, const fcpp_batch &b, int32_t *d_n
     if (d_offsets) {
         const int64_t n_tiles = (B + SCAN_TILE - 1) / SCAN_TILE;
         int64_t *tile_sums = (int64_t *)h->d_scan_tmp;
-        scan_tiles_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(h->d_rec, B, d_offsets, tile_sums);
-        scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, n_tiles, d_offsets + B);
-        scan_add_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_offsets, B, tile_sums);
-        h->launches += 3;
+        scan_tiles_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(h->d_rec, B, d_offsets, tile_sums,
+                                                                        n_tiles == 1 ? d_offsets + B : nullptr);
+        h->launches++;
+        if (n_tiles > 1) {  // batches of more than 4096 candidates: prefix of the tile sums, then add
+            scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, n_tiles, d_offsets + B);
+            scan_add_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_offsets, B, tile_sums);
+            h->launches += 2;
+        }
         e = cudaGetLastError();
     }
     return e;

@@ -107,6 +107,40 @@ __global__ void argmin_final(unsigned long long *key, int64_t *cand, int n_field
     }
 }
 
+// the four phases in ONE CTA (small batches: four dependent launches cost more than the work)
+constexpr int ARGMIN_SMALL_THREADS = 1024;
+__global__ void __launch_bounds__(ARGMIN_SMALL_THREADS) argmin_small(const fcpp_summary *__restrict__ sm,
+                                                                      const int32_t *__restrict__ cf, int64_t n, int kind,
+                                                                      int64_t base, unsigned long long *key, int64_t *cand,
+                                                                      int n_fields)
+{
+    for (int f = threadIdx.x; f < n_fields; f += ARGMIN_SMALL_THREADS) {
+        key[f] = ~0ull;
+        cand[f] = 0x7fffffffffffffffll;
+    }
+    __threadfence();
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n; c += ARGMIN_SMALL_THREADS)
+        if (sm[c].status == 0) atomicMin(&key[cf[c]], order_bits(cand_cost(sm[c], kind)));
+    __threadfence();
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n; c += ARGMIN_SMALL_THREADS)
+        if (sm[c].status == 0 && order_bits(cand_cost(sm[c], kind)) == __ldcg(&key[cf[c]]))
+            atomicMin((long long *)&cand[cf[c]], (long long)(base + c));
+    __threadfence();
+    __syncthreads();
+    for (int f = threadIdx.x; f < n_fields; f += ARGMIN_SMALL_THREADS) {
+        const unsigned long long k = __ldcg(&key[f]);
+        double *out = reinterpret_cast<double *>(key);
+        if (k == ~0ull) {
+            out[f] = INFINITY;
+            cand[f] = -1;
+        } else {
+            out[f] = unorder_bits(k);
+        }
+    }
+}
+
 // multi-GPU: per-field merge of the ranks' local bests after ONE all-gather of (cost, candidate)
 // words; lowest cost wins, ties go to the lowest global candidate index, -1 = no candidate
 __global__ void argmin_merge_kernel(const long long *__restrict__ g, int world, int n_fields,
@@ -217,6 +251,12 @@ cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, co
 {
     if (n_fields == 0) return cudaSuccess;
     unsigned long long *key = reinterpret_cast<unsigned long long *>(d_best_cost);
+    if (n_cand <= 16384 && n_fields <= 16384) {
+        argmin_small<<<1, ARGMIN_SMALL_THREADS, 0, st>>>(d_summary, d_cand_field, n_cand, cost_kind, cand_base, key,
+                                                           d_best_cand, n_fields);
+        h->launches++;
+        return cudaGetLastError();
+    }
     const int th = 256;
     const unsigned fb = (unsigned)((n_fields + th - 1) / th);
     argmin_init<<<fb, th, 0, st>>>(key, d_best_cand, n_fields);
