@@ -255,11 +255,19 @@ def main():
         ev[k][0].record()
         step_device()
         ev[k][1].record()
-        ev[k][1].synchronize()
-        ms3 = (C.c_float * 3)()
-        h.check(h.lib.fcpp_kernel_times(h.h, C.byref(ms3)))
-        ktimes.append(list(ms3))
+        if world == 1:
+            # per-kernel CUDA-event times of every step (the library brackets its kernels on this stream)
+            ev[k][1].synchronize()
+            ms3 = (C.c_float * 3)()
+            h.check(h.lib.fcpp_kernel_times(h.h, C.byref(ms3)))
+            ktimes.append(list(ms3))
+        # N > 1: no host synchronisation inside the timed region — every step ends in a collective, and a
+        # per-step host sync would add each rank's launch jitter to every rendezvous
     sync_all()
+    if world > 1:
+        ms3 = (C.c_float * 3)()
+        h.check(h.lib.fcpp_kernel_times(h.h, C.byref(ms3)))   # of the last step
+        ktimes.append(list(ms3))
     t_wall = time.perf_counter() - t_wall0
     launches = h.launches - l0
     clocks = sampler.stop()

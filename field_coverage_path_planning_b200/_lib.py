@@ -116,7 +116,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
-    "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_field_argmin_merge", "fcpp_speed_verify", "fcpp_raster_window",
+    "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_field_argmin_merge", "fcpp_field_argmin_exchange", "fcpp_speed_verify", "fcpp_raster_window",
     "fcpp_tour_lengths", "fcpp_distance_matrix", "fcpp_connection_matrix", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve",
     "fcpp_launch_count", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_last_total_points", "fcpp_set_profiling", "fcpp_kernel_times", "fcpp_set_cover_mode",
 ]
@@ -185,6 +185,8 @@ def load():
         L.fcpp_set_profiling.argtypes = [vp, C.c_int]
         L.fcpp_last_total_points.restype = C.c_int64
         L.fcpp_last_total_points.argtypes = [vp]
+        L.fcpp_field_argmin_exchange.restype = C.c_int
+        L.fcpp_field_argmin_exchange.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp, vp, vp]
         L.fcpp_set_cover_mode.restype = C.c_int
         L.fcpp_set_cover_mode.argtypes = [vp, C.c_int]
         L.fcpp_kernel_times.restype = C.c_int

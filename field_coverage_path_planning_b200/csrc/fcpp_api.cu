@@ -298,6 +298,21 @@ int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t w
     return FCPP_OK;
 }
 
+int fcpp_field_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
+                               const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
+                               int64_t *d_best_cand, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (world < 1 || world > FCPP_MAX_PEERS || rank < 0 || rank >= world || n_fields < 0 || !peer_bufs || !peer_flags ||
+        (n_fields > 0 && (!d_best_cost || !d_best_cand)))
+        return fail(h, FCPP_ERR_INVALID, "fcpp_field_argmin_exchange: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_argmin_exchange(h, world, rank, n_fields, epoch, peer_bufs, peer_flags, d_best_cost,
+                                                d_best_cand, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "argmin exchange kernel");
+    return FCPP_OK;
+}
+
 int fcpp_speed_verify(fcpp_handle *h, const fcpp_vehicle *veh, const double *d_path_xy, const double *d_speeds_in,
                       const int64_t *d_offsets, int64_t n_paths, int64_t max_path_len, int do_speed_plan,
                       double *d_speeds_out, double *d_curvature, fcpp_summary *d_summary, void *stream)

@@ -533,6 +533,9 @@ void fcpp_ga_read_state(const void *host_copy, int &gen, int &stagnant, int &don
                         double &best_len);
 cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int world, int32_t n_fields,
                                      double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);
+cudaError_t fcpp_launch_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
+                                        const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
+                                        int64_t *d_best_cand, cudaStream_t st);
 cudaError_t fcpp_launch_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, cudaStream_t st);
 cudaError_t fcpp_launch_connection_matrix(fcpp_handle *h, const double *d_verts, int32_t n_fields, double depot_x,
                                           double depot_y, double *d_C, int32_t *d_arg, cudaStream_t st);

@@ -200,6 +200,18 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
 int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t world, int32_t n_fields,
                             double *d_best_cost, int64_t *d_best_cand, void *stream);
 
+/* Multi-GPU, fused form of all-gather + fcpp_field_argmin_merge: ONE kernel writes this rank's (cost, candidate)
+ * words into every rank's symmetric buffer over peer memory (NVLink P2P stores), publishes a flag per rank,
+ * waits for the other ranks' flags and merges — no NCCL call.  d_best_cost / d_best_cand hold the local result
+ * on entry and the global one on exit.  peer_bufs[p] / peer_flags[p] (HOST arrays of `world` device addresses):
+ * rank p's slot array of 2 * world * 2 * n_fields 8-byte words and its flag array of `world` uint32, zeroed
+ * before the first call and mapped into this process (e.g. torch symmetric memory); epoch = 1, 2, 3, ... per
+ * call, identical on every rank.  A rank that does not arrive within ~10 s poisons the result (NaN, -2). */
+#define FCPP_MAX_PEERS 16
+int fcpp_field_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
+                               const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
+                               int64_t *d_best_cand, void *stream);
+
 /* Generic A7/A8/A13 on caller-supplied paths (ragged batch, path p = points offsets[p]..offsets[p+1]):
  * speed planning mlp3:467-589 (d_speeds_out may alias d_speeds_in), curvature verification
  * mlp3:1373-1424 and length/time mlp3:1290-1311 into d_summary (fields n_accel_viol, max_*,
