@@ -143,6 +143,22 @@ def test_prepare_batch_host_setup(built):
     with pytest.raises(ValueError):
         fc.prepare_batch([rect], fc.VehicleParams(), {"field_id": np.array([0], dtype=np.int32),
                                                       "start_corner": np.array([4], dtype=np.int32)})
+    # without a heading axis the heading is the field's (mlp3:244-263): trig per field, gathered per candidate
+    tilted = [(10, 5), (510, 40), (470, 260), (-20, 190)]
+    c2 = fc.make_candidates(3, radii=[6.0, 9.5], start_corners=[3, 0])
+    p2 = fc.prepare_batch([rect, tilted, sliver], fc.VehicleParams(), c2)
+    ang = np.array([0.0, np.arctan2(35.0, 500.0), 0.0])[c2["field_id"]]
+    np.testing.assert_array_equal(p2.arrays["cand_rot"],
+                                  np.stack([np.cos(-ang), np.sin(-ang), np.cos(ang), np.sin(ang)], axis=1))
+    f2 = p2.arrays["cand_flags"]
+    assert (((f2 & _lib.FLAG_ROTATED) != 0) == (c2["field_id"] == 1)).all()
+    assert ((f2 & 3) == c2["start_corner"]).all() and f2.dtype == np.int32
+    assert (((f2 & _lib.FLAG_REVERSE_ORDER) != 0) == (c2["start_corner"] == 3)).all()
+    assert ((f2 & _lib.FLAG_START_FROM_RIGHT) == 0).all()
+    # coverage de-duplication is requested when a candidate axis repeats coverage work (fcpp_batch.cover_dedupe)
+    assert pb.dedupe and p2.dedupe
+    assert not fc.prepare_batch([rect], fc.VehicleParams(), fc.make_candidates(1, radii=[5.0, 6.0])).dedupe
+    assert not fc.prepare_batch([rect, tilted], fc.VehicleParams(), fc.make_candidates(2, start_corners=[1])).dedupe
 
 
 def test_first_handle_call_in_a_fresh_process_returns():

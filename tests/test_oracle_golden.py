@@ -174,3 +174,37 @@ def test_oracle_vs_reference_executed_live():
         np.testing.assert_allclose(o[layer]["speeds"], r[layer]["speeds"], rtol=0, atol=1e-12)
     assert np.array_equal(o["approach_path"], r["approach_path"])
     assert np.array_equal(o["departure_path"], r["departure_path"])
+
+
+@pytest.mark.parametrize("case", ["rect120x80", "rect500x200", "offset_rect", "narrow_loops", "sheared", "tilted"])
+def test_zoned_band_model_equals_brute_force(case):
+    """The four exactness claims behind the coverage kernel's zoned band evaluation (chains = rectangle +
+    end discs, entries inside the R-inset cover no band cell, general entries stay inside their quadrant's
+    zone, runs of rows are constant between breakpoints) restated on the CPU (oracle/zoned_model.py) give
+    the brute-force counts of raster_oracle.c; fields without axis-aligned chains / with overlapping zones
+    are reported as 'fall back' (None), as the kernel does."""
+    from dataclasses import replace
+    from oracle import raster, ref_planner as rp, zoned_model
+    fields = {
+        "rect120x80": ([(0, 0), (120, 0), (120, 80), (0, 80)], 3.2, (5.0, 8.0, 11.0), 0.1),
+        "rect500x200": ([(0, 0), (500, 0), (500, 200), (0, 200)], 3.2, (7.2,), 0.1),      # BASELINE configs 1-2
+        "offset_rect": ([(1000.3, 2000.7), (1180.3, 2000.7), (1180.3, 2075.7), (1000.3, 2075.7)], 3.2, (6.4, 9.6), 0.25),
+        "narrow_loops": ([(0, 0), (90, 0), (90, 70), (0, 70)], 0.8, (6.0,), 0.1),
+        "sheared": ([(0, 0), (200, 0), (230, 90), (30, 90)], 3.2, (8.0,), 0.25),
+        "tilted": ([(0, 0), (150, 20), (140, 95), (-10, 75)], 3.2, (8.0,), 0.25),
+    }
+    verts, W, radii, h = fields[case]
+    got_zoned = 0
+    for R in radii:
+        for corner in (0, 2):
+            fs = rp.setup_field(replace(rp.VehicleParams(), working_width=W, min_turn_radius=R),
+                                field_vertices=[tuple(map(float, v)) for v in verts], obstacles=[])
+            hp = rp.plan_complete_coverage(fs, start_corner=corner)["headland"]["path"]
+            brute = raster.band_coverage(fs, hp, h)
+            model = zoned_model.band_zoned(fs, hp, h)
+            if model is not None:
+                assert model == brute, (case, R, corner, model, brute)
+                got_zoned += 1
+    # rectangles are evaluated zoned; the slanted straights of sheared / tilted fields are general entries that
+    # span the field, the zones overlap and the evaluation falls back to the whole band
+    assert (got_zoned > 0) == (case not in ("tilted", "sheared")), (case, got_zoned)
