@@ -728,6 +728,8 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
     __syncthreads();  // the last pass is done with the tile: reuse it for the breakpoints
     int *bp = reinterpret_cast<int *>(s.tile);  // [nb] sorted breakpoints, then [nb] slow runs (lo, hi)
     const int nb = 10 + 2 * nr + 8;
+    static_assert(T >= 2 * (10 + 2 * RECT_CAP + 8), "one thread per (run, end)");
+    static_assert(12 * (10 + 2 * RECT_CAP + 8) <= TW, "breakpoints, slow runs and row intervals live in the tile");
     {
         int v = -1;
         if (tid == 0) v = 0;
