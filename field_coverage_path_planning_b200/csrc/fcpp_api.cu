@@ -56,7 +56,6 @@ int ensure_workspace(fcpp_handle *h, int64_t n_cand)
     const int64_t tiles = n_cand / 4096 + 2;
     if (tiles > h->scan_tmp_cap) {
         if (h->d_scan_tmp) cudaFree(h->d_scan_tmp);
-    if (h->d_big) cudaFree(h->d_big);
         h->d_scan_tmp = nullptr;
         h->scan_tmp_cap = 0;
         cudaError_t e = cudaMalloc(&h->d_scan_tmp, (size_t)(tiles + 1024) * sizeof(int64_t));
@@ -235,6 +234,10 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
     h->plan_ncap_hint = want;
     h->layout_valid = true;
     h->layout_ncand = batch->n_cand;
+    h->layout_id[0] = batch->cand_R;
+    h->layout_id[1] = batch->cand_flags;
+    h->layout_id[2] = batch->field_verts;
+    h->layout_id[3] = stream;
     return FCPP_OK;
 }
 
@@ -251,8 +254,12 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
     const bool prof = h->profiling;
     if (prof) cudaEventRecord(h->ev[0], st);
     if (out->offsets) {
-        if (!h->layout_valid || h->layout_ncand != batch->n_cand)
-            return fail(h, FCPP_ERR_INVALID, "fcpp_layout must be called for this batch before fcpp_plan_batch");
+        // the layout is stamped with the batch it was computed for (candidate / field arrays, stream): a
+        // layout of another batch of the same size would hand stale records and offsets to the kernels
+        if (!h->layout_valid || h->layout_ncand != batch->n_cand || h->layout_id[0] != batch->cand_R ||
+            h->layout_id[1] != batch->cand_flags || h->layout_id[2] != batch->field_verts || h->layout_id[3] != stream)
+            return fail(h, FCPP_ERR_INVALID, "fcpp_layout must be called for this batch (same arrays, same stream) "
+                                             "before fcpp_plan_batch");
     } else {
         rc = fcpp_layout(h, batch, nullptr, nullptr, stream);
         if (rc) return rc;

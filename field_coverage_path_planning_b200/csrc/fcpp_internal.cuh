@@ -87,6 +87,7 @@ struct fcpp_handle {
     size_t dedupe_bytes;
     uint32_t dedupe_cap;     // slots of the (currently zeroed) table inside d_dedupe; 0 = not initialised
     int64_t layout_ncand;
+    const void *layout_id[4]; // identity of the batch the valid layout belongs to: cand_R, cand_flags, field_verts, stream
     void *d_ga;              // GA workspace (two populations, lengths, fitness, ranks, state, best route)
     size_t ga_bytes;
     void *h_ga_state;        // pinned host copy of the GA state

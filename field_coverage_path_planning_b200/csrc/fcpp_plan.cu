@@ -791,6 +791,9 @@ cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_poi
     a.big_stride = stride;
     a.n_items = n_items;
     const size_t bytes = plan_smem_bytes(0, a.obs_cap_verts, a.obs_cap_polys);
+    if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;  // obstacle tables larger than shared memory
+    cudaError_t ea = cudaFuncSetAttribute(plan_big_kernel<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ea != cudaSuccess) return ea;
     plan_big_kernel<GEN><<<(unsigned)ctas, T0, bytes, st>>>(a);
     h->launches++;
     return cudaGetLastError();

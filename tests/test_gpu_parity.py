@@ -570,3 +570,21 @@ def test_distributed_plan_batch_world1_nccl(fc):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_big_plan_workspace_survives_layout_passes(fc):
+    """Regression: the HBM staging of plans longer than shared memory (launch_big) is owned by the
+    plan launcher alone — a layout pass that grows the scan workspace in between must not free it.  Sequence:
+    long-path speed planning -> plan_batch on a fresh, larger batch -> long-path speed planning again."""
+    from oracle import ref_planner as rp
+    rng = np.random.default_rng(21)
+    pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=500, field_width=200)
+    path = np.cumsum(rng.normal(0, 1.0, size=(12000, 2)), axis=0)
+    speeds = rng.choice([4.0, 9.0, 15.0], size=len(path))
+    want = rp.speed_plan(path, speeds, rp.VehicleParams())
+    assert np.abs(pl._apply_curvature_based_speed_limit(path, speeds) - want).max() <= 1e-9
+    for n in (3, 9000, 40000):     # growing batches: every one re-allocates candidate records / scan workspace
+        cand = fc.make_candidates(1, radii=np.linspace(5.0, 12.0, n))
+        res = fc.plan_batch([RECT], fc.VehicleParams(), cand, coverage=False)
+        assert (res.summary["status"] == 0).all()
+        assert np.abs(pl._apply_curvature_based_speed_limit(path, speeds) - want).max() <= 1e-9

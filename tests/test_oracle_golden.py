@@ -66,6 +66,14 @@ def test_oracle_reproduces_reference(path):
         # lattice points that sit on the buffer boundary may flip -> allow 2 cells per window
         assert np.max(np.abs(np.array(got) - ref_cells)) <= 2
         assert g * g == 25600 or meta["vehicle"]["min_turn_radius"] != 8.0
+        # the averages verify_all_corners_coverage returns (mlp3:1573-1578), stored by make_golden.py
+        avg = [100.0 * np.mean([c[k] for c in got]) / (g * g) for k in (0, 1)]
+        np.testing.assert_allclose(avg + [avg[1] - avg[0]], z["corner_avg"], rtol=0, atol=100.0 * 2 / (g * g) + 1e-9)
+    # headland coverage_rate of the reference (mlp3:1357-1371; the stand-in's D2 area) against the
+    # integer raster of the band (D5): observed <= 2.5e-5 on rectangles, 1.3e-4 on the sheared field
+    if max(fs.field_length, fs.field_width) <= 600:     # the 3500 m fields take 3.5 s each: covered by the GPU test
+        total, cov = raster.band_coverage(fs, z["head_path"], 0.1)
+        assert abs(cov / total - float(z["coverage_rate_sampled"])) <= 2e-4
 
 
 def test_known_answers_readme():
