@@ -278,6 +278,9 @@ class BatchResult:
     d_summary: Optional[torch.Tensor] = None
     cand_base: int = 0
     extras: Dict = dc_field(default_factory=dict)
+    # plan_batch(..., winners=True): field -> (path [n,2], speeds [n] km/h, n_main) of the field's best candidate, on
+    # the host (in a distributed run: the fields whose winner this rank owns)
+    winner_paths: Optional[Dict[int, tuple]] = None
 
     def path(self, b: int):
         """(path [n,2], speeds [n], n_main) of local candidate ``b`` copied to the host."""
@@ -409,23 +412,95 @@ def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, 
     return res
 
 
+def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_cand: Optional[np.ndarray] = None) -> int:
+    """Bring the path and the speed profile of every field's best candidate to the host
+    (``res.winner_paths``); returns the bytes copied device -> host.  ``best_cand`` (default: the batch's own
+    argmin) holds GLOBAL candidate indices; winners outside this batch's range (other ranks' candidates in a
+    distributed run) are skipped.
+
+    outputs='paths' and a few winners: slices of the materialised paths, one synchronisation.  Otherwise (the
+    search configurations, which run summary-only) the winners are planned again as their own small batch
+    with materialised paths — the candidate arrays are slices of the prepared batch, coverage off."""
+    dev = db.dev
+    B = db.pb.n_cand
+    best = res.best_cand if best_cand is None else best_cand
+    own = np.nonzero((best >= res.cand_base) & (best < res.cand_base + B))[0]
+    res.winner_paths = {}
+    if len(own) == 0:
+        return 0
+    local = (best[own] - res.cand_base).astype(np.int64)
+    nbytes = 0
+    with torch.cuda.device(dev):
+        if outputs == "paths" and len(own) <= 16 and res.offsets is not None:
+            o0, o1 = res.offsets[local], res.offsets[local + 1]
+            tot = int((o1 - o0).sum())
+            ho = _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
+            hp = ho[:tot * 16].view(torch.float64).view(tot, 2)
+            hs = ho[tot * 16:tot * 24].view(torch.float64)
+            at = 0
+            for a, b in zip(o0, o1):
+                n = int(b - a)
+                hp[at:at + n].copy_(res.d_path[int(a):int(b)], non_blocking=True)
+                hs[at:at + n].copy_(res.d_speeds[int(a):int(b)], non_blocking=True)
+                at += n
+            torch.cuda.current_stream(dev).synchronize()
+            P, S = hp.numpy().copy(), hs.numpy().copy()
+            offs = np.concatenate([[0], np.cumsum(o1 - o0)])
+            nbytes = tot * 24
+        else:
+            arrays = dict(db.pb.arrays)
+            for k in ("cand_field", "cand_R", "cand_rot", "cand_flags", "cand_start"):
+                if k in arrays:
+                    arrays[k] = np.ascontiguousarray(arrays[k][local])
+            pbw = PreparedBatch(db.pb.vehicle, db.pb.n_fields, len(local), arrays, db.pb.max_obs_verts,
+                                db.pb.max_obs_polys, db.pb.grid_h, False, db.pb.turn_model, db.pb.clothoid_share, False)
+            dbw = DeviceBatch(pbw, dev, slot=db.slot)
+            rw = run_device_batch(dbw, "paths", copy_summary=False)
+            tot = int(rw.offsets[-1])
+            ho = _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
+            hp = ho[:tot * 16].view(torch.float64).view(tot, 2)
+            hs = ho[tot * 16:tot * 24].view(torch.float64)
+            hp.copy_(rw.d_path[:tot], non_blocking=True)
+            hs.copy_(rw.d_speeds[:tot], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            P, S = hp.numpy().copy(), hs.numpy().copy()
+            offs = rw.offsets
+            nbytes = tot * 24 + (len(local) + 1) * 8 + 16 * db.pb.n_fields
+            res.extras["h2d_bytes"] = res.extras.get("h2d_bytes", 0) + pbw.h2d_bytes()
+    nm = res.summary["n_main"] if len(res.summary) == B else None
+    for k, f in enumerate(own):
+        a, b = int(offs[k]), int(offs[k + 1])
+        n_main = int(nm[local[k]]) if nm is not None else -1
+        res.winner_paths[int(f)] = (P[a:b], S[a:b], n_main)
+    return nbytes
+
+
 def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
                      cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
-                     buffers: Optional[BatchBuffers] = None, fetch: bool = True) -> Optional[BatchResult]:
+                     buffers: Optional[BatchBuffers] = None, fetch: bool = True,
+                     winners: bool = False) -> Optional[BatchResult]:
     """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
 
     With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
-    whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only."""
+    whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only.
+    ``winners``: also bring every field's winning path and speeds to the host (``fetch_winner_paths``)."""
     buffers, offsets = _launch_device_batch(db, outputs, want_curvature, cost, cand_base, buffers)
     if not fetch:
         return None
-    return _fetch_device_batch(db, buffers, outputs, offsets, copy_summary, cand_base)
+    res = _fetch_device_batch(db, buffers, outputs, offsets, copy_summary, cand_base)
+    res.extras["h2d_bytes"] = db.pb.h2d_bytes()
+    res.extras["d2h_bytes"] = (len(res.summary) * _lib.SUMMARY_DTYPE.itemsize + 16 * db.pb.n_fields
+                               + ((db.pb.n_cand + 1) * 8 if outputs == "paths" else 0))
+    if winners:
+        res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs)
+    return res
 
 
 def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,
                obstacles=None, start_points=None, outputs: str = "summary", grid_h: float = 0.1,
                coverage: bool = True, cost: str = "length", device=None, want_curvature: bool = False,
-               distributed: bool = False, turn_model: str = "arc", clothoid_share: float = 0.5) -> BatchResult:
+               distributed: bool = False, turn_model: str = "arc", clothoid_share: float = 0.5,
+               winners: bool = False) -> BatchResult:
     """Evaluate B candidate plans.  See ``prepare_batch`` for the inputs.
 
     Returns a ``BatchResult``: per-candidate ``summary`` records (layout counts, path lengths and
@@ -438,17 +513,21 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     Fresnel integrals are evaluated per sample point on the device; ``clothoid_share`` in (0, 1] is
     the share of each turn's deflection spent on the clothoids.
 
+    ``winners=True`` also returns every field's winning path and speed profile on the host
+    (``BatchResult.winner_paths``) — what a search caller needs from a batch.
+
     ``distributed=True`` (inside a torch.distributed job): the candidates are sharded over the
     ranks in contiguous ranges, each rank plans its shard on its own GPU and the per-field best
-    is reduced with two NCCL all-reduces (see ``dist.py``)."""
+    is merged with ONE all-gather of the (cost, candidate) words + a merge kernel (see ``dist.py``);
+    ``winner_paths`` then holds the fields whose winner this rank owns."""
     vehicle = vehicle or VehicleParams()
     if distributed:
         from . import dist
         return dist.plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h,
-                                       coverage, cost, device, want_curvature, turn_model, clothoid_share)
+                                       coverage, cost, device, want_curvature, turn_model, clothoid_share, winners)
     dev = _dev(device)
     pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage, turn_model,
                        clothoid_share)
     db = DeviceBatch(pb, dev)
-    return run_device_batch(db, outputs, want_curvature, cost)
+    return run_device_batch(db, outputs, want_curvature, cost, winners=winners)
 

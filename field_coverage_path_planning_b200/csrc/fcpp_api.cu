@@ -305,6 +305,19 @@ int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t w
     return FCPP_OK;
 }
 
+int fcpp_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t cand_lo, int64_t cand_hi,
+                        const int64_t *d_best_cand, int32_t n_fields, void *d_out, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (n_fields < 0 || cand_hi < cand_lo || (n_fields > 0 && (!d_best_cand || !d_out)) || (cand_hi > cand_lo && !d_summary))
+        return fail(h, FCPP_ERR_INVALID, "fcpp_winner_records: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_winner_records(h, d_summary, cand_lo, cand_hi, d_best_cand, n_fields, d_out,
+                                               (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "winner records kernel");
+    return FCPP_OK;
+}
+
 int fcpp_field_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
                                const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
                                int64_t *d_best_cand, void *stream)

@@ -534,6 +534,8 @@ void fcpp_ga_read_state(const void *host_copy, int &gen, int &stagnant, int &don
                         double &best_len);
 cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int world, int32_t n_fields,
                                      double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);
+cudaError_t fcpp_launch_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t lo, int64_t hi,
+                                       const int64_t *d_best_cand, int32_t n_fields, void *d_out, cudaStream_t st);
 cudaError_t fcpp_launch_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
                                         const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
                                         int64_t *d_best_cand, cudaStream_t st);

@@ -239,6 +239,19 @@ __global__ void __launch_bounds__(EXCH_THREADS) argmin_exchange_kernel(const Exc
     }
 }
 
+// multi-GPU: this rank's contribution to the all-gather of the winners' summary records — the 176-byte record of
+// every field whose global winner lies in [lo, hi), zeros elsewhere (a SUM over the ranks then is the record)
+__global__ void winner_records_kernel(const fcpp_summary *__restrict__ sm, int64_t lo, int64_t hi,
+                                      const long long *__restrict__ best_cand, int n_fields, int4 *__restrict__ out)
+{
+    constexpr int W = sizeof(fcpp_summary) / 16;  // 11 int4 words per record
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_fields * W) return;
+    const int f = (int)(t / W), k = (int)(t - (int64_t)f * W);
+    const long long b = best_cand[f];
+    out[t] = (b >= lo && b < hi) ? reinterpret_cast<const int4 *>(sm + (b - lo))[k] : make_int4(0, 0, 0, 0);
+}
+
 // multi_field_planner.py:263-288 ("mfp"): D[i][j] = ||pos_i - pos_j||, 0 on the diagonal
 __global__ void distance_matrix_kernel(const double *__restrict__ pos, int n, double *__restrict__ D)
 {
@@ -290,6 +303,18 @@ cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, 
     if (n_fields == 0) return cudaSuccess;
     argmin_merge_kernel<<<(n_fields + 255) / 256, 256, 0, st>>>((const long long *)d_gathered, world, n_fields,
                                                                 d_best_cost, (long long *)d_best_cand);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t fcpp_launch_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t lo, int64_t hi,
+                                       const int64_t *d_best_cand, int32_t n_fields, void *d_out, cudaStream_t st)
+{
+    if (n_fields == 0) return cudaSuccess;
+    static_assert(sizeof(fcpp_summary) % 16 == 0, "records are copied as int4 words");
+    const int64_t n = (int64_t)n_fields * (sizeof(fcpp_summary) / 16);
+    winner_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_summary, lo, hi, (const long long *)d_best_cand,
+                                                                       n_fields, (int4 *)d_out);
     h->launches++;
     return cudaGetLastError();
 }

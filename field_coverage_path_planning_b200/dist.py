@@ -5,8 +5,8 @@ The reduction is exact and deterministic (ties go to the lowest global candidate
     1+2. CUDA: ONE all-gather of every rank's (best cost, best candidate) words and the library's
        merge kernel (fcpp_field_argmin_merge).  CPU/gloo (tests): all_reduce(MIN) of the cost, then
        all_reduce(MIN) of the candidate index where the local best equals the global minimum;
-    3. the winner's 176-byte summary record is contributed by its owner and summed as int32
-       words (every other rank contributes zeros), i.e. an all-gather of one record per field.
+    3. the winner's 176-byte summary record is contributed by its owner (fcpp_winner_records) and summed
+       as int32 words (every other rank contributes zeros), i.e. an all-gather of one record per field.
 Works on NCCL (CUDA tensors) and gloo (CPU tensors — used by the world_size-2 CPU tests).
 """
 from __future__ import annotations
@@ -130,9 +130,21 @@ def reduce_best(best_cost: torch.Tensor, best_cand: torch.Tensor, group=None, pe
 def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, lo: int, hi: int,
                           group=None) -> torch.Tensor:
     """[F, 176] uint8: the summary record of every field's global winner.
-    ``summary_bytes`` = this rank's records as a flat uint8 tensor ((hi-lo)*176 bytes)."""
+    ``summary_bytes`` = this rank's records as a flat uint8 tensor ((hi-lo)*176 bytes).
+    CUDA: one library kernel writes the records this rank owns (zeros elsewhere), one all-reduce sums them;
+    CPU tensors (gloo tests): the same with torch ops."""
     rec = _lib.SUMMARY_DTYPE.itemsize
     F = best_cand.numel()
+    if best_cand.is_cuda:
+        import ctypes as C
+        dev = best_cand.device
+        out = torch.empty((F, rec), dtype=torch.uint8, device=dev)
+        h = _lib.handle(dev.index)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        h.check(h.lib.fcpp_winner_records(h.h, summary_bytes.data_ptr() if hi > lo else None, lo, hi,
+                                          best_cand.data_ptr(), F, out.data_ptr(), st))
+        dist.all_reduce(out.view(torch.int32), op=dist.ReduceOp.SUM, group=group)
+        return out
     own = (best_cand >= lo) & (best_cand < hi)
     idx = torch.where(own, best_cand - lo, torch.zeros_like(best_cand))
     rows = summary_bytes.view(-1, rec)[idx] if hi > lo else torch.zeros((F, rec), dtype=torch.uint8,
@@ -144,9 +156,13 @@ def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, 
 
 
 def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h, coverage, cost,
-                       device, want_curvature, turn_model="arc", clothoid_share=0.5):
-    """plan_batch over all ranks of the default process group (see batch.plan_batch)."""
-    from .batch import DeviceBatch, _dev, prepare_batch, run_device_batch
+                       device, want_curvature, turn_model="arc", clothoid_share=0.5, winners=False):
+    """plan_batch over all ranks of the default process group (see batch.plan_batch): every rank plans its
+    contiguous shard; ONE all-gather + merge kernel gives every rank the per-field argmin, one kernel + one
+    all-reduce every winner's summary record; the local summaries, the merged argmin and the winners' records
+    come back to the host with ONE synchronisation."""
+    from .batch import (DeviceBatch, _Staging, _dev, _fetch_device_batch, _launch_device_batch, fetch_winner_paths,
+                        prepare_batch)
     if not dist.is_initialized():
         raise RuntimeError("distributed=True needs torch.distributed.init_process_group (backend 'nccl')")
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -160,12 +176,20 @@ def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, out
     dev = _dev(device)
     pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage, turn_model, clothoid_share)
     db = DeviceBatch(pb, dev)
-    res = run_device_batch(db, outputs, want_curvature, cost, cand_base=lo)
-    bufs = res.extras["buffers"]
-    reduce_best(bufs.d_cost, bufs.d_best)
+    F = pb.n_fields
+    bufs, offsets = _launch_device_batch(db, outputs, want_curvature, cost, lo, None)
+    reduce_best(bufs.d_cost, bufs.d_best)                   # in place: d_cost / d_best now hold the GLOBAL result
     win = gather_winner_records(bufs.d_sum, bufs.d_best, lo, hi)
-    res.best_cost = bufs.d_cost.cpu().numpy()[:pb.n_fields]
-    res.best_cand = bufs.d_best.cpu().numpy()[:pb.n_fields]
-    res.extras["winner_summary"] = win.cpu().numpy().view(_lib.SUMMARY_DTYPE).reshape(-1)[:pb.n_fields]
+    rec = _lib.SUMMARY_DTYPE.itemsize
+    with torch.cuda.device(dev):                            # the winners' records ride on the same read-back
+        hw = _Staging.get(dev, 7).host_out(max(F * rec, 256))
+        if F:
+            hw[:F * rec].copy_(win.view(-1), non_blocking=True)
+    res = _fetch_device_batch(db, bufs, outputs, offsets, True, lo)     # ONE synchronisation
+    res.extras["winner_summary"] = hw.numpy()[:F * rec].copy().view(_lib.SUMMARY_DTYPE).reshape(-1)[:F]
     res.extras["shard"] = (lo, hi)
+    res.extras["h2d_bytes"] = pb.h2d_bytes()
+    res.extras["d2h_bytes"] = (len(res.summary) * rec + 16 * F + F * rec + ((pb.n_cand + 1) * 8 if outputs == "paths" else 0))
+    if winners:
+        res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs)
     return res

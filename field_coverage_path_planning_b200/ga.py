@@ -181,139 +181,33 @@ class GAConfig:
 class GeneticAlgorithmSolver:
     """Permutation GA for the multi-field TSP ordering (ga:32-268) with GPU fitness."""
 
-    def __init__(self, config: GAConfig = None, seed: Optional[int] = None, device=None,
-                 operators: str = "device"):
-        if operators not in ("device", "host"):
-            raise ValueError("operators must be 'device' or 'host'")
+    def __init__(self, config: GAConfig = None, seed: Optional[int] = None, device=None):
         self.config = config or GAConfig()
         self.best_fitness_history: List[float] = []
         self.avg_fitness_history: List[float] = []
-        self.rng = np.random.default_rng(seed)
         # the reference is unseeded (global `random`): without a seed every solver draws a fresh one
         self.seed = int(seed) if seed is not None else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
-        self.operators = operators
         self._device = device
 
-    # -- fitness on the device (the hot path) ------------------------------------------------
-    def _fitness(self, D_dev: torch.Tensor, pop: np.ndarray):
-        d, fit = tour_lengths(D_dev, torch.from_numpy(pop).to(D_dev.device), return_fitness=True)
-        self._last_lengths = d.cpu().numpy()
-        return fit.cpu().numpy()
-
+    # -- fitness on the device (the hot path, ga:168-181) ----------------------------------------
     def _calculate_distance(self, route, distance_matrix) -> float:
         return float(tour_lengths(distance_matrix, np.asarray([route], dtype=np.int32), device=self._device)[0])
 
     def _calculate_fitness(self, route, distance_matrix) -> float:
         return 1.0 / (self._calculate_distance(route, distance_matrix) + 1e-6)
 
-    # -- host-side evolution operators (statistical parity, SURVEY.md §8(f) N1) ---------------
-    def _initialize_population(self, n: int) -> np.ndarray:
-        cfg = self.config
-        half = cfg.population_size // 2
-        rows = [self.rng.permutation(n) for _ in range(half)]
-        for i in range(half):   # "greedy" init of the reference is random too (ga:155-166)
-            start = i % n
-            rest = self.rng.permutation(np.delete(np.arange(n), start))
-            rows.append(np.concatenate([[start], rest]))
-        return np.asarray(rows, dtype=np.int32)
-
-    def _selection(self, pop: np.ndarray, fit: np.ndarray) -> np.ndarray:
-        k = self.config.tournament_size
-        m = len(pop)
-        # sampling WITHOUT replacement per tournament (random.sample, ga:189); first max wins
-        idx = np.argsort(self.rng.random((m, m)), axis=1)[:, :k] if m <= 2048 else \
-            np.stack([self.rng.choice(m, size=k, replace=False) for _ in range(m)])
-        win = idx[np.arange(m), np.argmax(fit[idx], axis=1)]
-        return pop[win].copy()
-
-    def _ox(self, p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
-        n = len(p1)
-        a, b = sorted(self.rng.choice(n, size=2, replace=False).tolist())
-        child = np.full(n, -1, dtype=np.int32)
-        child[a:b] = p1[a:b]
-        used = np.zeros(n, dtype=bool)
-        used[p1[a:b]] = True
-        order = np.concatenate([p2[b:], p2[:b]])          # fill starts at cx_point2, wrapping (ga:229-240)
-        fill = order[~used[order]]
-        pos = np.concatenate([np.arange(b, n), np.arange(0, a)])
-        child[pos] = fill
-        return child
-
-    def _crossover(self, pop: np.ndarray) -> np.ndarray:
-        out = []
-        m = len(pop)
-        for i in range(0, m, 2):
-            p1 = pop[i]
-            p2 = pop[i + 1] if i + 1 < m else pop[0]      # odd population pairs with individual 0 (ga:205)
-            if self.rng.random() < self.config.crossover_rate:
-                out.append(self._ox(p1, p2))
-                out.append(self._ox(p2, p1))
-            else:
-                out.append(p1.copy())
-                out.append(p2.copy())
-        return np.asarray(out, dtype=np.int32)
-
-    def _mutation(self, pop: np.ndarray) -> np.ndarray:
-        n = pop.shape[1]
-        hit = np.nonzero(self.rng.random(len(pop)) < self.config.mutation_rate)[0]
-        for r in hit:
-            i, j = self.rng.choice(n, size=2, replace=False)
-            pop[r, i], pop[r, j] = pop[r, j], pop[r, i]
-        return pop
-
-    def _elitism(self, old: np.ndarray, fit: np.ndarray, new: np.ndarray) -> np.ndarray:
-        e = self.config.elite_size
-        if e <= 0:            # python slicing of ga:262-266: new[:-0] is empty, argsort[-0:] is everything
-            return old[np.argsort(fit, kind="stable")]
-        elite = old[np.argsort(fit, kind="stable")[-e:]]
-        return np.concatenate([new[:-e], elite])                     # drops the LAST children (ga:266)
-
     def solve(self, distance_matrix: np.ndarray, verbose: bool = True) -> Tuple[List[int], dict]:
         """ga:44-135."""
         cfg = self.config
         t0 = time.time()
         n = len(distance_matrix)
-        if self.operators == "device":
-            route, stats, hist = ga_solve_device(cfg, distance_matrix, seed=self.seed, device=self._device)
-            self.best_fitness_history = hist[:, 0].tolist()
-            self.avg_fitness_history = hist[:, 1].tolist()
-            stats['time'] = time.time() - t0
-            if verbose:
-                print(f"[fcpp GA] nodes={n} generations={stats['generations']} best={stats['best_distance']:.1f} m "
-                      f"time={stats['time']:.2f} s (device operators)")
-            return route, stats
-        dev = _dev(self._device)
-        D_dev = torch.from_numpy(np.ascontiguousarray(distance_matrix, dtype=np.float64)).to(dev)
-        pop = self._initialize_population(n)
-        fit = self._fitness(D_dev, pop)
-        best_i = int(np.argmax(fit))
-        best_route, best_fit = pop[best_i].copy(), float(fit[best_i])
-        best_distance = float(self._last_lengths[best_i])
-        stagnant, gens, gen = 0, 0, -1
-        self.best_fitness_history, self.avg_fitness_history = [], []
-        for gen in range(cfg.max_generations):
-            gens = gen + 1
-            sel = self._selection(pop, fit)
-            chi = self._mutation(self._crossover(sel))
-            pop = self._elitism(pop, fit, chi)
-            fit = self._fitness(D_dev, pop)
-            gi = int(np.argmax(fit))
-            if fit[gi] > best_fit:
-                best_fit, best_route = float(fit[gi]), pop[gi].copy()
-                best_distance = float(self._last_lengths[gi])
-                stagnant = 0
-            else:
-                stagnant += 1
-            self.best_fitness_history.append(best_fit)
-            self.avg_fitness_history.append(float(np.mean(fit)))
-            if stagnant >= cfg.convergence_threshold:
-                break
-        route = best_route.tolist()
-        z = route.index(0)
-        route = route[z:] + route[:z]                      # depot first (ga:119-120)
-        stats = {'generations': gens, 'best_distance': best_distance, 'best_fitness': best_fit,
-                 'convergence_gen': gen - stagnant,      # ga:125-130
-                 'time': time.time() - t0}
+        # selection, OX crossover, swap mutation, elitism, fitness and best tracking all run on the device
+        # (fcpp_ga_solve); there is no host operator path
+        route, stats, hist = ga_solve_device(cfg, distance_matrix, seed=self.seed, device=self._device)
+        self.best_fitness_history = hist[:, 0].tolist()
+        self.avg_fitness_history = hist[:, 1].tolist()
+        stats['time'] = time.time() - t0
         if verbose:
-            print(f"[fcpp GA] nodes={n} generations={gens} best={best_distance:.1f} m time={stats['time']:.2f} s")
+            print(f"[fcpp GA] nodes={n} generations={stats['generations']} best={stats['best_distance']:.1f} m "
+                  f"time={stats['time']:.2f} s")
         return route, stats

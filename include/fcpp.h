@@ -200,6 +200,13 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
 int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t world, int32_t n_fields,
                             double *d_best_cost, int64_t *d_best_cand, void *stream);
 
+/* Multi-GPU: this rank's contribution to the exchange of the winners' records after the merge: d_out [F][176 bytes]
+ * = the summary record of every field whose global winner d_best_cand[f] lies in this rank's candidate range
+ * [cand_lo, cand_hi) (d_summary holds that range), zeros for every other field — summing the ranks' buffers as
+ * 32-bit words (one all-reduce) gives every rank every winner's record. */
+int fcpp_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t cand_lo, int64_t cand_hi,
+                        const int64_t *d_best_cand, int32_t n_fields, void *d_out, void *stream);
+
 /* Multi-GPU, fused form of all-gather + fcpp_field_argmin_merge: ONE kernel writes this rank's (cost, candidate)
  * words into every rank's symmetric buffer over peer memory (NVLink P2P stores), publishes a flag per rank,
  * waits for the other ranks' flags and merges — no NCCL call.  d_best_cost / d_best_cand hold the local result

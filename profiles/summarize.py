@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn an .ncu-rep (ncu --set full --import-source on) into the text summary committed under
 profiles/: per kernel the roofline-relevant metrics, the top stall reasons and the hottest CUDA
-source lines.   usage: python profiles/summarize.py gpurun_out/x.ncu-rep [profiles/ncu_traffic.json] > profiles/x.summary.md"""
+source lines.   usage: python profiles/summarize.py gpurun_out/x.ncu-rep [profiles/ncu_metrics.json [workload]] > profiles/x.summary.md"""
 import csv
 import io
 import subprocess
@@ -33,30 +33,40 @@ WANT = [
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def traffic_json(rows, idx, units, rep, out):
-    """profiles/ncu_traffic.json: DRAM bytes per launch of each kernel (read by bench.py -> roofline.traffic)"""
+def traffic_json(rows, idx, units, rep, out, workload="c2"):
+    """profiles/ncu_metrics.json: per workload and kernel the per-launch DRAM bytes and the issue-slot / FP64-pipe
+    utilisation of the committed capture (read by bench.py -> roofline.traffic / issue_slot_frac / fp64_pipe_frac).
+    The file is merged: other workloads' entries are kept."""
     import json
+    import os
     import re
-    res = {"_source": rep.rsplit("/", 1)[-1], "_how": "ncu --set full --clock-control none, one launch per kernel"}
+    res = {}
+    if os.path.exists(out):
+        res = json.load(open(out))
+    w = res.setdefault(workload, {})
     for r in rows[2:]:
         m = re.search(r"(\w+_kernel)", r[idx["Kernel Name"]])
         if not m:
             continue
         rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
         wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
-        res[m.group(1)] = {"dram_read_bytes": rd, "dram_write_bytes": wr,
-                           "duration_ms_under_ncu": float(r[idx["gpu__time_duration.sum"]]) *
-                           {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0)}
+        w[m.group(1)] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
+                         "issue_slot_frac": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]) / 100,
+                         "fp64_pipe_frac": float(r[idx["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]]) / 100,
+                         "warp_instructions": float(r[idx["smsp__inst_executed.sum"]]),
+                         "duration_ms_under_ncu": float(r[idx["gpu__time_duration.sum"]]) *
+                         {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0),
+                         "source": rep.rsplit("/", 1)[-1] + " (ncu --set full --clock-control none, one launch per kernel)"}
     json.dump(res, open(out, "w"), indent=1)
 
 
-def main(rep, traffic_out=None):
+def main(rep, traffic_out=None, workload="c2"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     if traffic_out:
-        traffic_json(rows, idx, units, rep, traffic_out)
+        traffic_json(rows, idx, units, rep, traffic_out, workload)
     print(f"# ncu summary of `{rep.rsplit('/', 1)[-1]}` (ncu --set full --clock-control none)\n")
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
@@ -87,4 +97,4 @@ def main(rep, traffic_out=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else "c2")
