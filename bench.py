@@ -427,7 +427,7 @@ def main():
     g = s["corner_g"].astype(np.int64)
     G_cells = s["cov_total"].astype(np.int64) + 4 * g * g
     npts = (s["n_main"] + s["n_head"]).astype(np.int64)
-    bytes_plan = float(((24 * npts if w.outputs == "paths" else 0) + 176 + 1008).sum())
+    bytes_plan = float((24 * npts * (1 if w.outputs == "paths" else 0) + 176 + 1008).sum())
     bytes_cover = float((2 * ((G_cells + 7) // 8) + 176 + 1008).sum())
     peak, peak_src = measured_peak_gbs()
     if k_cover >= k_plan:

@@ -396,48 +396,79 @@ __device__ __forceinline__ void corner_arc_pt(const TrigTables &tt, const TurnMo
 __device__ __forceinline__ int64_t qfix(double x) { return __double2ll_rn(x * FCPP_FIXED_UNIT); }
 
 // ---------------------------------------------------------------------------------------------
-// point generation: index -> (x, y, speed class)
+// point generation: index -> (x, y, speed class, structure tag)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W, int i,
-                                          double &x, double &y, uint8_t &cls)
+// A plan is made of a few CONGRUENT pieces: every main pass (2 swath ends + 20 turn samples) is a
+// translate / mirror image of the first one, every corner turn is the same 15-sample arc turned by a
+// multiple of 90 degrees, the interior of a straight or of a reverse fill is equally spaced and
+// collinear.  The structure tag of a point names its piece and its position in it, so that the plan
+// kernel takes the segment length, the curvature and the curvature speed limit of such a point from a
+// per-candidate table instead of recomputing sqrt / atan2 / divisions for every point; the first and
+// last point of every piece (where two pieces meet) are GENERIC and are evaluated from the coordinates.
+constexpr int SLOT_MAIN = 0;       // + j: position in a main pass (0, 1 = swath ends, 2 + a = turn sample a)
+constexpr int SLOT_ARC = 22;       // + a: corner-turn sample a (1 .. 13)
+constexpr int SLOT_REV = 37;       // + t: interior of the reverse fill after turn t of loop 0
+constexpr int SLOT_STRAIGHT = 40;  // + 4 k + t: interior of straight t of headland loop k
+constexpr int N_SLOTS = SLOT_STRAIGHT + 4 * FCPP_MAX_LOOPS;
+constexpr int TAG_GENERIC = 252;   // + speed class
+// generic points get a fixed ordinal (deterministic summation order): 0, 1 = first / last main point, then 21
+// per headland loop: 0 = loop start, 1 + 2 t / 2 + 2 t = ends of straight t, 9 + 2 t / 10 + 2 t = ends of turn t,
+// 15 + 2 t / 16 + 2 t = ends of reverse fill t
+constexpr int GEN_PER_LOOP = 21;
+constexpr int N_GENERIC = 2 + GEN_PER_LOOP * FCPP_MAX_LOOPS;
+
+// main-work point (visit index idx, position j in the pass) in the swath frame, before the rotate-back
+__device__ __forceinline__ void main_local_pt(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W,
+                                              int idx, int j, double &px, double &py)
 {
+    // mlp3:744-780: visit index idx, pass index pi, 2 endpoints + 20 arc samples per pass
+    const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
+    const double yy = r.min_y + pi * W;  // mlp3:751
+    const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
+    if (j < 2) {
+        const double xs = r.min_x + r.R, xe = r.max_x - r.R;  // mlp3:736-737
+        px = (go_left == (j == 0)) ? xe : xs;                  // mlp3:761-764
+        py = yy;
+    } else {
+        const int a = j - 2;
+        if (tm.model == FCPP_TURN_CLOTHOID) {
+            // clothoid-arc-clothoid U-turn leaving the swath end tangentially towards the next swath
+            double xi, eta;
+            cac_unit(3.141592653589793, FCPP_UTURN_POINTS, a, tm.lam, xi, eta);
+            const double xe = go_left ? r.min_x + r.R : r.max_x - r.R;
+            const double dir_x = go_left ? -1.0 : 1.0;
+            const double dir_y = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? -1.0 : 1.0;
+            px = xe + dir_x * (r.R * xi);
+            py = yy + dir_y * (r.R * eta);
+        } else {
+            const bool turn_right = !go_left;  // mlp3:776
+            px = turn_right ? (r.max_x - r.R * tt.cos20[a]) : (r.min_x + r.R * tt.cos20[a]);  // mlp3:815, :822
+            py = yy + r.R * tt.sin20[a];                                                       // mlp3:816, :823
+        }
+    }
+}
+
+__device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W,
+                                              int i, double &x, double &y, uint8_t &cls, int &tag, int &gord)
+{
+    gord = -1;
     if (i < r.n_main) {
-        // mlp3:744-780: visit index idx, pass index pi, 2 endpoints + 20 arc samples per pass
         const int per = 2 + FCPP_UTURN_POINTS;
         const int idx = i / per;
         const int j = i - idx * per;
-        const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
-        const double yy = r.min_y + pi * W;  // mlp3:751
-        const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
         double px, py;
-        if (j < 2) {
-            const double xs = r.min_x + r.R, xe = r.max_x - r.R;  // mlp3:736-737
-            px = (go_left == (j == 0)) ? xe : xs;                  // mlp3:761-764
-            py = yy;
-            cls = CLS_WORK;
-        } else {
-            const int a = j - 2;
-            if (tm.model == FCPP_TURN_CLOTHOID) {
-                // clothoid-arc-clothoid U-turn leaving the swath end tangentially towards the next swath
-                double xi, eta;
-                cac_unit(3.141592653589793, FCPP_UTURN_POINTS, a, tm.lam, xi, eta);
-                const double xe = go_left ? r.min_x + r.R : r.max_x - r.R;
-                const double dir_x = go_left ? -1.0 : 1.0;
-                const double dir_y = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? -1.0 : 1.0;
-                px = xe + dir_x * (r.R * xi);
-                py = yy + dir_y * (r.R * eta);
-            } else {
-                const bool turn_right = !go_left;  // mlp3:776
-                px = turn_right ? (r.max_x - r.R * tt.cos20[a]) : (r.min_x + r.R * tt.cos20[a]);  // mlp3:815, :822
-                py = yy + r.R * tt.sin20[a];                                                       // mlp3:816, :823
-            }
-            cls = CLS_TURN;
-        }
+        main_local_pt(r, tt, tm, W, idx, j, px, py);
+        cls = (j < 2) ? CLS_WORK : CLS_TURN;
         if (r.flags & FCPP_FLAG_ROTATED)
             rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
         else {
             x = px;
             y = py;
+        }
+        tag = SLOT_MAIN + j;
+        if (i == 0 || i == r.n_main - 1) {
+            tag = TAG_GENERIC + cls;
+            gord = (i == 0) ? 0 : 1;
         }
         return;
     }
@@ -454,10 +485,13 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
         m = hI - (k - 1) * FCPP_POINTS_PER_LOOP;
     }
     const int sc = r.flags & FCPP_FLAG_CORNER_MASK;
+    const int g0 = 2 + GEN_PER_LOOP * k;
     if (m == 0) {  // mlp3:978-980
         x = r.corners[k][sc][0];
         y = r.corners[k][sc][1];
         cls = CLS_HEAD;
+        tag = TAG_GENERIC + CLS_HEAD;
+        gord = g0;
         return;
     }
     m -= 1;
@@ -477,6 +511,11 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
                 y = m * sy + ay;
             }
             cls = CLS_HEAD;
+            tag = SLOT_STRAIGHT + 4 * k + t;
+            if (m == 0 || m == FCPP_STRAIGHT_POINTS - 1) {
+                tag = TAG_GENERIC + CLS_HEAD;
+                gord = g0 + 1 + 2 * t + (m ? 1 : 0);
+            }
             return;
         }
         m -= FCPP_STRAIGHT_POINTS;
@@ -484,6 +523,11 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
             if (m < FCPP_CORNER_POINTS) {
                 corner_arc_pt(tt, tm, r.corners[k][ni][0], r.corners[k][ni][1], r.R, ni, m, x, y);
                 cls = CLS_TURN;
+                tag = SLOT_ARC + m;
+                if (m == 0 || m == FCPP_CORNER_POINTS - 1) {
+                    tag = TAG_GENERIC + CLS_TURN;
+                    gord = g0 + 9 + 2 * t + (m ? 1 : 0);
+                }
                 return;
             }
             m -= FCPP_CORNER_POINTS;
@@ -494,6 +538,11 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
                 x = r.rev[t][0] + tt_ * r.rev[t][2];
                 y = r.rev[t][1] + tt_ * r.rev[t][3];
                 cls = CLS_REVERSE;
+                tag = SLOT_REV + t;
+                if (m == 0 || m == nr - 1) {
+                    tag = TAG_GENERIC + CLS_REVERSE;
+                    gord = g0 + 15 + 2 * t + (m ? 1 : 0);
+                }
                 return;
             }
             m -= nr;
@@ -502,6 +551,15 @@ __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt
     x = 0.0;
     y = 0.0;
     cls = CLS_HEAD;  // unreachable
+    tag = TAG_GENERIC + CLS_HEAD;
+    gord = 0;
+}
+
+__device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W, int i,
+                                          double &x, double &y, uint8_t &cls)
+{
+    int tag, gord;
+    gen_point_tag(r, tt, tm, W, i, x, y, cls, tag, gord);
 }
 
 

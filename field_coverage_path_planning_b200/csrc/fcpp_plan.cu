@@ -11,8 +11,12 @@
 //   A9  geofence / obstacle point tests              D3 (no reference code; README.md:24,200)
 //   A13 path length / work time                      mlp3:1290-1311
 //
-// The same kernel, instantiated with GEN=false, runs A7/A8/A13 on caller-supplied paths
-// (verify_curvature_constraints(path, speeds) of the drop-in API).
+// GEN = true (plan_body_gen): the plan is generated; the segment length, curvature and curvature speed limit of
+// every point inside a congruent piece (main passes, corner turns, straights, reverse fills — fcpp_internal.cuh)
+// come from a per-candidate table of ~100 entries, only the points where two pieces meet (~3 % of a plan) are
+// evaluated from their coordinates (sqrt, atan2, divisions).
+// GEN = false (plan_body_path): A7/A8/A13 on caller-supplied paths (verify_curvature_constraints(path, speeds)
+// of the drop-in API), every point evaluated from the coordinates.
 #include "fcpp_internal.cuh"
 
 namespace {
@@ -45,15 +49,27 @@ struct PlanArgs {
     int64_t n_items;          // candidates / paths in the batch
 };
 
+// per-candidate table entry of a structure slot: segment length to the next point, curvature, curvature-limited
+// speed (km/h) and its u = (v / 3.6)^2, time of the segment with the initial speeds
+struct Tpl {
+    double ds, kap, u, vl, tpre;
+};
+constexpr int TPL_PTS = 48;  // scratch points of the table set-up: 24 main + 15 turn samples
+
 struct Smem {
     double *X, *Y, *U;
-    uint8_t *CLS;
+    uint8_t *CLS;      // GEN: the structure tag of the point (fcpp_internal.cuh)
     CandRec *rec;
     TrigTables *tt;
     double *obs_xy;    // [obs_cap_verts][2]
     int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
     double *obs_bb;    // [obs_cap_polys][4] bbox of each obstacle grown by W/2 + 1e-6 (early reject)
     double *scratch;   // [SCRATCH]
+    Tpl *tbl;          // [N_SLOTS]
+    double *tpts;      // [TPL_PTS][2]
+    double *geo;       // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
+    double *gvl;       // [N_GENERIC] curvature-limited speed of the generic points
+    int32_t *glist;    // [N_GENERIC] point index of generic ordinal g (-1: none)
     uint64_t *bar;
 };
 
@@ -71,6 +87,11 @@ __host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int o
     s += align16(sizeof(int32_t) * (obs_polys + 1));
     s += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
     s += align16(sizeof(double) * SCRATCH);
+    s += align16(sizeof(Tpl) * N_SLOTS);
+    s += align16(sizeof(double) * 2 * TPL_PTS);
+    s += align16(sizeof(double) * 20);
+    s += align16(sizeof(double) * N_GENERIC);
+    s += align16(sizeof(int32_t) * N_GENERIC);
     s += 16;
     return s;
 }
@@ -99,6 +120,16 @@ __device__ inline Smem carve(unsigned char *base, int ncap, int obs_verts, int o
     o += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
     s.scratch = (double *)(base + o);
     o += align16(sizeof(double) * SCRATCH);
+    s.tbl = (Tpl *)(base + o);
+    o += align16(sizeof(Tpl) * N_SLOTS);
+    s.tpts = (double *)(base + o);
+    o += align16(sizeof(double) * 2 * TPL_PTS);
+    s.geo = (double *)(base + o);
+    o += align16(sizeof(double) * 20);
+    s.gvl = (double *)(base + o);
+    o += align16(sizeof(double) * N_GENERIC);
+    s.glist = (int32_t *)(base + o);
+    o += align16(sizeof(int32_t) * N_GENERIC);
     s.bar = (uint64_t *)(base + o);
     return s;
 }
@@ -266,20 +297,47 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
     return v0;
 }
 
-// One plan (GEN) or one caller-supplied path (!GEN).  `s` points at the staging arrays (shared
-// memory in plan_kernel, an HBM/L2 scratch slice in plan_big_kernel), `cap` is their capacity.
-template <bool GEN, bool BIG, int T>
-__device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
-                                          const uint32_t phase)
+// a / b for a finite a >= 0 and a normal b > 0 (speeds >= 0.1 m/s): reciprocal seed + two Newton steps + one
+// residual correction — correctly rounded in all but the rarest cases (the sums it feeds are compared at 1e-9),
+// a third of the instructions of the generic division and no slow path
+__device__ __forceinline__ double div_pos(double a, double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// final speed of a point from its scanned u (mlp3:558-587): the km/h limit comes back verbatim when the scans
+// left it alone, else 3.6 sqrt(u); the square root only runs in warps where some lane needs it.
+// Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ double final_speed(bool act, double u, double u_lim, double vl)
+{
+    const bool need = act && (u != u_lim);
+    double v = vl;
+    if (__any_sync(0xffffffffu, need)) {
+        const double sq = sqrt(need ? u : 1.0);
+        if (need) v = 3.6 * sq;
+    }
+    return v;
+}
+
+// One generated plan.  `s` points at the staging arrays (shared memory in plan_kernel, an HBM/L2 scratch slice
+// in plan_big_kernel), `cap` is their capacity.
+template <bool BIG, int T>
+__device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
+                                              const uint32_t phase)
 {
     const int tid = threadIdx.x;
-    const fcpp_vehicle &veh = GEN ? a.b.vehicle : a.veh;
+    const fcpp_vehicle &veh = a.b.vehicle;
     fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
 
     int N, n_main;
     int64_t off = 0;
     int n_obs_poly = 0;
-    if (GEN) {
+    {
         // stage the candidate record (and the field's obstacle vertices) with TMA bulk copies
         int f = 0, v0 = 0, nv = 0;
         if (tid == 0) {
@@ -296,9 +354,10 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             bulk_g2s(s.rec, a.recs + cand, sizeof(CandRec), s.bar);
             if (nv > 0) bulk_g2s(s.obs_xy, a.b.obs_verts + 2 * (int64_t)v0, nv * 16, s.bar);
         }
-        // trig tables + polygon starts through the ordinary path meanwhile
+        // trig tables through the ordinary path meanwhile; the generic-point list starts empty
         for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
             ((double *)s.tt)[k] = ((const double *)a.trig)[k];
+        for (int k = tid; k < N_GENERIC; k += T) s.glist[k] = -1;
         mbar_wait_block(s.bar, phase);
         const CandRec &r = *s.rec;
         if (a.b.obs_poly_start) {
@@ -340,76 +399,170 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             }
             return;
         }
-        __syncthreads();
-    } else {
-        off = a.in_offsets[cand];
-        N = (int)(a.in_offsets[cand + 1] - off);
-        n_main = N;
-        if (N > cap && !BIG && a.big_enabled) return;
-        if (N > cap || N == 0) {
-            if (sum && tid == 0) {
-                sum->status = N ? FCPP_CAND_TOO_LARGE : 0;
-                sum->n_main = N;
-                sum->n_head = 0;
-                sum->n_accel_viol = 0;
-                sum->len_main = sum->time_main = sum->time_main_pre = 0.0;
-                sum->max_curvature = sum->max_lateral_accel = sum->max_jump = 0.0;
-            }
-            return;
-        }
     }
+    const CandRec &r = *s.rec;
+    const double W = veh.working_width;
+    TurnModel tm;
+    tm.model = a.b.turn_model;
+    tm.lam = a.b.clothoid_share;
+    const double rr = W / 2;
+    const double r2 = rr * rr;
 
     // ------------------------------------------------------------------------------------
-    // phase 1: points -> shared memory (+ HBM when paths are materialised) + geofence tests
+    // phase 0: per-candidate tables.  Scratch points of the first main pass (+ the first two points of the
+    // second) in the swath frame and of one corner turn; geofence edges; obstacle boxes.
     // ------------------------------------------------------------------------------------
-    int n_bviol = 0, n_oviol = 0;
-    if (GEN) {
-        const CandRec &r = *s.rec;
-        const double W = veh.working_width;
-        // field edges for the D3 test: cross(e, p - v) < -eps*|e|
-        double fax[4], fay[4], fex[4], fey[4], fth[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int k1 = (k + 1) & 3;
-            fax[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k];
-            fay[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k + 1];
-            fex[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1] - fax[k];
-            fey[k] = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1 + 1] - fay[k];
-            fth[k] = -FCPP_GEOFENCE_EPS * sqrt(fex[k] * fex[k] + fey[k] * fey[k]);
+    if (tid < 24) {
+        if (r.P >= 2) {
+            double px, py;
+            main_local_pt(r, *s.tt, tm, W, tid < 22 ? 0 : 1, tid < 22 ? tid : tid - 22, px, py);
+            s.tpts[2 * tid] = px;
+            s.tpts[2 * tid + 1] = py;
         }
-        const double rr = W / 2;
-        const double r2 = rr * rr;
-        TurnModel tm;
-        tm.model = a.b.turn_model;
-        tm.lam = a.b.clothoid_share;
+    } else if (tid >= 32 && tid < 32 + FCPP_CORNER_POINTS) {
+        double px, py;
+        corner_arc_pt(*s.tt, tm, 0.0, 0.0, r.R, 0, tid - 32, px, py);
+        s.tpts[2 * (tid - 8)] = px;  // scratch points 24 .. 38
+        s.tpts[2 * (tid - 8) + 1] = py;
+    } else if (tid >= 64 && tid < 68) {
+        // field edges for the D3 test: cross(e, p - v) < -eps*|e|
+        const int k = tid - 64, k1 = (k + 1) & 3;
+        const double ax = a.b.field_verts[(int64_t)r.field * 8 + 2 * k], ay = a.b.field_verts[(int64_t)r.field * 8 + 2 * k + 1];
+        const double ex = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1] - ax;
+        const double ey = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1 + 1] - ay;
+        s.geo[5 * k] = ax;
+        s.geo[5 * k + 1] = ay;
+        s.geo[5 * k + 2] = ex;
+        s.geo[5 * k + 3] = ey;
+        s.geo[5 * k + 4] = -FCPP_GEOFENCE_EPS * sqrt(ex * ex + ey * ey);
+    } else if (tid >= 96 && tid < 96 + n_obs_poly) {
         // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above
         // any rounding of the exact test) can neither be inside it nor within W/2 of an edge
-        for (int p = tid; p < n_obs_poly; p += T) {
-            double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-            for (int q = s.obs_vs[p]; q < s.obs_vs[p + 1]; ++q) {
-                x0 = fmin(x0, s.obs_xy[2 * q]);
-                x1 = fmax(x1, s.obs_xy[2 * q]);
-                y0 = fmin(y0, s.obs_xy[2 * q + 1]);
-                y1 = fmax(y1, s.obs_xy[2 * q + 1]);
-            }
-            s.obs_bb[4 * p] = x0 - rr - 1e-6;
-            s.obs_bb[4 * p + 1] = y0 - rr - 1e-6;
-            s.obs_bb[4 * p + 2] = x1 + rr + 1e-6;
-            s.obs_bb[4 * p + 3] = y1 + rr + 1e-6;
+        const int p = tid - 96;
+        double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+        for (int q = s.obs_vs[p]; q < s.obs_vs[p + 1]; ++q) {
+            x0 = fmin(x0, s.obs_xy[2 * q]);
+            x1 = fmax(x1, s.obs_xy[2 * q]);
+            y0 = fmin(y0, s.obs_xy[2 * q + 1]);
+            y1 = fmax(y1, s.obs_xy[2 * q + 1]);
         }
-        __syncthreads();
+        s.obs_bb[4 * p] = x0 - rr - 1e-6;
+        s.obs_bb[4 * p + 1] = y0 - rr - 1e-6;
+        s.obs_bb[4 * p + 2] = x1 + rr + 1e-6;
+        s.obs_bb[4 * p + 3] = y1 + rr + 1e-6;
+    }
+    for (int p = 96 + T - 96 + tid; p < 96 + n_obs_poly; p += T) {  // more obstacles than threads 96..T-1: rare
+        const int q0 = p - 96;
+        double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+        for (int q = s.obs_vs[q0]; q < s.obs_vs[q0 + 1]; ++q) {
+            x0 = fmin(x0, s.obs_xy[2 * q]);
+            x1 = fmax(x1, s.obs_xy[2 * q]);
+            y0 = fmin(y0, s.obs_xy[2 * q + 1]);
+            y1 = fmax(y1, s.obs_xy[2 * q + 1]);
+        }
+        s.obs_bb[4 * q0] = x0 - rr - 1e-6;
+        s.obs_bb[4 * q0 + 1] = y0 - rr - 1e-6;
+        s.obs_bb[4 * q0 + 2] = x1 + rr + 1e-6;
+        s.obs_bb[4 * q0 + 3] = y1 + rr + 1e-6;
+    }
+    __syncthreads();
+    {
+        // one thread per table slot
+        int slot = -1;
+        double ds = 0.0, kap = 0.0, v0 = 0.0, v1 = 0.0;
+        if (tid < 22) {
+            if (r.P >= 2) {
+                slot = SLOT_MAIN + tid;
+                const double *p = s.tpts;
+                const int j = tid;
+                const double dx2 = p[2 * (j + 1)] - p[2 * j], dy2 = p[2 * (j + 1) + 1] - p[2 * j + 1];
+                ds = sqrt_z(dx2 * dx2 + dy2 * dy2);
+                // the point before slot 0 is the last turn sample of the previous pass: use pass 1's start (points 21, 22, 23)
+                const int c = (j == 0) ? 22 : j;
+                const double ax = p[2 * (c - 1)], ay = p[2 * (c - 1) + 1], bx = p[2 * c], by = p[2 * c + 1];
+                const double cx = p[2 * (c + 1)], cy = p[2 * (c + 1) + 1];
+                const double d1x = bx - ax, d1y = by - ay, d2x = cx - bx, d2y = cy - by;
+                kap = curvature3(d1x, d1y, sqrt_z(d1x * d1x + d1y * d1y), d2x, d2y, sqrt_z(d2x * d2x + d2y * d2y));
+                v0 = (j < 2) ? veh.max_work_speed_kmh : veh.headland_turn_speed_kmh;
+                v1 = (j == 0 || j == 21) ? veh.max_work_speed_kmh : veh.headland_turn_speed_kmh;
+            }
+        } else if (tid >= 32 && tid < 32 + FCPP_CORNER_POINTS) {
+            const int aI = tid - 32;
+            if (aI >= 1 && aI <= FCPP_CORNER_POINTS - 2) {
+                slot = SLOT_ARC + aI;
+                const double *p = s.tpts + 2 * 24;
+                const double d1x = p[2 * aI] - p[2 * (aI - 1)], d1y = p[2 * aI + 1] - p[2 * (aI - 1) + 1];
+                const double d2x = p[2 * (aI + 1)] - p[2 * aI], d2y = p[2 * (aI + 1) + 1] - p[2 * aI + 1];
+                ds = sqrt_z(d2x * d2x + d2y * d2y);
+                kap = curvature3(d1x, d1y, sqrt_z(d1x * d1x + d1y * d1y), d2x, d2y, ds);
+                v0 = v1 = veh.headland_turn_speed_kmh;
+            }
+        } else if (tid >= 64 && tid < 67) {
+            const int t = tid - 64;
+            if (r.n_rev[t] >= 2) {  // points ex + (m step) d: equally spaced, collinear (mlp3:1214-1216)
+                slot = SLOT_REV + t;
+                const double step = r.rev[t][4] / (r.n_rev[t] - 1);
+                const double sx = step * r.rev[t][2], sy = step * r.rev[t][3];
+                ds = sqrt_z(sx * sx + sy * sy);
+                v0 = v1 = veh.reverse_speed_kmh;
+            }
+        } else if (tid >= 96 && tid < 96 + 4 * r.K) {
+            const int kt = tid - 96, k = kt >> 2, t = kt & 3;
+            const int sc = r.flags & FCPP_FLAG_CORNER_MASK, ci = (sc + t) & 3, ni = (sc + t + 1) & 3;
+            slot = SLOT_STRAIGHT + kt;
+            const double sx = (r.corners[k][ni][0] - r.corners[k][ci][0]) / (FCPP_STRAIGHT_POINTS - 1);
+            const double sy = (r.corners[k][ni][1] - r.corners[k][ci][1]) / (FCPP_STRAIGHT_POINTS - 1);
+            ds = sqrt_z(sx * sx + sy * sy);
+            v0 = v1 = veh.max_headland_speed_kmh;
+        }
+        if (slot >= 0) {
+            const double vl = vlimit(v0, kap, veh);
+            const double vms = div36(vl);
+            Tpl e;
+            e.ds = ds;
+            e.kap = kap;
+            e.vl = vl;
+            e.u = vms * vms;
+            e.tpre = div_z(ds, fmax(div36((v0 + v1) / 2), FCPP_MIN_SPEED_MS));
+            s.tbl[slot] = e;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------
+    // phase 1: points -> HBM (when paths are materialised) + geofence tests; ds / kappa / U of every point of a
+    // congruent piece from the table; the generic points are listed by their fixed ordinal
+    // ------------------------------------------------------------------------------------
+    int n_bviol = 0, n_oviol = 0;
+    double acc_len_m = 0.0, acc_len_h = 0.0, acc_tpre_m = 0.0, acc_tpre_h = 0.0;
+    {
         double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
         for (int i = tid; i < N; i += T) {
             double x, y;
             uint8_t c;
-            gen_point(r, *s.tt, tm, W, i, x, y, c);
-            s.X[i] = x;
-            s.Y[i] = y;
-            s.CLS[i] = c;
+            int tag, gord;
+            gen_point_tag(r, *s.tt, tm, W, i, x, y, c, tag, gord);
             if (gp) gp[i] = make_double2(x, y);
+            s.CLS[i] = (uint8_t)tag;
+            if (gord >= 0) {
+                s.glist[gord] = i;
+            } else {
+                const Tpl e = s.tbl[tag];
+                s.X[i] = e.ds;
+                s.Y[i] = e.kap;
+                s.U[i] = e.u;
+                if (i < n_main) {
+                    acc_len_m += e.ds;
+                    acc_tpre_m += e.tpre;
+                } else {
+                    acc_len_h += e.ds;
+                    acc_tpre_h += e.tpre;
+                }
+            }
             bool outb = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) outb = outb || (fex[k] * (y - fay[k]) - fey[k] * (x - fax[k]) < fth[k]);
+            for (int k = 0; k < 4; ++k)
+                outb = outb || (s.geo[5 * k + 2] * (y - s.geo[5 * k + 1]) - s.geo[5 * k + 3] * (x - s.geo[5 * k]) < s.geo[5 * k + 4]);
             n_bviol += outb;
             bool hit = false;
             for (int p = 0; p < n_obs_poly && !hit; ++p) {
@@ -439,96 +592,58 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             }
             n_oviol += hit;
         }
-    } else {
-        const double2 *gp = reinterpret_cast<const double2 *>(a.in_path) + off;
-        for (int i = tid; i < N; i += T) {
-            const double2 p = gp[i];
-            s.X[i] = p.x;
-            s.Y[i] = p.y;
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------------------------
+    // phase 2: the generic points (first / last point of every piece) from their coordinates: mlp3:490-504
+    // ------------------------------------------------------------------------------------
+    const int n_gslots = 2 + GEN_PER_LOOP * r.K;
+    for (int g = tid; g < n_gslots; g += T) {
+        const int i = s.glist[g];
+        if (i < 0) continue;
+        // the point and its two neighbours, regenerated (one loop body: the generator is large)
+        double P3[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        uint8_t C3[3] = {0, 0, 0};
+#pragma unroll 1
+        for (int d = 0; d < 3; ++d) {
+            const int q = i - 1 + d;
+            if (q >= 0 && q < N) gen_point(r, *s.tt, tm, W, q, P3[d][0], P3[d][1], C3[d]);
+        }
+        const double px = P3[0][0], py = P3[0][1], cx = P3[1][0], cy = P3[1][1], nx = P3[2][0], ny = P3[2][1];
+        const uint8_t c0 = C3[1], c1 = C3[2];
+        double ds1 = 0.0, ds2 = 0.0, dx1 = cx - px, dy1 = cy - py, dx2 = nx - cx, dy2 = ny - cy;
+        if (i > 0) ds1 = sqrt_z(dx1 * dx1 + dy1 * dy1);
+        if (i + 1 < N) ds2 = sqrt_z(dx2 * dx2 + dy2 * dy2);
+        double kap = 0.0;
+        if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
+        const double v0 = cls_speed(veh, c0);
+        const double vl = vlimit(v0, kap, veh);
+        const double vms = div36(vl);
+        s.X[i] = ds2;
+        s.Y[i] = kap;
+        s.U[i] = vms * vms;
+        s.gvl[g] = vl;
+        // per-layer length and pre-adjustment time (mlp3:616-617, :882-883)
+        if (i + 1 < N && i != n_main - 1) {
+            const double t = div_z(ds2, fmax(div36((v0 + cls_speed(veh, c1)) / 2), FCPP_MIN_SPEED_MS));
+            if (i < n_main) {
+                acc_len_m += ds2;
+                acc_tpre_m += t;
+            } else {
+                acc_len_h += ds2;
+                acc_tpre_h += t;
+            }
         }
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------------------------
-    // phase 2: per-thread contiguous chunk: ds_i -> X[i], kappa_i -> Y[i], U_i=(vlim/3.6)^2
-    // ------------------------------------------------------------------------------------
     const int chunk = (N + T - 1) / T;
     const int cs = min(N, tid * chunk);
     const int ce = min(N, cs + chunk);
-    double hpx = 0.0, hpy = 0.0, hnx = 0.0, hny = 0.0;
-    if (cs < ce) {
-        if (cs > 0) {
-            hpx = s.X[cs - 1];
-            hpy = s.Y[cs - 1];
-        }
-        if (ce < N) {
-            hnx = s.X[ce];
-            hny = s.Y[ce];
-        }
-    }
-    __syncthreads();
-    double acc_len_m = 0.0, acc_len_h = 0.0, acc_tpre_m = 0.0, acc_tpre_h = 0.0;
-    if (cs < ce) {
-        double px = hpx, py = hpy;
-        double cx = s.X[cs], cy = s.Y[cs];
-        double dx1 = cx - px, dy1 = cy - py;
-        double ds1 = (cs > 0) ? sqrt_z(dx1 * dx1 + dy1 * dy1) : 0.0;
-        for (int i = cs; i < ce; ++i) {
-            double nx, ny;
-            if (i + 1 < ce) {
-                nx = s.X[i + 1];
-                ny = s.Y[i + 1];
-            } else {
-                nx = hnx;
-                ny = hny;
-            }
-            double dx2 = 0.0, dy2 = 0.0, ds2 = 0.0;
-            if (i + 1 < N) {
-                dx2 = nx - cx;
-                dy2 = ny - cy;
-                ds2 = sqrt_z(dx2 * dx2 + dy2 * dy2);
-            }
-            double kap = 0.0;
-            if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
-            double v0, v1 = 0.0;
-            if (GEN) {
-                v0 = cls_speed(veh, s.CLS[i]);
-                if (i + 1 < N) v1 = cls_speed(veh, s.CLS[i + 1]);
-            } else {
-                v0 = a.in_speeds[off + i];
-                if (i + 1 < N) v1 = a.in_speeds[off + i + 1];
-            }
-            const double vl = (GEN || a.do_speed_plan) ? vlimit(v0, kap, veh) : v0;
-            const double vms = div36(vl);
-            s.X[i] = ds2;
-            s.Y[i] = kap;
-            s.U[i] = vms * vms;
-            // per-layer length and pre-adjustment time (mlp3:616-617, :882-883)
-            if (i + 1 < N && i != n_main - 1) {
-                const double t = div_z(ds2, fmax(div36((v0 + v1) / 2), FCPP_MIN_SPEED_MS));
-                if (i < n_main) {
-                    acc_len_m += ds2;
-                    acc_tpre_m += t;
-                } else {
-                    acc_len_h += ds2;
-                    acc_tpre_h += t;
-                }
-            }
-            dx1 = dx2;
-            dy1 = dy2;
-            ds1 = ds2;
-            cx = nx;
-            cy = ny;
-        }
-    }
-    __syncthreads();
-
-    const bool do_scan = GEN || a.do_speed_plan;
+    const bool do_scan = N >= 3;
     const double two_a = 2 * veh.max_longitudinal_accel;
-    if (do_scan && N >= 3) {
-        // --------------------------------------------------------------------------------
+    if (do_scan) {
         // phase 3: forward pass  f_i = min(U_i, f_{i-1} + 2a*ds_{i-1})   (mlp3:558-571)
-        // --------------------------------------------------------------------------------
         {
             MP agg;
             agg.C = 0.0;
@@ -548,11 +663,8 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
             }
         }
         __syncthreads();
-        // --------------------------------------------------------------------------------
-        // phase 4: backward pass  b_i = min(f_i, b_{i+1} + 2a*ds_i)      (mlp3:574-587)
-        // run as a forward scan over the reversed sequence: thread order is reversed by
-        // giving thread tid the chunk of thread T-1-tid
-        // --------------------------------------------------------------------------------
+        // phase 4: backward pass  b_i = min(f_i, b_{i+1} + 2a*ds_i)      (mlp3:574-587), as a forward scan over the
+        // reversed sequence: thread tid takes the chunk of thread T-1-tid
         {
             const int rt = T - 1 - tid;
             const int rs = min(N, rt * chunk);
@@ -578,28 +690,238 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
     }
 
     // ------------------------------------------------------------------------------------
-    // phase 5a: final speeds (km/h) -> U[i] and HBM; lateral-acceleration validation
+    // phase 5a: final speeds (km/h) -> U[i] and HBM; lateral-acceleration validation (mlp3:1383-1410)
     // ------------------------------------------------------------------------------------
     int n_aviol = 0;
     double mx[3] = {0.0, 0.0, 0.0};  // max kappa, max a_lat, max |kappa jump|
-    {
-        double *gs = nullptr, *gk = nullptr;
-        if (GEN) {
-            gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
-            gk = a.out.curvature ? a.out.curvature + off : nullptr;
-        } else {
-            gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
-            gk = a.out.curvature ? a.out.curvature + off : nullptr;
+    double *gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
+    double *gk = a.out.curvature ? a.out.curvature + off : nullptr;
+    auto finish_point = [&](bool act, int i, double u_lim, double vl) {
+        const double kap = act ? s.Y[i] : 0.0;
+        const double u = act ? s.U[i] : 0.0;
+        const double v = do_scan ? final_speed(act, u, u_lim, vl) : vl;
+        if (!act) return;
+        if (gs) gs[i] = v;
+        if (gk) gk[i] = kap;
+        if (i >= 1 && i + 1 < N) {
+            const double vm = div36(v);
+            const double alat = vm * vm * kap;  // mlp3:1389-1390
+            n_aviol += (alat > veh.max_lateral_accel);
+            mx[0] = fmax(mx[0], kap);
+            mx[1] = fmax(mx[1], alat);
+            if (i + 2 < N) mx[2] = fmax(mx[2], fabs(s.Y[i + 1] - kap));
         }
+        s.U[i] = v;  // safe: U[i] is read only by its owner in this phase
+    };
+    for (int base = 0; base < N; base += T) {  // warp-uniform trip count (final_speed votes)
+        const int i = base + tid;
+        const int tag = (i < N) ? s.CLS[i] : TAG_GENERIC;
+        const bool act = tag < TAG_GENERIC;
+        double u_lim = 0.0, vl = 0.0;
+        if (act) {
+            u_lim = s.tbl[tag].u;
+            vl = s.tbl[tag].vl;
+        }
+        finish_point(act, i, u_lim, vl);
+    }
+    for (int base = 0; base < n_gslots; base += T) {
+        const int g = base + tid;
+        const int i = (g < n_gslots) ? s.glist[g] : -1;
+        const bool act = i >= 0;
+        double vl = 0.0, u_lim = 0.0;
+        if (act) {
+            vl = s.gvl[g];
+            const double vms = div36(vl);
+            u_lim = vms * vms;
+        }
+        finish_point(act, i, u_lim, vl);
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------------------------
+    // phase 5b: work time with the adjusted speeds (mlp3:423-431, :1298-1311)
+    // ------------------------------------------------------------------------------------
+    double acc_t_m = 0.0, acc_t_h = 0.0;
+    for (int i = tid; i + 1 < N; i += T) {
+        if (i == n_main - 1) continue;
+        const double t = div_pos(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
+        if (i < n_main)
+            acc_t_m += t;
+        else
+            acc_t_h += t;
+    }
+    double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
+                      acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
+    block_reduce<9, false, T / 32>(sums, s.scratch);
+    block_reduce<3, true, T / 32>(mx, s.scratch);
+    if (tid == 0 && sum) {
+        sum->status = 0;
+        sum->len_main = sums[0];
+        sum->len_head = sums[1];
+        sum->time_main_pre = sums[2];
+        sum->time_head_pre = sums[3];
+        sum->time_main = sums[4];
+        sum->time_head = sums[5];
+        sum->n_accel_viol = (int)sums[6];
+        sum->n_boundary_viol = (int)sums[7];
+        sum->n_obstacle_viol = (int)sums[8];
+        sum->max_curvature = mx[0];
+        sum->max_lateral_accel = mx[1];
+        sum->max_jump = mx[2];
+        sum->reserved = 0.0;
+        if (!a.b.do_coverage) {
+            sum->cov_cells = sum->cov_total = 0;
+            for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
+        }
+    }
+}
+
+// One caller-supplied path (A7 / A8 / A13 of the drop-in API): every point from its coordinates.
+template <bool BIG, int T>
+__device__ __forceinline__ void plan_body_path(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap)
+{
+    const int tid = threadIdx.x;
+    const fcpp_vehicle &veh = a.veh;
+    fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
+    const int64_t off = a.in_offsets[cand];
+    const int N = (int)(a.in_offsets[cand + 1] - off);
+    const int n_main = N;
+    if (N > cap && !BIG && a.big_enabled) return;
+    if (N > cap || N == 0) {
+        if (sum && tid == 0) {
+            sum->status = N ? FCPP_CAND_TOO_LARGE : 0;
+            sum->n_main = N;
+            sum->n_head = 0;
+            sum->n_accel_viol = 0;
+            sum->len_main = sum->time_main = sum->time_main_pre = 0.0;
+            sum->max_curvature = sum->max_lateral_accel = sum->max_jump = 0.0;
+        }
+        return;
+    }
+    {
+        const double2 *gp = reinterpret_cast<const double2 *>(a.in_path) + off;
+        for (int i = tid; i < N; i += T) {
+            const double2 p = gp[i];
+            s.X[i] = p.x;
+            s.Y[i] = p.y;
+        }
+    }
+    __syncthreads();
+
+    // per-thread contiguous chunk: ds_i -> X[i], kappa_i -> Y[i], U_i = (vlim/3.6)^2
+    const int chunk = (N + T - 1) / T;
+    const int cs = min(N, tid * chunk);
+    const int ce = min(N, cs + chunk);
+    double hpx = 0.0, hpy = 0.0, hnx = 0.0, hny = 0.0;
+    if (cs < ce) {
+        if (cs > 0) {
+            hpx = s.X[cs - 1];
+            hpy = s.Y[cs - 1];
+        }
+        if (ce < N) {
+            hnx = s.X[ce];
+            hny = s.Y[ce];
+        }
+    }
+    __syncthreads();
+    double acc_len_m = 0.0, acc_tpre_m = 0.0;
+    if (cs < ce) {
+        double px = hpx, py = hpy;
+        double cx = s.X[cs], cy = s.Y[cs];
+        double dx1 = cx - px, dy1 = cy - py;
+        double ds1 = (cs > 0) ? sqrt_z(dx1 * dx1 + dy1 * dy1) : 0.0;
+        for (int i = cs; i < ce; ++i) {
+            double nx, ny;
+            if (i + 1 < ce) {
+                nx = s.X[i + 1];
+                ny = s.Y[i + 1];
+            } else {
+                nx = hnx;
+                ny = hny;
+            }
+            double dx2 = 0.0, dy2 = 0.0, ds2 = 0.0;
+            if (i + 1 < N) {
+                dx2 = nx - cx;
+                dy2 = ny - cy;
+                ds2 = sqrt_z(dx2 * dx2 + dy2 * dy2);
+            }
+            double kap = 0.0;
+            if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
+            const double v0 = a.in_speeds[off + i];
+            const double v1 = (i + 1 < N) ? a.in_speeds[off + i + 1] : 0.0;
+            const double vl = a.do_speed_plan ? vlimit(v0, kap, veh) : v0;
+            const double vms = div36(vl);
+            s.X[i] = ds2;
+            s.Y[i] = kap;
+            s.U[i] = vms * vms;
+            if (i + 1 < N) {  // length and pre-adjustment time (mlp3:1290-1311)
+                acc_len_m += ds2;
+                acc_tpre_m += div_z(ds2, fmax(div36((v0 + v1) / 2), FCPP_MIN_SPEED_MS));
+            }
+            dx1 = dx2;
+            dy1 = dy2;
+            ds1 = ds2;
+            cx = nx;
+            cy = ny;
+        }
+    }
+    __syncthreads();
+
+    const bool do_scan = a.do_speed_plan && N >= 3;
+    const double two_a = 2 * veh.max_longitudinal_accel;
+    if (do_scan) {
+        {
+            MP agg;
+            agg.C = 0.0;
+            agg.M = INFINITY;
+            for (int i = cs; i < ce; ++i) {
+                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
+                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                agg.M = fmin(s.U[i], agg.M + c);
+                agg.C = agg.C + c;
+            }
+            double carry = mp_block_exclusive(agg, s.scratch);
+            for (int i = cs; i < ce; ++i) {
+                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
+                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                carry = fmin(s.U[i], carry + c);
+                s.U[i] = carry;
+            }
+        }
+        __syncthreads();
+        {
+            const int rt = T - 1 - tid;
+            const int rs = min(N, rt * chunk);
+            const int re = min(N, rs + chunk);
+            MP agg;
+            agg.C = 0.0;
+            agg.M = INFINITY;
+            for (int i = re - 1; i >= rs; --i) {
+                const double dsn = s.X[i];
+                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                agg.M = fmin(s.U[i], agg.M + c);
+                agg.C = agg.C + c;
+            }
+            double carry = mp_block_exclusive(agg, s.scratch);
+            for (int i = re - 1; i >= rs; --i) {
+                const double dsn = s.X[i];
+                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                carry = fmin(s.U[i], carry + c);
+                s.U[i] = carry;
+            }
+        }
+        __syncthreads();
+    }
+
+    int n_aviol = 0;
+    double mx[3] = {0.0, 0.0, 0.0};
+    {
+        double *gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
+        double *gk = a.out.curvature ? a.out.curvature + off : nullptr;
         for (int i = tid; i < N; i += T) {
             const double kap = s.Y[i];
-            double v0;
-            if (GEN)
-                v0 = cls_speed(veh, s.CLS[i]);
-            else
-                v0 = a.in_speeds[off + i];
+            const double v0 = a.in_speeds[off + i];
             double v;
-            if (do_scan && N >= 3) {
+            if (do_scan) {
                 const double vl = vlimit(v0, kap, veh);
                 const double vms = div36(vl);
                 const double u = s.U[i];
@@ -617,52 +939,48 @@ __device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, cons
                 mx[1] = fmax(mx[1], alat);
                 if (i + 2 < N) mx[2] = fmax(mx[2], fabs(s.Y[i + 1] - kap));
             }
-            s.U[i] = v;  // safe: U[i] is read only by its owner in this loop
+            s.U[i] = v;
         }
     }
     __syncthreads();
-    // ------------------------------------------------------------------------------------
-    // phase 5b: work time with the adjusted speeds (mlp3:423-431, :1298-1311)
-    // ------------------------------------------------------------------------------------
-    double acc_t_m = 0.0, acc_t_h = 0.0;
-    for (int i = tid; i + 1 < N; i += T) {
-        if (i == n_main - 1) continue;
-        const double t = div_z(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
-        if (i < n_main)
-            acc_t_m += t;
-        else
-            acc_t_h += t;
-    }
-    double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
-                      acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
-    block_reduce<9, false, T / 32>(sums, s.scratch);
+    double acc_t_m = 0.0;
+    for (int i = tid; i + 1 < N; i += T)
+        acc_t_m += div_z(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
+    double sums[4] = {acc_len_m, acc_tpre_m, acc_t_m, (double)n_aviol};
+    block_reduce<4, false, T / 32>(sums, s.scratch);
     block_reduce<3, true, T / 32>(mx, s.scratch);
     if (tid == 0 && sum) {
         sum->status = 0;
-        if (!GEN) {
-            sum->n_passes = 0;
-            sum->n_loops = 0;
-            sum->n_main = N;
-            sum->n_head = 0;
-        }
+        sum->n_passes = 0;
+        sum->n_loops = 0;
+        sum->n_main = n_main;
+        sum->n_head = 0;
         sum->len_main = sums[0];
-        sum->len_head = sums[1];
-        sum->time_main_pre = sums[2];
-        sum->time_head_pre = sums[3];
-        sum->time_main = sums[4];
-        sum->time_head = sums[5];
-        sum->n_accel_viol = (int)sums[6];
-        sum->n_boundary_viol = (int)sums[7];
-        sum->n_obstacle_viol = (int)sums[8];
+        sum->len_head = 0.0;
+        sum->time_main_pre = sums[1];
+        sum->time_head_pre = 0.0;
+        sum->time_main = sums[2];
+        sum->time_head = 0.0;
+        sum->n_accel_viol = (int)sums[3];
+        sum->n_boundary_viol = 0;
+        sum->n_obstacle_viol = 0;
         sum->max_curvature = mx[0];
         sum->max_lateral_accel = mx[1];
         sum->max_jump = mx[2];
         sum->reserved = 0.0;
-        if (!GEN || !a.b.do_coverage) {
-            sum->cov_cells = sum->cov_total = 0;
-            for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
-        }
+        sum->cov_cells = sum->cov_total = 0;
+        for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
     }
+}
+
+template <bool GEN, bool BIG, int T>
+__device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
+                                          const uint32_t phase)
+{
+    if (GEN)
+        plan_body_gen<BIG, T>(a, s, cand, cap, phase);
+    else
+        plan_body_path<BIG, T>(a, s, cand, cap);
 }
 
 #ifndef FCPP_PLAN_MIN_CTAS
