@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCPP_LIB selects another build of the same library (A/B timing of kernel variants); there is still
 # no fallback: the file must exist and export the ABI
 LIB_PATH = os.environ.get("FCPP_LIB") or os.path.join(_HERE, "libfcpp.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_CORNER_MASK = 3
 FLAG_REVERSE_ORDER = 4
@@ -77,6 +77,7 @@ class Outputs(C.Structure):
         ("path_xy", C.c_void_p),
         ("speeds_kmh", C.c_void_p),
         ("curvature", C.c_void_p),
+        ("path_capacity", C.c_int64),
     ]
 
 

@@ -271,6 +271,17 @@ __device__ inline void centroid4(const double (*v)[2], double &cx, double &cy)
     cy = oy + sy / (3.0 * a2);
 }
 
+// x / y for a compile-time constant y, correctly rounded, in three instructions instead of the generic FP64
+// division and its ~70-instruction slow path for a zero numerator (Markstein: with r = RN(1/y) and q0 = RN(x r),
+// RN(q0 + r RN(x - y q0)) = RN(x / y) whenever the significand of y is not all ones; checked against the division
+// on 1.5e9 random doubles for y = 3.6 and y = 19).  The result is bit-identical to `x / y`.
+__device__ __forceinline__ double div_const(double x, double y, double r /* = 1.0 / y */)
+{
+    if (!(fabs(x) < 1e150)) return x / y;  // inf / nan / absurd magnitudes: the generic path
+    const double q0 = x * r;
+    return fma(fma(-q0, y, x), r, q0);
+}
+
 // mlp3:265-284
 __device__ __forceinline__ void rotate_pt(double px, double py, double ca, double sa, double cx, double cy,
                                           double &ox, double &oy)
@@ -405,17 +416,26 @@ __device__ __forceinline__ int64_t qfix(double x) { return __double2ll_rn(x * FC
 // kernel takes the segment length, the curvature and the curvature speed limit of such a point from a
 // per-candidate table instead of recomputing sqrt / atan2 / divisions for every point; the first and
 // last point of every piece (where two pieces meet) are GENERIC and are evaluated from the coordinates.
-constexpr int SLOT_MAIN = 0;       // + j: position in a main pass (0, 1 = swath ends, 2 + a = turn sample a)
+constexpr int SLOT_CHAIN = 0;      // + c: position in a regular main chain (0 .. 19 = turn samples, 20, 21 = the next swath's ends)
 constexpr int SLOT_ARC = 22;       // + a: corner-turn sample a (1 .. 13)
 constexpr int SLOT_REV = 37;       // + t: interior of the reverse fill after turn t of loop 0
 constexpr int SLOT_STRAIGHT = 40;  // + 4 k + t: interior of straight t of headland loop k
 constexpr int N_SLOTS = SLOT_STRAIGHT + 4 * FCPP_MAX_LOOPS;
 constexpr int TAG_GENERIC = 252;   // + speed class
-// generic points get a fixed ordinal (deterministic summation order): 0, 1 = first / last main point, then 21
-// per headland loop: 0 = loop start, 1 + 2 t / 2 + 2 t = ends of straight t, 9 + 2 t / 10 + 2 t = ends of turn t,
-// 15 + 2 t / 16 + 2 t = ends of reverse fill t
+// The main work is a sequence of CHAINS separated by zero-length segments (a turn starts on the swath end it
+// follows, mlp3:773-778, and the acceleration passes do not cross a zero-length segment, mlp3:560, :576): the
+// first chain is the first swath, every further chain is one turn (20 samples) + the next swath (2 ends) = 22
+// points.  All chains but the first and the last are congruent — same lengths, curvatures, limits, hence the same
+// speed profile — and are evaluated ONCE per candidate (fcpp_plan.cu); only the first 2 and the last 22 main
+// points are staged point by point together with the headland.
+constexpr int CHAIN_POINTS = 2 + FCPP_UTURN_POINTS;
+constexpr int MAIN_STAGED = 2 + CHAIN_POINTS;
+__host__ __device__ __forceinline__ int main_skip(int n_main) { return n_main > MAIN_STAGED ? n_main - MAIN_STAGED : 0; }
+// generic points (evaluated from their coordinates) get a fixed ordinal (deterministic summation order): the staged
+// main points first, then 21 per headland loop: 0 = loop start, 1 + 2 t / 2 + 2 t = ends of straight t,
+// 9 + 2 t / 10 + 2 t = ends of turn t, 15 + 2 t / 16 + 2 t = ends of reverse fill t
 constexpr int GEN_PER_LOOP = 21;
-constexpr int N_GENERIC = 2 + GEN_PER_LOOP * FCPP_MAX_LOOPS;
+constexpr int N_GENERIC = MAIN_STAGED + GEN_PER_LOOP * FCPP_MAX_LOOPS;
 
 // main-work point (visit index idx, position j in the pass) in the swath frame, before the rotate-back
 __device__ __forceinline__ void main_local_pt(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W,
@@ -465,11 +485,8 @@ __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables
             x = px;
             y = py;
         }
-        tag = SLOT_MAIN + j;
-        if (i == 0 || i == r.n_main - 1) {
-            tag = TAG_GENERIC + cls;
-            gord = (i == 0) ? 0 : 1;
-        }
+        tag = TAG_GENERIC + cls;  // staged main points (the first 2 and the last 22) are all generic
+        gord = i < 2 ? i : i - main_skip(r.n_main);
         return;
     }
     // ---- headland (mlp3:943-1011) ----
@@ -485,7 +502,7 @@ __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables
         m = hI - (k - 1) * FCPP_POINTS_PER_LOOP;
     }
     const int sc = r.flags & FCPP_FLAG_CORNER_MASK;
-    const int g0 = 2 + GEN_PER_LOOP * k;
+    const int g0 = MAIN_STAGED + GEN_PER_LOOP * k;
     if (m == 0) {  // mlp3:978-980
         x = r.corners[k][sc][0];
         y = r.corners[k][sc][1];
@@ -505,8 +522,10 @@ __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables
                 x = bx;
                 y = by;
             } else {
-                const double sx = (bx - ax) / (FCPP_STRAIGHT_POINTS - 1);
-                const double sy = (by - ay) / (FCPP_STRAIGHT_POINTS - 1);
+                // np.linspace: step = delta / 19 (an axis-aligned straight has a zero delta: no slow path here)
+                constexpr double DIV = FCPP_STRAIGHT_POINTS - 1;
+                const double sx = div_const(bx - ax, DIV, 1.0 / DIV);
+                const double sy = div_const(by - ay, DIV, 1.0 / DIV);
                 x = m * sx + ax;
                 y = m * sy + ay;
             }

@@ -11,12 +11,14 @@
 //   A9  geofence / obstacle point tests              D3 (no reference code; README.md:24,200)
 //   A13 path length / work time                      mlp3:1290-1311
 //
-// GEN = true (plan_body_gen): the plan is generated; the segment length, curvature and curvature speed limit of
-// every point inside a congruent piece (main passes, corner turns, straights, reverse fills — fcpp_internal.cuh)
-// come from a per-candidate table of ~100 entries, only the points where two pieces meet (~3 % of a plan) are
-// evaluated from their coordinates (sqrt, atan2, divisions).
-// GEN = false (plan_body_path): A7/A8/A13 on caller-supplied paths (verify_curvature_constraints(path, speeds)
-// of the drop-in API), every point evaluated from the coordinates.
+// plan_gen_kernel: the plan is generated.  A plan is made of congruent pieces (fcpp_internal.cuh): the main work is a
+// sequence of 22-point chains (turn + next swath) separated by zero-length segments that the acceleration passes do
+// not cross, all but the first and the last congruent — they are speed-planned and validated ONCE per candidate and
+// their points only generated, tested against the geofence / obstacles and written; the headland's straights,
+// corner turns and reverse fills take segment length, curvature and speed limit from a per-candidate table; only
+// the points where two pieces meet (~5 % of a plan) are evaluated from their coordinates (sqrt, atan2, divisions).
+// path_kernel / path_big_kernel: A7/A8/A13 on caller-supplied paths (verify_curvature_constraints(path, speeds) of
+// the drop-in API), every point evaluated from the coordinates.
 #include "fcpp_internal.cuh"
 
 namespace {
@@ -36,7 +38,7 @@ struct PlanArgs {
     const int64_t *in_offsets;
     int do_speed_plan;
     // both
-    int ncap;          // smem capacity in points
+    int ncap;          // smem capacity in (staged) points
     int nmin;          // this launch handles nmin < N <= ncap (tiers by plan length, see launch_tiers)
     int defer;         // 1: a later launch with a larger staging handles N > ncap
     int obs_cap_verts; // smem capacity for obstacle vertices
@@ -56,81 +58,29 @@ struct Tpl {
 };
 constexpr int TPL_PTS = 48;  // scratch points of the table set-up: 24 main + 15 turn samples
 
+// staging of the caller-supplied-path kernels: x -> ds, y -> kappa, u per point + reduction scratch
 struct Smem {
     double *X, *Y, *U;
-    uint8_t *CLS;      // GEN: the structure tag of the point (fcpp_internal.cuh)
-    CandRec *rec;
-    TrigTables *tt;
-    double *obs_xy;    // [obs_cap_verts][2]
-    int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
-    double *obs_bb;    // [obs_cap_polys][4] bbox of each obstacle grown by W/2 + 1e-6 (early reject)
     double *scratch;   // [SCRATCH]
-    Tpl *tbl;          // [N_SLOTS]
-    double *tpts;      // [TPL_PTS][2]
-    double *geo;       // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
-    double *gvl;       // [N_GENERIC] curvature-limited speed of the generic points
-    int32_t *glist;    // [N_GENERIC] point index of generic ordinal g (-1: none)
-    uint64_t *bar;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 constexpr int SCRATCH = 320;  // block reductions: 9 values x 32 warps
-__host__ __device__ inline size_t plan_smem_bytes(int ncap, int obs_verts, int obs_polys)
+__host__ __device__ inline size_t plan_smem_bytes(int ncap)
 {
-    size_t s = 0;
-    s += align16(sizeof(double) * ncap) * 3;
-    s += align16(ncap);
-    s += align16(sizeof(CandRec));
-    s += align16(sizeof(TrigTables));
-    s += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
-    s += align16(sizeof(int32_t) * (obs_polys + 1));
-    s += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
-    s += align16(sizeof(double) * SCRATCH);
-    s += align16(sizeof(Tpl) * N_SLOTS);
-    s += align16(sizeof(double) * 2 * TPL_PTS);
-    s += align16(sizeof(double) * 20);
-    s += align16(sizeof(double) * N_GENERIC);
-    s += align16(sizeof(int32_t) * N_GENERIC);
-    s += 16;
-    return s;
+    return 3 * align16(sizeof(double) * ncap) + align16(sizeof(double) * SCRATCH);
 }
 
-__device__ inline Smem carve(unsigned char *base, int ncap, int obs_verts, int obs_polys)
+__device__ inline Smem carve(unsigned char *base, int ncap)
 {
     Smem s;
-    size_t o = 0;
-    s.X = (double *)(base + o);
-    o += align16(sizeof(double) * ncap);
-    s.Y = (double *)(base + o);
-    o += align16(sizeof(double) * ncap);
-    s.U = (double *)(base + o);
-    o += align16(sizeof(double) * ncap);
-    s.CLS = (uint8_t *)(base + o);
-    o += align16(ncap);
-    s.rec = (CandRec *)(base + o);
-    o += align16(sizeof(CandRec));
-    s.tt = (TrigTables *)(base + o);
-    o += align16(sizeof(TrigTables));
-    s.obs_xy = (double *)(base + o);
-    o += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
-    s.obs_vs = (int32_t *)(base + o);
-    o += align16(sizeof(int32_t) * (obs_polys + 1));
-    s.obs_bb = (double *)(base + o);
-    o += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
-    s.scratch = (double *)(base + o);
-    o += align16(sizeof(double) * SCRATCH);
-    s.tbl = (Tpl *)(base + o);
-    o += align16(sizeof(Tpl) * N_SLOTS);
-    s.tpts = (double *)(base + o);
-    o += align16(sizeof(double) * 2 * TPL_PTS);
-    s.geo = (double *)(base + o);
-    o += align16(sizeof(double) * 20);
-    s.gvl = (double *)(base + o);
-    o += align16(sizeof(double) * N_GENERIC);
-    s.glist = (int32_t *)(base + o);
-    o += align16(sizeof(int32_t) * N_GENERIC);
-    s.bar = (uint64_t *)(base + o);
+    const size_t arr = align16(sizeof(double) * ncap);
+    s.scratch = (double *)base;
+    base += align16(sizeof(double) * SCRATCH);
+    s.X = (double *)base;
+    s.Y = (double *)(base + arr);
+    s.U = (double *)(base + 2 * arr);
     return s;
 }
 
@@ -297,6 +247,61 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
     return v0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GEN: one generated plan per CTA
+// ---------------------------------------------------------------------------------------------
+// shared memory of the generated-plan kernel: fixed part (compile-time offsets) + obstacle tables + the staging of
+// the `ncap` staged points (first 2 + last 22 main points + headland): ds, kappa, u (FP64) and the structure tag
+struct GenFixed {
+    CandRec rec;
+    TrigTables tt;
+    Tpl tbl[N_SLOTS];
+    double tpts[2 * TPL_PTS];
+    double geo[20];              // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
+    double gvl[N_GENERIC];       // curvature-limited speed of the generic points
+    double scratch[SCRATCH];
+    double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
+    double chain_sum[8];           // per regular chain: length, time (initial speeds), time (final speeds),
+                                   // accel violations, max kappa, max a_lat, max kappa jump
+    int32_t glist[N_GENERIC];    // point index of generic ordinal g (-1: none)
+    uint64_t bar;
+};
+struct GenSmem {
+    GenFixed *f;
+    double *obs_xy;    // [obs_cap_verts][2]
+    double *obs_bb;    // [obs_cap_polys][4] bbox of each obstacle grown by W/2 + 1e-6 (early reject)
+    int32_t *obs_vs;   // [obs_cap_polys + 1], relative to the field's first vertex
+    double *X, *Y, *U;
+    uint8_t *TAG;
+};
+__host__ __device__ inline size_t gen_smem_bytes(int ncap, int obs_verts, int obs_polys)
+{
+    size_t s = align16(sizeof(GenFixed));
+    s += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
+    s += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
+    s += align16(sizeof(int32_t) * (obs_polys + 1));
+    s += 3 * align16(sizeof(double) * ncap) + align16(ncap);
+    return s;
+}
+__device__ __forceinline__ GenSmem gen_carve(unsigned char *base, int ncap, int obs_verts, int obs_polys)
+{
+    GenSmem s;
+    s.f = reinterpret_cast<GenFixed *>(base);
+    size_t o = align16(sizeof(GenFixed));
+    s.obs_xy = (double *)(base + o);
+    o += align16(sizeof(double) * 2 * (obs_verts > 0 ? obs_verts : 1));
+    s.obs_bb = (double *)(base + o);
+    o += align16(sizeof(double) * 4 * (obs_polys > 0 ? obs_polys : 1));
+    s.obs_vs = (int32_t *)(base + o);
+    o += align16(sizeof(int32_t) * (obs_polys + 1));
+    const size_t arr = align16(sizeof(double) * ncap);
+    s.X = (double *)(base + o);
+    s.Y = (double *)(base + o + arr);
+    s.U = (double *)(base + o + 2 * arr);
+    s.TAG = (uint8_t *)(base + o + 3 * arr);
+    return s;
+}
+
 // a / b for a finite a >= 0 and a normal b > 0 (speeds >= 0.1 m/s): reciprocal seed + two Newton steps + one
 // residual correction — correctly rounded in all but the rarest cases (the sums it feeds are compared at 1e-9),
 // a third of the instructions of the generic division and no slow path
@@ -324,66 +329,114 @@ __device__ __forceinline__ double final_speed(bool act, double u, double u_lim, 
     return v;
 }
 
-// One generated plan.  `s` points at the staging arrays (shared memory in plan_kernel, an HBM/L2 scratch slice
-// in plan_big_kernel), `cap` is their capacity.
-template <bool BIG, int T>
-__device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
-                                              const uint32_t phase)
+// geofence (D3) and obstacle (D2/D3) point tests of one generated point
+__device__ __forceinline__ void point_tests(const GenSmem &s, int n_obs_poly, double r2, double x, double y, int &n_bviol,
+                                            int &n_oviol)
 {
-    const int tid = threadIdx.x;
+    const double *geo = s.f->geo;
+    bool outb = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        outb = outb || (geo[5 * k + 2] * (y - geo[5 * k + 1]) - geo[5 * k + 3] * (x - geo[5 * k]) < geo[5 * k + 4]);
+    n_bviol += outb;
+    bool hit = false;
+    for (int p = 0; p < n_obs_poly && !hit; ++p) {
+        if (x < s.obs_bb[4 * p] || y < s.obs_bb[4 * p + 1] || x > s.obs_bb[4 * p + 2] || y > s.obs_bb[4 * p + 3])
+            continue;
+        const int vs = s.obs_vs[p], ve = s.obs_vs[p + 1];
+        bool inside = false;
+        for (int q = vs; q < ve; ++q) {
+            const int q1 = (q + 1 < ve) ? q + 1 : vs;
+            const double ax = s.obs_xy[2 * q], ay = s.obs_xy[2 * q + 1];
+            const double bx = s.obs_xy[2 * q1], by = s.obs_xy[2 * q1 + 1];
+            // even-odd crossing (oracle/geom.py point_in_polygon_crossing)
+            if ((ay > y) != (by > y)) {
+                const double xi = ax + (y - ay) * (bx - ax) / (by - ay);
+                if (x < xi) inside = !inside;
+            }
+            // D2 distance test (oracle/geom.py dist2_point_segment)
+            const double dx = bx - ax, dy = by - ay, wx = x - ax, wy = y - ay;
+            const double dd = dx * dx + dy * dy;
+            const double tt_ = wx * dx + wy * dy;
+            double u = dd > 0.0 ? tt_ / dd : 0.0;
+            u = fmin(fmax(u, 0.0), 1.0);
+            const double qx = wx - u * dx, qy = wy - u * dy;
+            hit = hit || (qx * qx + qy * qy < r2);
+        }
+        hit = hit || inside;
+    }
+    n_oviol += hit;
+}
+
+#ifndef FCPP_PLAN_GEN_THREADS
+#define FCPP_PLAN_GEN_THREADS 128
+#endif
+constexpr int TG = FCPP_PLAN_GEN_THREADS;
+static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 + 4 * FCPP_MAX_LOOPS - 1 in two rounds");
+
+__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs a)
+{
+    constexpr int T = TG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GenSmem s = gen_carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    GenFixed &f = *s.f;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t cand = blockIdx.x;
     const fcpp_vehicle &veh = a.b.vehicle;
     fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
+    if (tid == 0) mbar_init(&f.bar, 1);
+    __syncthreads();
 
-    int N, n_main;
-    int64_t off = 0;
     int n_obs_poly = 0;
     {
         // stage the candidate record (and the field's obstacle vertices) with TMA bulk copies
-        int f = 0, v0 = 0, nv = 0;
         if (tid == 0) {
-            f = a.recs[cand].field;
+            const int fi = a.recs[cand].field;
             uint32_t bytes = sizeof(CandRec);
+            int v0 = 0, nv = 0;
             if (a.b.obs_poly_start) {
-                const int p0 = a.b.obs_poly_start[f], p1 = a.b.obs_poly_start[f + 1];
+                const int p0 = a.b.obs_poly_start[fi], p1 = a.b.obs_poly_start[fi + 1];
                 v0 = a.b.obs_vert_start[p0];
                 nv = a.b.obs_vert_start[p1] - v0;
                 if (nv > a.obs_cap_verts) nv = a.obs_cap_verts;
                 bytes += nv * 16;
             }
-            mbar_expect_tx(s.bar, bytes);
-            bulk_g2s(s.rec, a.recs + cand, sizeof(CandRec), s.bar);
-            if (nv > 0) bulk_g2s(s.obs_xy, a.b.obs_verts + 2 * (int64_t)v0, nv * 16, s.bar);
+            mbar_expect_tx(&f.bar, bytes);
+            bulk_g2s(&f.rec, a.recs + cand, sizeof(CandRec), &f.bar);
+            if (nv > 0) bulk_g2s(s.obs_xy, a.b.obs_verts + 2 * (int64_t)v0, nv * 16, &f.bar);
         }
         // trig tables through the ordinary path meanwhile; the generic-point list starts empty
         for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
-            ((double *)s.tt)[k] = ((const double *)a.trig)[k];
-        for (int k = tid; k < N_GENERIC; k += T) s.glist[k] = -1;
-        mbar_wait_block(s.bar, phase);
-        const CandRec &r = *s.rec;
-        if (a.b.obs_poly_start) {
-            const int p0 = a.b.obs_poly_start[r.field], p1 = a.b.obs_poly_start[r.field + 1];
-            n_obs_poly = min(p1 - p0, a.obs_cap_polys);
-            const int base = a.b.obs_vert_start[p0];
-            for (int k = tid; k <= n_obs_poly; k += T) s.obs_vs[k] = a.b.obs_vert_start[p0 + k] - base;
-        }
-        N = r.n_total;
-        n_main = r.n_main;
-        if (a.out.offsets) off = a.out.offsets[cand];
-        if (sum && tid == 0) {
-            sum->n_passes = r.P;
-            sum->n_loops = r.K;
-            sum->n_main = r.n_main;
-            sum->n_head = r.n_head;
-            sum->n_rev[0] = r.n_rev[0];
-            sum->n_rev[1] = r.n_rev[1];
-            sum->n_rev[2] = r.n_rev[2];
-            sum->corner_g = r.corner_g;
-        }
+            ((double *)&f.tt)[k] = ((const double *)a.trig)[k];
+        for (int k = tid; k < N_GENERIC; k += T) f.glist[k] = -1;
+        mbar_wait_block(&f.bar, 0);
+    }
+    const CandRec &r = f.rec;
+    if (a.b.obs_poly_start) {
+        const int p0 = a.b.obs_poly_start[r.field], p1 = a.b.obs_poly_start[r.field + 1];
+        n_obs_poly = min(p1 - p0, a.obs_cap_polys);
+        const int base = a.b.obs_vert_start[p0];
+        for (int k = tid; k <= n_obs_poly; k += T) s.obs_vs[k] = a.b.obs_vert_start[p0 + k] - base;
+    }
+    const int N = r.n_total, n_main = r.n_main;
+    const int n_skip = main_skip(n_main);  // regular chain points: i in [2, 2 + n_skip)
+    const int NS = N - n_skip;             // staged points
+    const int64_t off = a.out.offsets ? a.out.offsets[cand] : 0;
+    if (sum && tid == 0) {
+        sum->n_passes = r.P;
+        sum->n_loops = r.K;
+        sum->n_main = r.n_main;
+        sum->n_head = r.n_head;
+        sum->n_rev[0] = r.n_rev[0];
+        sum->n_rev[1] = r.n_rev[1];
+        sum->n_rev[2] = r.n_rev[2];
+        sum->corner_g = r.corner_g;
+    }
+    {
         int st = r.status;
-        if (N > cap) {
-            if (!BIG && a.big_enabled) return;  // plan_big_kernel owns this candidate
-            st |= FCPP_CAND_TOO_LARGE;
-        }
+        if (NS > a.ncap) st |= FCPP_CAND_TOO_LARGE;
+        // the paths of this plan would not fit the caller's buffers (sized from an earlier batch)
+        if (a.out.path_capacity > 0 && off + N > a.out.path_capacity) st |= FCPP_CAND_TOO_LARGE;
         if (st != 0 || N == 0) {
             if (sum && tid == 0) {
                 sum->status = st;
@@ -400,13 +453,15 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
             return;
         }
     }
-    const CandRec &r = *s.rec;
+    __syncthreads();  // obs_vs is complete
     const double W = veh.working_width;
     TurnModel tm;
     tm.model = a.b.turn_model;
     tm.lam = a.b.clothoid_share;
     const double rr = W / 2;
     const double r2 = rr * rr;
+    const double two_a = 2 * veh.max_longitudinal_accel;
+    const bool do_scan = N >= 3;
 
     // ------------------------------------------------------------------------------------
     // phase 0: per-candidate tables.  Scratch points of the first main pass (+ the first two points of the
@@ -415,30 +470,31 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
     if (tid < 24) {
         if (r.P >= 2) {
             double px, py;
-            main_local_pt(r, *s.tt, tm, W, tid < 22 ? 0 : 1, tid < 22 ? tid : tid - 22, px, py);
-            s.tpts[2 * tid] = px;
-            s.tpts[2 * tid + 1] = py;
+            main_local_pt(r, f.tt, tm, W, tid < 22 ? 0 : 1, tid < 22 ? tid : tid - 22, px, py);
+            f.tpts[2 * tid] = px;
+            f.tpts[2 * tid + 1] = py;
         }
     } else if (tid >= 32 && tid < 32 + FCPP_CORNER_POINTS) {
         double px, py;
-        corner_arc_pt(*s.tt, tm, 0.0, 0.0, r.R, 0, tid - 32, px, py);
-        s.tpts[2 * (tid - 8)] = px;  // scratch points 24 .. 38
-        s.tpts[2 * (tid - 8) + 1] = py;
+        corner_arc_pt(f.tt, tm, 0.0, 0.0, r.R, 0, tid - 32, px, py);
+        f.tpts[2 * (tid - 8)] = px;  // scratch points 24 .. 38
+        f.tpts[2 * (tid - 8) + 1] = py;
     } else if (tid >= 64 && tid < 68) {
         // field edges for the D3 test: cross(e, p - v) < -eps*|e|
         const int k = tid - 64, k1 = (k + 1) & 3;
         const double ax = a.b.field_verts[(int64_t)r.field * 8 + 2 * k], ay = a.b.field_verts[(int64_t)r.field * 8 + 2 * k + 1];
         const double ex = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1] - ax;
         const double ey = a.b.field_verts[(int64_t)r.field * 8 + 2 * k1 + 1] - ay;
-        s.geo[5 * k] = ax;
-        s.geo[5 * k + 1] = ay;
-        s.geo[5 * k + 2] = ex;
-        s.geo[5 * k + 3] = ey;
-        s.geo[5 * k + 4] = -FCPP_GEOFENCE_EPS * sqrt(ex * ex + ey * ey);
-    } else if (tid >= 96 && tid < 96 + n_obs_poly) {
-        // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above
-        // any rounding of the exact test) can neither be inside it nor within W/2 of an edge
-        const int p = tid - 96;
+        f.geo[5 * k] = ax;
+        f.geo[5 * k + 1] = ay;
+        f.geo[5 * k + 2] = ex;
+        f.geo[5 * k + 3] = ey;
+        f.geo[5 * k + 4] = -FCPP_GEOFENCE_EPS * sqrt(ex * ex + ey * ey);
+    }
+    // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above any rounding of the
+    // exact test) can neither be inside it nor within W/2 of an edge
+    for (int p = tid - 96; p < n_obs_poly; p += T) {
+        if (p < 0) continue;
         double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
         for (int q = s.obs_vs[p]; q < s.obs_vs[p + 1]; ++q) {
             x0 = fmin(x0, s.obs_xy[2 * q]);
@@ -451,54 +507,39 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
         s.obs_bb[4 * p + 2] = x1 + rr + 1e-6;
         s.obs_bb[4 * p + 3] = y1 + rr + 1e-6;
     }
-    for (int p = 96 + T - 96 + tid; p < 96 + n_obs_poly; p += T) {  // more obstacles than threads 96..T-1: rare
-        const int q0 = p - 96;
-        double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-        for (int q = s.obs_vs[q0]; q < s.obs_vs[q0 + 1]; ++q) {
-            x0 = fmin(x0, s.obs_xy[2 * q]);
-            x1 = fmax(x1, s.obs_xy[2 * q]);
-            y0 = fmin(y0, s.obs_xy[2 * q + 1]);
-            y1 = fmax(y1, s.obs_xy[2 * q + 1]);
-        }
-        s.obs_bb[4 * q0] = x0 - rr - 1e-6;
-        s.obs_bb[4 * q0 + 1] = y0 - rr - 1e-6;
-        s.obs_bb[4 * q0 + 2] = x1 + rr + 1e-6;
-        s.obs_bb[4 * q0 + 3] = y1 + rr + 1e-6;
-    }
     __syncthreads();
-    {
-        // one thread per table slot
+    // one thread per table slot (two rounds when the CTA has fewer threads than slots' thread ids)
+    for (int vt = tid; vt < 96 + 4 * FCPP_MAX_LOOPS; vt += T) {
         int slot = -1;
         double ds = 0.0, kap = 0.0, v0 = 0.0, v1 = 0.0;
-        if (tid < 22) {
+        if (vt < CHAIN_POINTS) {
             if (r.P >= 2) {
-                slot = SLOT_MAIN + tid;
-                const double *p = s.tpts;
-                const int j = tid;
-                const double dx2 = p[2 * (j + 1)] - p[2 * j], dy2 = p[2 * (j + 1) + 1] - p[2 * j + 1];
-                ds = sqrt_z(dx2 * dx2 + dy2 * dy2);
-                // the point before slot 0 is the last turn sample of the previous pass: use pass 1's start (points 21, 22, 23)
-                const int c = (j == 0) ? 22 : j;
-                const double ax = p[2 * (c - 1)], ay = p[2 * (c - 1) + 1], bx = p[2 * c], by = p[2 * c + 1];
-                const double cx = p[2 * (c + 1)], cy = p[2 * (c + 1) + 1];
-                const double d1x = bx - ax, d1y = by - ay, d2x = cx - bx, d2y = cy - by;
-                kap = curvature3(d1x, d1y, sqrt_z(d1x * d1x + d1y * d1y), d2x, d2y, sqrt_z(d2x * d2x + d2y * d2y));
-                v0 = (j < 2) ? veh.max_work_speed_kmh : veh.headland_turn_speed_kmh;
-                v1 = (j == 0 || j == 21) ? veh.max_work_speed_kmh : veh.headland_turn_speed_kmh;
+                // chain point c = scratch point c + 2: turn samples of pass 0, then the two ends of swath 1
+                const int c = vt;
+                slot = SLOT_CHAIN + c;
+                const double *p = f.tpts + 2 * (c + 2);
+                const double d1x = p[0] - p[-2], d1y = p[1] - p[-1];
+                if (c < CHAIN_POINTS - 1) {
+                    const double d2x = p[2] - p[0], d2y = p[3] - p[1];
+                    ds = sqrt_z(d2x * d2x + d2y * d2y);
+                    kap = curvature3(d1x, d1y, sqrt_z(d1x * d1x + d1y * d1y), d2x, d2y, ds);
+                }  // the chain's last point is followed by its own copy (the next turn's first sample): ds = kappa = 0
+                v0 = (c < FCPP_UTURN_POINTS) ? veh.headland_turn_speed_kmh : veh.max_work_speed_kmh;
+                v1 = (c < FCPP_UTURN_POINTS - 1) ? veh.headland_turn_speed_kmh : veh.max_work_speed_kmh;
             }
-        } else if (tid >= 32 && tid < 32 + FCPP_CORNER_POINTS) {
-            const int aI = tid - 32;
+        } else if (vt >= 32 && vt < 32 + FCPP_CORNER_POINTS) {
+            const int aI = vt - 32;
             if (aI >= 1 && aI <= FCPP_CORNER_POINTS - 2) {
                 slot = SLOT_ARC + aI;
-                const double *p = s.tpts + 2 * 24;
+                const double *p = f.tpts + 2 * 24;
                 const double d1x = p[2 * aI] - p[2 * (aI - 1)], d1y = p[2 * aI + 1] - p[2 * (aI - 1) + 1];
                 const double d2x = p[2 * (aI + 1)] - p[2 * aI], d2y = p[2 * (aI + 1) + 1] - p[2 * aI + 1];
                 ds = sqrt_z(d2x * d2x + d2y * d2y);
                 kap = curvature3(d1x, d1y, sqrt_z(d1x * d1x + d1y * d1y), d2x, d2y, ds);
                 v0 = v1 = veh.headland_turn_speed_kmh;
             }
-        } else if (tid >= 64 && tid < 67) {
-            const int t = tid - 64;
+        } else if (vt >= 64 && vt < 67) {
+            const int t = vt - 64;
             if (r.n_rev[t] >= 2) {  // points ex + (m step) d: equally spaced, collinear (mlp3:1214-1216)
                 slot = SLOT_REV + t;
                 const double step = r.rev[t][4] / (r.n_rev[t] - 1);
@@ -506,12 +547,13 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
                 ds = sqrt_z(sx * sx + sy * sy);
                 v0 = v1 = veh.reverse_speed_kmh;
             }
-        } else if (tid >= 96 && tid < 96 + 4 * r.K) {
-            const int kt = tid - 96, k = kt >> 2, t = kt & 3;
+        } else if (vt >= 96 && vt < 96 + 4 * r.K) {
+            const int kt = vt - 96, k = kt >> 2, t = kt & 3;
             const int sc = r.flags & FCPP_FLAG_CORNER_MASK, ci = (sc + t) & 3, ni = (sc + t + 1) & 3;
             slot = SLOT_STRAIGHT + kt;
-            const double sx = (r.corners[k][ni][0] - r.corners[k][ci][0]) / (FCPP_STRAIGHT_POINTS - 1);
-            const double sy = (r.corners[k][ni][1] - r.corners[k][ci][1]) / (FCPP_STRAIGHT_POINTS - 1);
+            constexpr double DIV = FCPP_STRAIGHT_POINTS - 1;
+            const double sx = div_const(r.corners[k][ni][0] - r.corners[k][ci][0], DIV, 1.0 / DIV);
+            const double sy = div_const(r.corners[k][ni][1] - r.corners[k][ci][1], DIV, 1.0 / DIV);
             ds = sqrt_z(sx * sx + sy * sy);
             v0 = v1 = veh.max_headland_speed_kmh;
         }
@@ -524,108 +566,156 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
             e.vl = vl;
             e.u = vms * vms;
             e.tpre = div_z(ds, fmax(div36((v0 + v1) / 2), FCPP_MIN_SPEED_MS));
-            s.tbl[slot] = e;
+            f.tbl[slot] = e;
         }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------------------------
-    // phase 1: points -> HBM (when paths are materialised) + geofence tests; ds / kappa / U of every point of a
-    // congruent piece from the table; the generic points are listed by their fixed ordinal
+    // phase 0b (warp 0): the regular chain once — acceleration passes over its 22 points (a zero-length segment
+    // precedes and follows it, so it is a closed system, mlp3:560, :576), final speeds, validation, sums
+    // ------------------------------------------------------------------------------------
+    if (tid < 32 && n_skip > 0) {
+        const bool on = lane < CHAIN_POINTS;
+        const Tpl e = f.tbl[SLOT_CHAIN + (on ? lane : 0)];
+        const double ds_prev = __shfl_up_sync(0xffffffffu, e.ds, 1);
+        // forward: element c = (increment from c-1, U_c); the chain starts behind a zero-length segment
+        MP inc;
+        inc.C = (on && lane > 0 && !(ds_prev < FCPP_ZERO_LEN)) ? two_a * ds_prev : INFINITY;
+        inc.M = on ? e.u : INFINITY;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const MP o = mp_shfl_up(inc, d);
+            if (lane >= d) inc = mp_combine(o, inc);
+        }
+        const double fwd = inc.M;
+        // backward over the mirrored lanes: lane l holds chain point 21 - l
+        const int src = CHAIN_POINTS - 1 - lane;  // valid for lane < 22
+        const double f_m = __shfl_sync(0xffffffffu, fwd, src & 31);
+        const double ds_m = __shfl_sync(0xffffffffu, e.ds, src & 31);  // ds of the mirrored point = increment to ITS successor
+        MP b;
+        b.C = (on && !(ds_m < FCPP_ZERO_LEN)) ? two_a * ds_m : INFINITY;  // applied when coming from the successor
+        b.M = on ? f_m : INFINITY;
+        // scan element for the mirrored order: value_l = min(M_l, value_{l-1} + C_l) with C_l = increment between
+        // point (21-l) and its successor (21-l+1) = ds of point 21-l
+        if (lane == 0) b.C = INFINITY;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const MP o = mp_shfl_up(b, d);
+            if (lane >= d) b = mp_combine(o, b);
+        }
+        const double u_fin = __shfl_sync(0xffffffffu, b.M, src & 31);  // back to chain order
+        const double v = do_scan ? final_speed(on, u_fin, e.u, e.vl) : e.vl;
+        const double v_next = __shfl_down_sync(0xffffffffu, v, 1);
+        const double k_next = __shfl_down_sync(0xffffffffu, e.kap, 1);
+        double t_adj = 0.0, alat = 0.0, jump = 0.0;
+        if (on) {
+            f.chain_v[lane] = v;
+            if (lane < CHAIN_POINTS - 1) {
+                t_adj = div_pos(e.ds, fmax(div36((v + v_next) / 2), FCPP_MIN_SPEED_MS));
+                jump = fabs(k_next - e.kap);
+            }
+            const double vm = div36(v);
+            alat = vm * vm * e.kap;
+        }
+        const double s_len = warp_sum(on ? e.ds : 0.0), s_tpre = warp_sum(on ? e.tpre : 0.0), s_tadj = warp_sum(t_adj);
+        const double s_av = warp_sum((on && alat > veh.max_lateral_accel) ? 1.0 : 0.0);
+        const double m_k = warp_max(on ? e.kap : 0.0), m_a = warp_max(alat), m_j = warp_max(jump);
+        if (lane == 0) {
+            f.chain_sum[0] = s_len;
+            f.chain_sum[1] = s_tpre;
+            f.chain_sum[2] = s_tadj;
+            f.chain_sum[3] = s_av;
+            f.chain_sum[4] = m_k;
+            f.chain_sum[5] = m_a;
+            f.chain_sum[6] = m_j;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------
+    // phase 1: the staged points (first 2 + last 22 main points, headland): points -> HBM (when paths are
+    // materialised) + point tests; ds / kappa / U of every point inside a congruent headland piece from the
+    // table; the generic points are listed by their fixed ordinal
     // ------------------------------------------------------------------------------------
     int n_bviol = 0, n_oviol = 0;
     double acc_len_m = 0.0, acc_len_h = 0.0, acc_tpre_m = 0.0, acc_tpre_h = 0.0;
-    {
-        double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
-        for (int i = tid; i < N; i += T) {
-            double x, y;
-            uint8_t c;
-            int tag, gord;
-            gen_point_tag(r, *s.tt, tm, W, i, x, y, c, tag, gord);
-            if (gp) gp[i] = make_double2(x, y);
-            s.CLS[i] = (uint8_t)tag;
-            if (gord >= 0) {
-                s.glist[gord] = i;
-            } else {
-                const Tpl e = s.tbl[tag];
-                s.X[i] = e.ds;
-                s.Y[i] = e.kap;
-                s.U[i] = e.u;
-                if (i < n_main) {
-                    acc_len_m += e.ds;
-                    acc_tpre_m += e.tpre;
-                } else {
-                    acc_len_h += e.ds;
-                    acc_tpre_h += e.tpre;
-                }
-            }
-            bool outb = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                outb = outb || (s.geo[5 * k + 2] * (y - s.geo[5 * k + 1]) - s.geo[5 * k + 3] * (x - s.geo[5 * k]) < s.geo[5 * k + 4]);
-            n_bviol += outb;
-            bool hit = false;
-            for (int p = 0; p < n_obs_poly && !hit; ++p) {
-                if (x < s.obs_bb[4 * p] || y < s.obs_bb[4 * p + 1] || x > s.obs_bb[4 * p + 2] || y > s.obs_bb[4 * p + 3])
-                    continue;
-                const int vs = s.obs_vs[p], ve = s.obs_vs[p + 1];
-                bool inside = false;
-                for (int q = vs; q < ve; ++q) {
-                    const int q1 = (q + 1 < ve) ? q + 1 : vs;
-                    const double ax = s.obs_xy[2 * q], ay = s.obs_xy[2 * q + 1];
-                    const double bx = s.obs_xy[2 * q1], by = s.obs_xy[2 * q1 + 1];
-                    // even-odd crossing (oracle/geom.py point_in_polygon_crossing)
-                    if ((ay > y) != (by > y)) {
-                        const double xi = ax + (y - ay) * (bx - ax) / (by - ay);
-                        if (x < xi) inside = !inside;
-                    }
-                    // D2 distance test (oracle/geom.py dist2_point_segment)
-                    const double dx = bx - ax, dy = by - ay, wx = x - ax, wy = y - ay;
-                    const double dd = dx * dx + dy * dy;
-                    const double tt_ = wx * dx + wy * dy;
-                    double u = dd > 0.0 ? tt_ / dd : 0.0;
-                    u = fmin(fmax(u, 0.0), 1.0);
-                    const double qx = wx - u * dx, qy = wy - u * dy;
-                    hit = hit || (qx * qx + qy * qy < r2);
-                }
-                hit = hit || inside;
-            }
-            n_oviol += hit;
+    double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
+    double *gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
+    double *gk = a.out.curvature ? a.out.curvature + off : nullptr;
+    for (int q = tid; q < NS; q += T) {
+        const int i = q < 2 ? q : q + n_skip;
+        double x, y;
+        uint8_t c;
+        int tag, gord;
+        gen_point_tag(r, f.tt, tm, W, i, x, y, c, tag, gord);
+        if (gp) gp[i] = make_double2(x, y);
+        s.TAG[q] = (uint8_t)tag;
+        if (gord >= 0) {
+            f.glist[gord] = i;
+        } else {
+            const Tpl e = f.tbl[tag];
+            s.X[q] = e.ds;
+            s.Y[q] = e.kap;
+            s.U[q] = e.u;
+            acc_len_h += e.ds;  // table slots of staged points are headland pieces
+            acc_tpre_h += e.tpre;
         }
+        point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
     }
-    __syncthreads();
+    __syncthreads();  // glist, chain_v
     // ------------------------------------------------------------------------------------
-    // phase 2: the generic points (first / last point of every piece) from their coordinates: mlp3:490-504
+    // phase 1b: the regular chains' points (most of a plan): generated, tested, written with the chain's speeds
     // ------------------------------------------------------------------------------------
-    const int n_gslots = 2 + GEN_PER_LOOP * r.K;
+    for (int i = 2 + tid; i < 2 + n_skip; i += T) {
+        const int idx = i / CHAIN_POINTS;
+        const int j = i - idx * CHAIN_POINTS;
+        double px, py, x, y;
+        main_local_pt(r, f.tt, tm, W, idx, j, px, py);
+        if (r.flags & FCPP_FLAG_ROTATED)
+            rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
+        else {
+            x = px;
+            y = py;
+        }
+        const int c = j >= 2 ? j - 2 : j + FCPP_UTURN_POINTS;  // position in its chain
+        if (gp) gp[i] = make_double2(x, y);
+        if (gs) gs[i] = f.chain_v[c];
+        if (gk) gk[i] = f.tbl[SLOT_CHAIN + c].kap;
+        point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
+    }
+    // ------------------------------------------------------------------------------------
+    // phase 2: the generic points (where two pieces meet, the irregular main points) from their coordinates
+    // (mlp3:490-504): the point and its two neighbours are regenerated
+    // ------------------------------------------------------------------------------------
+    const int n_gslots = MAIN_STAGED + GEN_PER_LOOP * r.K;
     for (int g = tid; g < n_gslots; g += T) {
-        const int i = s.glist[g];
+        const int i = f.glist[g];
         if (i < 0) continue;
-        // the point and its two neighbours, regenerated (one loop body: the generator is large)
         double P3[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         uint8_t C3[3] = {0, 0, 0};
 #pragma unroll 1
         for (int d = 0; d < 3; ++d) {
-            const int q = i - 1 + d;
-            if (q >= 0 && q < N) gen_point(r, *s.tt, tm, W, q, P3[d][0], P3[d][1], C3[d]);
+            const int qq = i - 1 + d;
+            if (qq >= 0 && qq < N) gen_point(r, f.tt, tm, W, qq, P3[d][0], P3[d][1], C3[d]);
         }
-        const double px = P3[0][0], py = P3[0][1], cx = P3[1][0], cy = P3[1][1], nx = P3[2][0], ny = P3[2][1];
-        const uint8_t c0 = C3[1], c1 = C3[2];
-        double ds1 = 0.0, ds2 = 0.0, dx1 = cx - px, dy1 = cy - py, dx2 = nx - cx, dy2 = ny - cy;
+        const double dx1 = P3[1][0] - P3[0][0], dy1 = P3[1][1] - P3[0][1];
+        const double dx2 = P3[2][0] - P3[1][0], dy2 = P3[2][1] - P3[1][1];
+        double ds1 = 0.0, ds2 = 0.0;
         if (i > 0) ds1 = sqrt_z(dx1 * dx1 + dy1 * dy1);
         if (i + 1 < N) ds2 = sqrt_z(dx2 * dx2 + dy2 * dy2);
         double kap = 0.0;
         if (i >= 1 && i + 1 < N) kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds2);
-        const double v0 = cls_speed(veh, c0);
+        const double v0 = cls_speed(veh, C3[1]);
         const double vl = vlimit(v0, kap, veh);
         const double vms = div36(vl);
-        s.X[i] = ds2;
-        s.Y[i] = kap;
-        s.U[i] = vms * vms;
-        s.gvl[g] = vl;
+        const int q = i < 2 ? i : i - n_skip;
+        s.X[q] = ds2;
+        s.Y[q] = kap;
+        s.U[q] = vms * vms;
+        f.gvl[g] = vl;
         // per-layer length and pre-adjustment time (mlp3:616-617, :882-883)
         if (i + 1 < N && i != n_main - 1) {
-            const double t = div_z(ds2, fmax(div36((v0 + cls_speed(veh, c1)) / 2), FCPP_MIN_SPEED_MS));
+            const double t = div_z(ds2, fmax(div36((v0 + cls_speed(veh, C3[2])) / 2), FCPP_MIN_SPEED_MS));
             if (i < n_main) {
                 acc_len_m += ds2;
                 acc_tpre_m += t;
@@ -637,70 +727,69 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
     }
     __syncthreads();
 
-    const int chunk = (N + T - 1) / T;
-    const int cs = min(N, tid * chunk);
-    const int ce = min(N, cs + chunk);
-    const bool do_scan = N >= 3;
-    const double two_a = 2 * veh.max_longitudinal_accel;
+    // ------------------------------------------------------------------------------------
+    // phases 3 / 4 over the staged sequence (the zero-length segment after point 1 separates the two staged ends
+    // of the main work): forward f = min(U, f_prev + 2a ds_prev) (mlp3:558-571), backward (mlp3:574-587)
+    // ------------------------------------------------------------------------------------
+    const int chunk = (NS + T - 1) / T;
+    const int cs = min(NS, tid * chunk);
+    const int ce = min(NS, cs + chunk);
     if (do_scan) {
-        // phase 3: forward pass  f_i = min(U_i, f_{i-1} + 2a*ds_{i-1})   (mlp3:558-571)
         {
             MP agg;
             agg.C = 0.0;
             agg.M = INFINITY;
-            for (int i = cs; i < ce; ++i) {
-                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
-                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
-                agg.M = fmin(s.U[i], agg.M + c);
+            for (int q = cs; q < ce; ++q) {
+                const double dsp = (q > 0) ? s.X[q - 1] : 0.0;
+                const double c = (q > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                agg.M = fmin(s.U[q], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, s.scratch);
-            for (int i = cs; i < ce; ++i) {
-                const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
-                const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
-                carry = fmin(s.U[i], carry + c);
-                s.U[i] = carry;
+            double carry = mp_block_exclusive(agg, f.scratch);
+            for (int q = cs; q < ce; ++q) {
+                const double dsp = (q > 0) ? s.X[q - 1] : 0.0;
+                const double c = (q > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
+                carry = fmin(s.U[q], carry + c);
+                s.U[q] = carry;
             }
         }
         __syncthreads();
-        // phase 4: backward pass  b_i = min(f_i, b_{i+1} + 2a*ds_i)      (mlp3:574-587), as a forward scan over the
-        // reversed sequence: thread tid takes the chunk of thread T-1-tid
         {
             const int rt = T - 1 - tid;
-            const int rs = min(N, rt * chunk);
-            const int re = min(N, rs + chunk);
+            const int rs = min(NS, rt * chunk);
+            const int re = min(NS, rs + chunk);
             MP agg;
             agg.C = 0.0;
             agg.M = INFINITY;
-            for (int i = re - 1; i >= rs; --i) {
-                const double dsn = s.X[i];  // ds_i (0 for the last point)
-                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
-                agg.M = fmin(s.U[i], agg.M + c);
+            for (int q = re - 1; q >= rs; --q) {
+                const double dsn = s.X[q];  // ds to the successor (0 for the last point)
+                const double c = (q + 1 < NS && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                agg.M = fmin(s.U[q], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, s.scratch);
-            for (int i = re - 1; i >= rs; --i) {
-                const double dsn = s.X[i];
-                const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
-                carry = fmin(s.U[i], carry + c);
-                s.U[i] = carry;
+            double carry = mp_block_exclusive(agg, f.scratch);
+            for (int q = re - 1; q >= rs; --q) {
+                const double dsn = s.X[q];
+                const double c = (q + 1 < NS && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
+                carry = fmin(s.U[q], carry + c);
+                s.U[q] = carry;
             }
         }
         __syncthreads();
     }
 
     // ------------------------------------------------------------------------------------
-    // phase 5a: final speeds (km/h) -> U[i] and HBM; lateral-acceleration validation (mlp3:1383-1410)
+    // phase 5a: final speeds (km/h) of the staged points -> U[q] and HBM; lateral-acceleration validation
+    // (mlp3:1383-1410)
     // ------------------------------------------------------------------------------------
     int n_aviol = 0;
     double mx[3] = {0.0, 0.0, 0.0};  // max kappa, max a_lat, max |kappa jump|
-    double *gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
-    double *gk = a.out.curvature ? a.out.curvature + off : nullptr;
-    auto finish_point = [&](bool act, int i, double u_lim, double vl) {
-        const double kap = act ? s.Y[i] : 0.0;
-        const double u = act ? s.U[i] : 0.0;
+    auto finish_point = [&](bool act, int q, double u_lim, double vl) {
+        const double kap = act ? s.Y[q] : 0.0;
+        const double u = act ? s.U[q] : 0.0;
         const double v = do_scan ? final_speed(act, u, u_lim, vl) : vl;
         if (!act) return;
+        const int i = q < 2 ? q : q + n_skip;
         if (gs) gs[i] = v;
         if (gk) gk[i] = kap;
         if (i >= 1 && i + 1 < N) {
@@ -709,41 +798,45 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
             n_aviol += (alat > veh.max_lateral_accel);
             mx[0] = fmax(mx[0], kap);
             mx[1] = fmax(mx[1], alat);
-            if (i + 2 < N) mx[2] = fmax(mx[2], fabs(s.Y[i + 1] - kap));
+            // the successor in the staged order is the successor in the plan except after point 1, where both
+            // curvatures are 0 (a zero-length segment on either side)
+            if (i + 2 < N) mx[2] = fmax(mx[2], fabs(s.Y[q + 1] - kap));
         }
-        s.U[i] = v;  // safe: U[i] is read only by its owner in this phase
+        s.U[q] = v;  // safe: U[q] is read only by its owner in this phase
     };
-    for (int base = 0; base < N; base += T) {  // warp-uniform trip count (final_speed votes)
-        const int i = base + tid;
-        const int tag = (i < N) ? s.CLS[i] : TAG_GENERIC;
+    for (int base = 0; base < NS; base += T) {  // warp-uniform trip count (final_speed votes)
+        const int q = base + tid;
+        const int tag = (q < NS) ? s.TAG[q] : TAG_GENERIC;
         const bool act = tag < TAG_GENERIC;
         double u_lim = 0.0, vl = 0.0;
         if (act) {
-            u_lim = s.tbl[tag].u;
-            vl = s.tbl[tag].vl;
+            u_lim = f.tbl[tag].u;
+            vl = f.tbl[tag].vl;
         }
-        finish_point(act, i, u_lim, vl);
+        finish_point(act, q, u_lim, vl);
     }
     for (int base = 0; base < n_gslots; base += T) {
         const int g = base + tid;
-        const int i = (g < n_gslots) ? s.glist[g] : -1;
+        const int i = (g < n_gslots) ? f.glist[g] : -1;
         const bool act = i >= 0;
         double vl = 0.0, u_lim = 0.0;
         if (act) {
-            vl = s.gvl[g];
+            vl = f.gvl[g];
             const double vms = div36(vl);
             u_lim = vms * vms;
         }
-        finish_point(act, i, u_lim, vl);
+        finish_point(act, act ? (i < 2 ? i : i - n_skip) : 0, u_lim, vl);
     }
     __syncthreads();
     // ------------------------------------------------------------------------------------
     // phase 5b: work time with the adjusted speeds (mlp3:423-431, :1298-1311)
     // ------------------------------------------------------------------------------------
     double acc_t_m = 0.0, acc_t_h = 0.0;
-    for (int i = tid; i + 1 < N; i += T) {
+    for (int q = tid; q + 1 < NS; q += T) {
+        const int i = q < 2 ? q : q + n_skip;
         if (i == n_main - 1) continue;
-        const double t = div_pos(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
+        // (after point 1 the staged successor is not the plan's, but that segment has zero length: t = 0)
+        const double t = div_pos(s.X[q], fmax(div36((s.U[q] + s.U[q + 1]) / 2), FCPP_MIN_SPEED_MS));
         if (i < n_main)
             acc_t_m += t;
         else
@@ -751,22 +844,25 @@ __device__ __forceinline__ void plan_body_gen(const PlanArgs &a, const Smem &s, 
     }
     double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
                       acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
-    block_reduce<9, false, T / 32>(sums, s.scratch);
-    block_reduce<3, true, T / 32>(mx, s.scratch);
+    block_reduce<9, false, T / 32>(sums, f.scratch);
+    block_reduce<3, true, T / 32>(mx, f.scratch);
     if (tid == 0 && sum) {
+        // the regular chains: one chain's sums times their number
+        const double nreg = (double)(n_skip / CHAIN_POINTS);
+        const bool reg = n_skip > 0;
         sum->status = 0;
-        sum->len_main = sums[0];
+        sum->len_main = sums[0] + (reg ? nreg * f.chain_sum[0] : 0.0);
         sum->len_head = sums[1];
-        sum->time_main_pre = sums[2];
+        sum->time_main_pre = sums[2] + (reg ? nreg * f.chain_sum[1] : 0.0);
         sum->time_head_pre = sums[3];
-        sum->time_main = sums[4];
+        sum->time_main = sums[4] + (reg ? nreg * f.chain_sum[2] : 0.0);
         sum->time_head = sums[5];
-        sum->n_accel_viol = (int)sums[6];
+        sum->n_accel_viol = (int)(sums[6] + (reg ? nreg * f.chain_sum[3] : 0.0));
         sum->n_boundary_viol = (int)sums[7];
         sum->n_obstacle_viol = (int)sums[8];
-        sum->max_curvature = mx[0];
-        sum->max_lateral_accel = mx[1];
-        sum->max_jump = mx[2];
+        sum->max_curvature = reg ? fmax(mx[0], f.chain_sum[4]) : mx[0];
+        sum->max_lateral_accel = reg ? fmax(mx[1], f.chain_sum[5]) : mx[1];
+        sum->max_jump = reg ? fmax(mx[2], f.chain_sum[6]) : mx[2];
         sum->reserved = 0.0;
         if (!a.b.do_coverage) {
             sum->cov_cells = sum->cov_total = 0;
@@ -973,97 +1069,68 @@ __device__ __forceinline__ void plan_body_path(const PlanArgs &a, const Smem &s,
     }
 }
 
-template <bool GEN, bool BIG, int T>
-__device__ __forceinline__ void plan_body(const PlanArgs &a, const Smem &s, const int64_t cand, const int cap,
-                                          const uint32_t phase)
-{
-    if (GEN)
-        plan_body_gen<BIG, T>(a, s, cand, cap, phase);
-    else
-        plan_body_path<BIG, T>(a, s, cand, cap);
-}
-
 #ifndef FCPP_PLAN_MIN_CTAS
 #define FCPP_PLAN_MIN_CTAS 4
 #endif
-// T threads per CTA: T0 (256) when four or more CTAs fit an SM, 2*T0 / 4*T0 when the staging of long
-// plans leaves room for only two / one (a 2 km x 1 km plan has 7 191 points = 180 KB): the SM keeps
-// ~32 resident warps either way
-template <bool GEN, int T>
-__global__ void __launch_bounds__(T, (T0 * FCPP_PLAN_MIN_CTAS) / T) plan_kernel(const PlanArgs a)
+// Caller-supplied paths.  T threads per CTA: T0 (256) when four or more CTAs fit an SM, 2*T0 / 4*T0 when the
+// staging of long paths leaves room for only two / one: the SM keeps ~32 resident warps either way
+template <int T>
+__global__ void __launch_bounds__(T, (T0 * FCPP_PLAN_MIN_CTAS) / T) path_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (a.nmin >= 0 || a.defer) {  // tiered launch: is this plan in this tier's length range?
-        const int n = GEN ? a.recs[blockIdx.x].n_total : (int)(a.in_offsets[blockIdx.x + 1] - a.in_offsets[blockIdx.x]);
+    if (a.nmin >= 0 || a.defer) {  // tiered launch: is this path in this tier's length range?
+        const int n = (int)(a.in_offsets[blockIdx.x + 1] - a.in_offsets[blockIdx.x]);
         if (n <= a.nmin || (a.defer && n > a.ncap)) return;
     }
-    const Smem s = carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
-    if (threadIdx.x == 0) mbar_init(s.bar, 1);
-    __syncthreads();
-    plan_body<GEN, false, T>(a, s, blockIdx.x, a.ncap, 0);
+    const Smem s = carve(smem_raw, a.ncap);
+    plan_body_path<false, T>(a, s, blockIdx.x, a.ncap);
 }
 
-// Plans that do not fit the shared-memory staging (N > ~9000 points, e.g. a 5 km x 3 km field):
-// a few persistent CTAs walk the batch and run the same body with x/y/u/class staged in a
-// per-CTA slice of library-owned HBM (L2-resident in practice).
-template <bool GEN>
-__global__ void __launch_bounds__(T0, 3) plan_big_kernel(const PlanArgs a)
+// Paths that do not fit the shared-memory staging (N > ~9000 points): a few persistent CTAs walk the batch and
+// run the same body with x/y/u staged in a per-CTA slice of library-owned HBM (L2-resident in practice).
+__global__ void __launch_bounds__(T0, 3) path_big_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem s = carve(smem_raw, 0, a.obs_cap_verts, a.obs_cap_polys);
+    Smem s = carve(smem_raw, 0);
     unsigned char *slice = a.big_scratch + (int64_t)blockIdx.x * a.big_stride;
     const size_t arr = align16(sizeof(double) * (size_t)a.big_ncap);
     s.X = (double *)slice;
     s.Y = (double *)(slice + arr);
     s.U = (double *)(slice + 2 * arr);
-    s.CLS = (uint8_t *)(slice + 3 * arr);
-    if (threadIdx.x == 0) mbar_init(s.bar, 1);
-    __syncthreads();
-    uint32_t phase = 0;
     for (int64_t c = blockIdx.x; c < a.n_items; c += gridDim.x) {
-        const int n = GEN ? a.recs[c].n_total : (int)(a.in_offsets[c + 1] - a.in_offsets[c]);
-        if (n <= a.ncap) continue;  // handled by plan_kernel
-        plan_body<GEN, true, T0>(a, s, c, a.big_ncap, phase);
-        if (GEN) phase ^= 1u;
+        const int n = (int)(a.in_offsets[c + 1] - a.in_offsets[c]);
+        if (n <= a.ncap) continue;  // handled by path_kernel
+        plan_body_path<true, T0>(a, s, c, a.big_ncap);
         __syncthreads();
     }
 }
 
-// configure + launch plan_kernel with the thread count that keeps ~32 warps resident per SM
-template <bool GEN, int T>
+template <int T>
 cudaError_t launch_variant(const PlanArgs &a, int64_t n, size_t bytes, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(plan_kernel<GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(path_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    plan_kernel<GEN, T><<<(unsigned)n, T, bytes, st>>>(a);
+    path_kernel<T><<<(unsigned)n, T, bytes, st>>>(a);
     return cudaGetLastError();
 }
 // largest point capacity whose staging lets `ctas` CTAs share one SM (1 KB reserved per CTA)
-int capacity_for_ctas(fcpp_handle *h, int obs_verts, int obs_polys, int ctas)
+int capacity_for_ctas(fcpp_handle *h, int ctas)
 {
-    const size_t budget = (size_t)h->max_smem_sm / ctas - 1024;
-    int lo = 0, hi = 1 << 20;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) / 2;
-        const size_t b = plan_smem_bytes(mid, obs_verts, obs_polys);
-        if (b <= budget && b <= (size_t)h->max_smem_optin)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo / 64 * 64;
+    size_t budget = (size_t)h->max_smem_sm / ctas - 1024;
+    if (budget > (size_t)h->max_smem_optin) budget = (size_t)h->max_smem_optin;
+    const size_t fixed = plan_smem_bytes(0);
+    if (budget <= fixed) return 0;
+    return (int)((budget - fixed) / 24) / 64 * 64;
 }
 
-// One launch when the longest plan of the batch leaves room for four CTAs per SM (BASELINE config 2).
-// A batch of mixed lengths (config 3: the plan length follows the heading) is cut into up to three
-// TIERS by plan length — N <= cap4 at T0 threads and four CTAs per SM, cap4 < N <= cap2 at 2*T0 and
-// two, longer at 4*T0 and one — so that short plans do not inherit the occupancy of the longest.
-// Every tier launches one CTA per candidate; CTAs outside the tier's range exit on one 4-byte read.
-template <bool GEN>
+// One launch when the longest path of the batch leaves room for four CTAs per SM.  A batch of mixed lengths is cut
+// into up to three TIERS by length — N <= cap4 at T0 threads and four CTAs per SM, cap4 < N <= cap2 at 2*T0 and
+// two, longer at 4*T0 and one — so that short paths do not inherit the occupancy of the longest.  Every tier
+// launches one CTA per path; CTAs outside the tier's range exit on one read.
 cudaError_t launch_tiers(fcpp_handle *h, PlanArgs &a, int64_t n, int want, int cap_max, bool big, cudaStream_t st)
 {
-    const int cap4 = capacity_for_ctas(h, a.obs_cap_verts, a.obs_cap_polys, 4);
-    const int cap2 = capacity_for_ctas(h, a.obs_cap_verts, a.obs_cap_polys, 2);
+    const int cap4 = capacity_for_ctas(h, 4);
+    const int cap2 = capacity_for_ctas(h, 2);
     const int last = (want > 0 && want < cap_max) ? want : cap_max;
     int caps[3], nt = 0;
     if (last > cap4 && cap4 >= 256) caps[nt++] = cap4;
@@ -1075,25 +1142,25 @@ cudaError_t launch_tiers(fcpp_handle *h, PlanArgs &a, int64_t n, int want, int c
         a.nmin = prev;
         a.defer = (t + 1 < nt) ? 1 : 0;
         a.big_enabled = (t + 1 == nt && big) ? 1 : 0;
-        const size_t bytes = plan_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+        const size_t bytes = plan_smem_bytes(a.ncap);
         if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;
         const int fit = (int)((size_t)h->max_smem_sm / (bytes + 1024));
         h->launches++;
-        cudaError_t e = fit >= 4   ? launch_variant<GEN, T0>(a, n, bytes, st)
-                        : fit >= 2 ? launch_variant<GEN, 2 * T0>(a, n, bytes, st)
-                                   : launch_variant<GEN, 4 * T0>(a, n, bytes, st);
+        cudaError_t e = fit >= 4   ? launch_variant<T0>(a, n, bytes, st)
+                        : fit >= 2 ? launch_variant<2 * T0>(a, n, bytes, st)
+                                   : launch_variant<4 * T0>(a, n, bytes, st);
         if (e != cudaSuccess) return e;
         prev = caps[t];
     }
     return cudaSuccess;
 }
 
-// launch plan_big_kernel when the longest plan exceeds the shared-memory capacity
-template <bool GEN>
+// launch path_big_kernel when the longest path exceeds the shared-memory capacity.  The HBM staging (h->d_big) is
+// owned and resized here only.
 cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_points, cudaStream_t st)
 {
     const int big_ncap = (max_points + 255) / 256 * 256;
-    const int64_t stride = (int64_t)(3 * align16(sizeof(double) * (size_t)big_ncap) + align16((size_t)big_ncap));
+    const int64_t stride = (int64_t)(3 * align16(sizeof(double) * (size_t)big_ncap));
     int64_t ctas = n_items < 2 * h->sm_count ? n_items : 2 * h->sm_count;
     while (ctas > 1 && ctas * stride > ((int64_t)8 << 30)) ctas /= 2;  // at most 8 GiB of scratch
     if (ctas * stride > h->big_cap) {
@@ -1108,32 +1175,16 @@ cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_poi
     a.big_scratch = (unsigned char *)h->d_big;
     a.big_stride = stride;
     a.n_items = n_items;
-    const size_t bytes = plan_smem_bytes(0, a.obs_cap_verts, a.obs_cap_polys);
-    if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;  // obstacle tables larger than shared memory
-    cudaError_t ea = cudaFuncSetAttribute(plan_big_kernel<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ea != cudaSuccess) return ea;
-    plan_big_kernel<GEN><<<(unsigned)ctas, T0, bytes, st>>>(a);
+    path_big_kernel<<<(unsigned)ctas, T0, plan_smem_bytes(0), st>>>(a);
     h->launches++;
     return cudaGetLastError();
 }
 
-int capacity_for(fcpp_handle *h, int obs_verts, int obs_polys, int want)
-{
-    // largest point capacity that fits the opt-in shared memory; `want` caps it so that small
-    // plans leave room for more resident CTAs per SM
-    int lo = 0, hi = 1 << 20;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) / 2;
-        if (plan_smem_bytes(mid, obs_verts, obs_polys) <= (size_t)h->max_smem_optin)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return want > 0 && want < lo ? want : lo;
-}
-
 }  // namespace
 
+// Generated plans: one CTA per candidate.  Only the first 2 + last 22 main points and the headland are staged in
+// shared memory (~25 B per point), so the staging depends on the longest HEADLAND of the batch, not on the plan
+// length: no length tiers, no HBM staging, 7-8 CTAs of 128 threads per SM at every field size.
 cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
                              int *ncap_out)
 {
@@ -1145,14 +1196,16 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     a.out = o;
     a.obs_cap_verts = b.obs_poly_start ? b.max_obs_verts : 0;
     a.obs_cap_polys = b.obs_poly_start ? b.max_obs_polys : 0;
-    a.ncap = capacity_for(h, a.obs_cap_verts, a.obs_cap_polys, h->plan_ncap_hint);
+    a.ncap = (MAIN_STAGED + (h->cover_pcap > 0 ? h->cover_pcap : 0) + 63) / 64 * 64;
     if (ncap_out) *ncap_out = a.ncap;
-    const bool big = h->plan_ncap_hint > a.ncap;
-    a.big_enabled = big ? 1 : 0;
     a.n_items = b.n_cand;
-    cudaError_t e = launch_tiers<true>(h, a, b.n_cand, h->plan_ncap_hint, a.ncap, big, st);
-    if (e == cudaSuccess && big) e = launch_big<true>(h, a, b.n_cand, h->plan_ncap_hint, st);
-    return e;
+    const size_t bytes = gen_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;  // obstacle tables / headland beyond shared memory
+    cudaError_t e = cudaFuncSetAttribute(plan_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    plan_gen_kernel<<<(unsigned)b.n_cand, TG, bytes, st>>>(a);
+    h->launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, const double *d_path,
@@ -1170,12 +1223,13 @@ cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, co
     a.out.summary = d_summary;
     a.out.speeds_kmh = d_speeds_out;
     a.out.curvature = d_curv;
+    const int cap_max = capacity_for_ctas(h, 1);
     const int want = max_len > 0 ? (int)((max_len + 255) / 256 * 256) : 0;
-    a.ncap = capacity_for(h, 0, 0, want);
+    a.ncap = (want > 0 && want < cap_max) ? want : cap_max;
     const bool big = want > a.ncap;
     a.big_enabled = big ? 1 : 0;
     a.n_items = n_paths;
-    cudaError_t e = launch_tiers<false>(h, a, n_paths, want > 0 ? want : a.ncap, a.ncap, big, st);
-    if (e == cudaSuccess && big) e = launch_big<false>(h, a, n_paths, want, st);
+    cudaError_t e = launch_tiers(h, a, n_paths, want > 0 ? want : a.ncap, a.ncap, big, st);
+    if (e == cudaSuccess && big) e = launch_big(h, a, n_paths, want, st);
     return e;
 }

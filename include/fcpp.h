@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FCPP_ABI_VERSION 1
+#define FCPP_ABI_VERSION 2
 
 /* hard-coded sample counts of the reference */
 #define FCPP_UTURN_POINTS 20      /* mlp3:807  */
@@ -53,7 +53,8 @@ typedef enum {
 #define FCPP_CAND_INSET_EMPTY 1   /* mlp3:597-598 ValueError */
 #define FCPP_CAND_LOOP_SKIPPED 2  /* mlp3:967-969 + :939 (vstack shape error) */
 #define FCPP_CAND_TOO_MANY_LOOPS 4
-#define FCPP_CAND_TOO_LARGE 8     /* N exceeds the shared-memory staging capacity */
+#define FCPP_CAND_TOO_LARGE 8     /* the staged part exceeds the shared-memory capacity, or the plan's points the
+                                     caller's path buffers (fcpp_outputs.path_capacity) */
 #define FCPP_CAND_GRID_TOO_LARGE 16
 
 typedef struct fcpp_handle fcpp_handle;
@@ -159,6 +160,9 @@ typedef struct {
     double *path_xy;        /* [total][2]  main_work.path then headland.path (mlp3:411) */
     double *speeds_kmh;     /* [total]     adjusted speeds (mlp3:415-420) */
     double *curvature;      /* [total] or NULL: kappa per point (0 at both ends) */
+    int64_t path_capacity;  /* > 0: points the path buffers hold.  A caller that keeps buffers from an earlier batch
+                               (no read-back of the layout's total) sets it: a plan whose points would not fit gets
+                               status FCPP_CAND_TOO_LARGE instead of being written; 0 = unchecked */
 } fcpp_outputs;
 
 int fcpp_abi_version(void);
