@@ -319,8 +319,17 @@ class BatchBuffers:
                     self.d_kap = torch.empty(total_points, dtype=torch.float64, device=dev)
 
 
+def corner_grids(words: np.ndarray, g: int) -> np.ndarray:
+    """[4, g, g] bool occupancy grids (grid[c][j, i] = lattice point (i, j) of corner c, mlp3:1477) from one
+    candidate's ``corner_bits`` words (fcpp_outputs.corner_bits layout)."""
+    rw = (g + 31) // 32
+    w = np.ascontiguousarray(words[:4 * g * rw], dtype=np.uint32).reshape(4, g, rw)
+    bits = np.unpackbits(w.view(np.uint8).reshape(4, g, rw * 4), axis=2, bitorder="little")
+    return bits[:, :, :g].astype(bool)
+
+
 def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, cost: str, cand_base: int,
-                         buffers: Optional["BatchBuffers"], path_alloc=None):
+                         buffers: Optional["BatchBuffers"], path_alloc=None, corner_bits: bool = False):
     """Enqueue layout, prefix sum, plan, coverage and argmin kernels of one batch on torch's current
     stream.  Returns (buffers, offsets or None).  Without ``buffers`` the path storage is sized from
     the layout pass (one small synchronous read-back); ``path_alloc(total) -> BatchBuffers | None``
@@ -361,6 +370,15 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
                     raise ValueError("buffers were allocated without path storage")
                 h.check(L.fcpp_layout(h.h, C.byref(db.c), None, buffers.d_off.data_ptr(), stream))
         out.summary = buffers.d_sum.data_ptr()
+        if corner_bits:
+            # occupancy bits of the four verification corner windows (mlp3:1503-1510 'grid'), sized by the largest R
+            g = int(2 * float(db.pb.arrays["cand_R"].max()) / 0.1) if B else 1
+            stride = 4 * g * ((g + 31) // 32)
+            if getattr(buffers, "d_cbits", None) is None or buffers.d_cbits.numel() < B * stride:
+                buffers.d_cbits = torch.zeros(max(B * stride, 1), dtype=torch.int32, device=dev)
+            buffers.cbits_stride = stride
+            out.corner_bits = buffers.d_cbits.data_ptr()
+            out.corner_bits_stride = stride
         if outputs == "paths":
             out.offsets = buffers.d_off.data_ptr()
             out.path_xy = buffers.d_path.data_ptr()
@@ -478,16 +496,19 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
 def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
                      cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
                      buffers: Optional[BatchBuffers] = None, fetch: bool = True,
-                     winners: bool = False) -> Optional[BatchResult]:
+                     winners: bool = False, corner_bits: bool = False) -> Optional[BatchResult]:
     """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
 
     With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
     whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only.
     ``winners``: also bring every field's winning path and speeds to the host (``fetch_winner_paths``)."""
-    buffers, offsets = _launch_device_batch(db, outputs, want_curvature, cost, cand_base, buffers)
+    buffers, offsets = _launch_device_batch(db, outputs, want_curvature, cost, cand_base, buffers,
+                                            corner_bits=corner_bits)
     if not fetch:
         return None
     res = _fetch_device_batch(db, buffers, outputs, offsets, copy_summary, cand_base)
+    if corner_bits:   # [B, stride] words on the device; batch.corner_grids() unpacks one candidate's
+        res.extras["corner_bits"] = buffers.d_cbits[:db.pb.n_cand * buffers.cbits_stride].view(db.pb.n_cand, -1)
     res.extras["h2d_bytes"] = db.pb.h2d_bytes()
     res.extras["d2h_bytes"] = (len(res.summary) * _lib.SUMMARY_DTYPE.itemsize + 16 * db.pb.n_fields
                                + ((db.pb.n_cand + 1) * 8 if outputs == "paths" else 0))

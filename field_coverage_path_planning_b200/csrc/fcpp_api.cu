@@ -149,6 +149,7 @@ const char *fcpp_last_error(const fcpp_handle *h) { return h ? h->err : "invalid
 
 int64_t fcpp_launch_count(const fcpp_handle *h) { return h ? h->launches : 0; }
 
+int32_t fcpp_last_fused(const fcpp_handle *h) { return h ? h->last_fused : 0; }
 int32_t fcpp_last_max_points(const fcpp_handle *h) { return h ? h->last_maxn : 0; }
 int32_t fcpp_last_max_head_points(const fcpp_handle *h) { return h ? h->last_maxhead : 0; }
 int64_t fcpp_last_total_points(const fcpp_handle *h) { return h ? h->last_total : -1; }
@@ -265,13 +266,27 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
         if (rc) return rc;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
-    int ncap = 0;
-    cudaError_t e = fcpp_launch_plan(h, *batch, *out, st, &ncap);
-    if (e != cudaSuccess) return cuda_fail(h, e, "plan kernel");
-    if (prof) cudaEventRecord(h->ev[2], st);
+    cudaError_t e;
+    h->last_fused = 0;
     if (batch->do_coverage) {
-        e = fcpp_launch_cover(h, *batch, *out, st);
-        if (e != cudaSuccess) return cuda_fail(h, e, "coverage kernel");
+        // plan + coverage: ONE fused kernel with CTA roles when it fits (fcpp_hot.cu), else two launches — the
+        // second event then sits between them
+        int fused = 0;
+        if (prof && (h->cover_mode & 4)) {
+            e = fcpp_launch_plan(h, *batch, *out, st, nullptr);
+            if (e != cudaSuccess) return cuda_fail(h, e, "plan kernel");
+            cudaEventRecord(h->ev[2], st);
+            e = fcpp_launch_cover(h, *batch, *out, st);
+        } else {
+            if (prof) cudaEventRecord(h->ev[2], st);
+            e = fcpp_launch_plan_cover(h, *batch, *out, st, &fused);
+        }
+        if (e != cudaSuccess) return cuda_fail(h, e, "plan / coverage kernels");
+        h->last_fused = fused;
+    } else {
+        e = fcpp_launch_plan(h, *batch, *out, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(h, e, "plan kernel");
+        if (prof) cudaEventRecord(h->ev[2], st);
     }
     if (prof) cudaEventRecord(h->ev[3], st);
     h->layout_valid = false;  // one layout per plan call

@@ -646,7 +646,7 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
         }
         if (words > 12ll * TW) okz = false;
 #ifdef FCPP_COVER_DEBUG
-        if (tid == 0 && (blockIdx.x % 512) == 0) {
+        if (tid == 0 && (blockIdx.x % 512) == 0) {  // (debug builds only)
             printf("cand %d nrect %d okz %d words %lld\n", (int)blockIdx.x, nr, (int)okz, words);
             for (int z = 0; z < 4; ++z) printf("  zone %d cols [%d,%d] rows [%d,%d]\n", z, s.zbox[z].x, s.zbox[z].y, s.zbox[z].z, s.zbox[z].w);
         }
@@ -818,21 +818,23 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
     return true;
 }
 
-__global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
-                                                     const TrigTables *__restrict__ trig,
-                                                     fcpp_summary *__restrict__ summary, int pc, int mode,
-                                                     const int32_t *__restrict__ rep /*[2][n_cand]*/)
+// One candidate's coverage by the T threads of a CTA (stand-alone cover_kernel, or a coverage-role CTA of the fused
+// plan + coverage kernel in fcpp_hot.cu).
+__device__ __forceinline__ void cover_body(const fcpp_batch &b, const CandRec *__restrict__ recs,
+                                           const TrigTables *__restrict__ trig, fcpp_summary *__restrict__ summary,
+                                           int pc, int mode, const int32_t *__restrict__ rep /*[2][n_cand]*/,
+                                           uint32_t *__restrict__ corner_bits, int64_t corner_bits_stride,
+                                           const int64_t cand)
 {
     // a part (A10 corner windows / A11 band) whose inputs equal those of an earlier candidate is
     // skipped: the candidate takes that one's counts afterwards (cover_copy_kernel).  A10 does not
     // depend on the start corner or the heading, A11 not on the heading.
-    const bool do10 = !rep || rep[blockIdx.x] == (int32_t)blockIdx.x;
-    const bool do11 = !rep || rep[b.n_cand + blockIdx.x] == (int32_t)blockIdx.x;
+    const bool do10 = !rep || rep[cand] == (int32_t)cand;
+    const bool do11 = !rep || rep[b.n_cand + cand] == (int32_t)cand;
     if (!do10 && !do11) return;
     CoverFixed &s = *reinterpret_cast<CoverFixed *>(cover_smem);
     const CoverDyn d;
     const int tid = threadIdx.x;
-    const int64_t cand = blockIdx.x;
     fcpp_summary *sum = summary + cand;
 
     if (tid == 0) mbar_init(&s.bar, 1);
@@ -955,6 +957,13 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
                 for (int c = 0; c < group; ++c) {
                     const int n = count_words(s.tile + c * cstride, nrows * rw);
                     if (n) atomicAdd(&s.cnt[4 + c], n);
+                }
+                if (corner_bits && (int64_t)4 * g * rw <= corner_bits_stride) {  // the 'grid' of mlp3:1503-1510
+                    uint32_t *dst = corner_bits + cand * corner_bits_stride;
+                    for (int k = tid; k < group * nrows * rw; k += T) {
+                        const int c = k / (nrows * rw), w = k - c * nrows * rw;
+                        dst[((int64_t)(c0 + c) * g + j0) * rw + w] = s.tile[c * cstride + w];
+                    }
                 }
                 __syncthreads();
                 for (int c = 0; c < group; ++c) {
@@ -1136,6 +1145,16 @@ __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fc
     if (tid == 0 && (err10 | err11)) sum->status |= FCPP_CAND_GRID_TOO_LARGE;
 }
 
+__global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
+                                                                        const TrigTables *__restrict__ trig,
+                                                                        fcpp_summary *__restrict__ summary, int pc, int mode,
+                                                                        const int32_t *__restrict__ rep,
+                                                                        uint32_t *__restrict__ corner_bits,
+                                                                        int64_t corner_bits_stride)
+{
+    cover_body(b, recs, trig, summary, pc, mode, rep, corner_bits, corner_bits_stride, blockIdx.x);
+}
+
 int cover_point_capacity(int max_head)
 {
     const int pc = max_head > 4 * VPOLY_CAP ? max_head : 4 * VPOLY_CAP;
@@ -1236,18 +1255,24 @@ __global__ void __launch_bounds__(128) cover_copy_kernel(fcpp_summary *__restric
 
 }  // namespace
 
-cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st)
-{
-    if (b.n_cand == 0) return cudaSuccess;
-    int pc = cover_point_capacity(h->cover_pcap);
-    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + 16) pc -= 64;
-    const size_t bytes = cover_smem_bytes(pc);
-    cudaError_t e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    // de-duplication (asked for by the batch, unless switched off by cover mode bit 1)
+// What a coverage launch needs besides the batch: shared-memory size and the de-duplication tables.
+struct CoverLaunch {
+    int pc = 0;
+    size_t bytes = 0;
     int32_t *d_rep = nullptr;
     unsigned long long *keys = nullptr, *hash = nullptr;
     unsigned int *vals = nullptr;
+};
+
+// sizes + (when the batch asks for it) the de-duplication kernels that precede the coverage kernel
+static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream_t st, CoverLaunch &L)
+{
+    int pc = cover_point_capacity(h->cover_pcap);
+    while (cover_smem_bytes(pc) > (size_t)h->max_smem_optin && pc > 4 * VPOLY_CAP + 16) pc -= 64;
+    L.pc = pc;
+    L.bytes = cover_smem_bytes(pc);
+    cudaError_t e = cudaSuccess;
+    // de-duplication (asked for by the batch, unless switched off by cover mode bit 1)
     const int64_t n = b.n_cand;
     if (b.cover_dedupe && n > 1 && !(h->cover_mode & 2) && n < (1ll << 28)) {
         uint32_t cap = 1024;
@@ -1264,27 +1289,49 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
         }
         // layout: keys [cap] | vals [cap] | hash / slot [2][n] | rep [2][n]; a different capacity moves the
         // arrays, so the table is zeroed again
-        keys = (unsigned long long *)h->d_dedupe;
-        vals = (unsigned int *)(keys + cap);
-        hash = (unsigned long long *)(vals + cap);
-        d_rep = (int32_t *)(hash + 2 * n);
+        L.keys = (unsigned long long *)h->d_dedupe;
+        L.vals = (unsigned int *)(L.keys + cap);
+        L.hash = (unsigned long long *)(L.vals + cap);
+        L.d_rep = (int32_t *)(L.hash + 2 * n);
         if (h->dedupe_cap != cap) {
             e = cudaMemsetAsync(h->d_dedupe, 0, (size_t)cap * 12, st);
             if (e != cudaSuccess) return e;
             h->dedupe_cap = cap;
         }
         const unsigned g = (unsigned)((n + 127) / 128);
-        cover_key_kernel<<<g, 128, 0, st>>>(h->d_rec, n, keys, vals, cap - 1, hash);
-        cover_rep_kernel<<<g, 128, 0, st>>>(h->d_rec, n, keys, vals, cap - 1, hash, d_rep);
+        cover_key_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash);
+        cover_rep_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash, L.d_rep);
         h->launches += 2;
+        e = cudaGetLastError();
     }
-    cover_kernel<<<(unsigned)b.n_cand, T, bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, pc, h->cover_mode, d_rep);
+    return e;
+}
+
+// hands the representatives' counts to the other members of their groups and empties the hash table
+static cudaError_t cover_finish(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
+                                const CoverLaunch &L)
+{
+    if (!L.d_rep) return cudaSuccess;
+    const int64_t n = b.n_cand;
+    cover_copy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(o.summary, n, L.d_rep, L.keys, L.vals, L.hash);
     h->launches++;
-    if (d_rep) {
-        cover_copy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(o.summary, n, d_rep, keys, vals, hash);
-        h->launches++;
-    }
     return cudaGetLastError();
+}
+
+cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st)
+{
+    if (b.n_cand == 0) return cudaSuccess;
+    CoverLaunch L;
+    cudaError_t e = cover_prepare(h, b, st, L);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes);
+    if (e != cudaSuccess) return e;
+    cover_kernel<<<(unsigned)b.n_cand, T, L.bytes, st>>>(b, h->d_rec, h->d_trig, o.summary, L.pc, h->cover_mode, L.d_rep,
+                                                          o.corner_bits, o.corner_bits_stride);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cover_finish(h, b, o, st, L);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -82,7 +82,8 @@ struct fcpp_handle {
     int64_t last_total;      // total points of the last synchronous layout pass with offsets (-1: unknown)
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
     int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation,
-                             // bit 1 = no coverage de-duplication
+                             // bit 1 = no coverage de-duplication, bit 2 = plan and coverage as two launches
+    int last_fused;          // the last fcpp_plan_batch ran the fused plan + coverage kernel
     void *d_dedupe;          // coverage de-duplication: hash table, hashes, representatives
     size_t dedupe_bytes;
     uint32_t dedupe_cap;     // slots of the (currently zeroed) table inside d_dedupe; 0 = not initialised
@@ -588,6 +589,8 @@ cudaError_t fcpp_launch_layout(fcpp_handle *h, const fcpp_batch &b, int32_t *d_n
 cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
                              int *too_large);
 cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st);
+cudaError_t fcpp_launch_plan_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
+                                   int *fused_out);
 cudaError_t fcpp_launch_speed_verify(fcpp_handle *h, const fcpp_vehicle &veh, const double *d_path,
                                      const double *d_speeds_in, const int64_t *d_offsets, int64_t n_paths,
                                      int64_t max_len, int do_speed_plan, double *d_speeds_out, double *d_curv,

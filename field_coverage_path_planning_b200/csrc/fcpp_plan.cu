@@ -84,6 +84,16 @@ __device__ inline Smem carve(unsigned char *base, int ncap)
     return s;
 }
 
+// Barrier of the group of threads that works on one plan: the whole CTA in the stand-alone kernels, a 128-thread
+// quarter of a 512-thread CTA (named barrier) when four plans share a CTA of the fused plan + coverage kernel
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct QuarterSync {
+    int id;  // hardware barrier 1 .. 4
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // min-plus scan element: the map u -> min(M, u + C)
 // ---------------------------------------------------------------------------------------------
@@ -107,9 +117,10 @@ __device__ __forceinline__ MP mp_shfl_up(const MP &v, int d)
 
 // exclusive block scan of per-thread aggregates in thread order; returns the carry-in value
 // (the M of the composition of all earlier threads; +inf for thread 0)
-__device__ __forceinline__ double mp_block_exclusive(MP agg, double *sh /*>= 2*NWARP*/)
+template <class Sync>
+__device__ __forceinline__ double mp_block_exclusive(MP agg, double *sh /*>= 2*NWARP*/, int tid, const Sync &sync)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     MP inc = agg;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -120,8 +131,8 @@ __device__ __forceinline__ double mp_block_exclusive(MP agg, double *sh /*>= 2*N
         sh[2 * warp] = inc.C;
         sh[2 * warp + 1] = inc.M;
     }
-    __syncthreads();
-    // composition of all earlier warps (serial over <= 8 warps)
+    sync();
+    // composition of all earlier warps (serial over the few warps of the group)
     MP pre;
     pre.C = 0.0;
     pre.M = INFINITY;
@@ -138,7 +149,7 @@ __device__ __forceinline__ double mp_block_exclusive(MP agg, double *sh /*>= 2*N
         ex.M = INFINITY;
     }
     const MP tot = mp_combine(pre, ex);
-    __syncthreads();
+    sync();
     return tot.M;
 }
 
@@ -155,20 +166,20 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// reduce NV sums / maxes across the block (deterministic order); result valid in thread 0
-template <int NV, bool IS_MAX, int NWARP>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], double *sh)
+// reduce NV sums / maxes across the group (deterministic order); result valid in thread 0
+template <int NV, bool IS_MAX, int NWARP, class Sync>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *sh, int tid, const Sync &sync)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) v[k] = IS_MAX ? warp_max(v[k]) : warp_sum(v[k]);
-    __syncthreads();
+    sync();
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) sh[warp * NV + k] = v[k];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    sync();
+    if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             double a = sh[k];
@@ -250,6 +261,12 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
 // ---------------------------------------------------------------------------------------------
 // GEN: one generated plan per CTA
 // ---------------------------------------------------------------------------------------------
+#ifndef FCPP_PLAN_GEN_THREADS
+#define FCPP_PLAN_GEN_THREADS 128
+#endif
+constexpr int TG = FCPP_PLAN_GEN_THREADS;
+static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 + 4 * FCPP_MAX_LOOPS - 1 in two rounds");
+
 // shared memory of the generated-plan kernel: fixed part (compile-time offsets) + obstacle tables + the staging of
 // the `ncap` staged points (first 2 + last 22 main points + headland): ds, kappa, u (FP64) and the structure tag
 struct GenFixed {
@@ -259,7 +276,7 @@ struct GenFixed {
     double tpts[2 * TPL_PTS];
     double geo[20];              // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
     double gvl[N_GENERIC];       // curvature-limited speed of the generic points
-    double scratch[SCRATCH];
+    double scratch[9 * (FCPP_PLAN_GEN_THREADS / 32) + 8];  // group reductions: 9 values per warp; scans: 2 per warp
     double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
     double chain_sum[8];           // per regular chain: length, time (initial speeds), time (final speeds),
                                    // accel violations, max kappa, max a_lat, max kappa jump
@@ -368,24 +385,20 @@ __device__ __forceinline__ void point_tests(const GenSmem &s, int n_obs_poly, do
     n_oviol += hit;
 }
 
-#ifndef FCPP_PLAN_GEN_THREADS
-#define FCPP_PLAN_GEN_THREADS 128
-#endif
-constexpr int TG = FCPP_PLAN_GEN_THREADS;
-static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 + 4 * FCPP_MAX_LOOPS - 1 in two rounds");
 
-__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs a)
+// One generated plan by the TG threads of a group (tid = 0 .. TG-1) in their own shared-memory region.
+template <class Sync>
+__device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *smem, const int tid, const int64_t cand,
+                                              const Sync &sync)
 {
     constexpr int T = TG;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GenSmem s = gen_carve(smem_raw, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    const GenSmem s = gen_carve(smem, a.ncap, a.obs_cap_verts, a.obs_cap_polys);
     GenFixed &f = *s.f;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t cand = blockIdx.x;
+    const int lane = tid & 31;
     const fcpp_vehicle &veh = a.b.vehicle;
     fcpp_summary *sum = a.out.summary ? a.out.summary + cand : nullptr;
     if (tid == 0) mbar_init(&f.bar, 1);
-    __syncthreads();
+    sync();
 
     int n_obs_poly = 0;
     {
@@ -409,7 +422,14 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
         for (int k = tid; k < (int)(sizeof(TrigTables) / sizeof(double)); k += T)
             ((double *)&f.tt)[k] = ((const double *)a.trig)[k];
         for (int k = tid; k < N_GENERIC; k += T) f.glist[k] = -1;
-        mbar_wait_block(&f.bar, 0);
+        // ONE thread polls the mbarrier, the group barrier releases the rest, and every thread then observes the
+        // completed phase itself (acquire of the async-proxy writes)
+        if (tid == 0)
+            while (!mbar_try_wait(&f.bar, 0)) {
+            }
+        sync();
+        while (!mbar_try_wait(&f.bar, 0)) {
+        }
     }
     const CandRec &r = f.rec;
     if (a.b.obs_poly_start) {
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
             return;
         }
     }
-    __syncthreads();  // obs_vs is complete
+    sync();  // obs_vs is complete
     const double W = veh.working_width;
     TurnModel tm;
     tm.model = a.b.turn_model;
@@ -507,7 +527,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
         s.obs_bb[4 * p + 2] = x1 + rr + 1e-6;
         s.obs_bb[4 * p + 3] = y1 + rr + 1e-6;
     }
-    __syncthreads();
+    sync();
     // one thread per table slot (two rounds when the CTA has fewer threads than slots' thread ids)
     for (int vt = tid; vt < 96 + 4 * FCPP_MAX_LOOPS; vt += T) {
         int slot = -1;
@@ -569,7 +589,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
             f.tbl[slot] = e;
         }
     }
-    __syncthreads();
+    sync();
 
     // ------------------------------------------------------------------------------------
     // phase 0b (warp 0): the regular chain once — acceleration passes over its 22 points (a zero-length segment
@@ -662,7 +682,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
         }
         point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
     }
-    __syncthreads();  // glist, chain_v
+    sync();  // glist, chain_v
     // ------------------------------------------------------------------------------------
     // phase 1b: the regular chains' points (most of a plan): generated, tested, written with the chain's speeds
     // ------------------------------------------------------------------------------------
@@ -725,7 +745,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
             }
         }
     }
-    __syncthreads();
+    sync();
 
     // ------------------------------------------------------------------------------------
     // phases 3 / 4 over the staged sequence (the zero-length segment after point 1 separates the two staged ends
@@ -745,7 +765,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
                 agg.M = fmin(s.U[q], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, f.scratch);
+            double carry = mp_block_exclusive(agg, f.scratch, tid, sync);
             for (int q = cs; q < ce; ++q) {
                 const double dsp = (q > 0) ? s.X[q - 1] : 0.0;
                 const double c = (q > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
@@ -753,7 +773,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
                 s.U[q] = carry;
             }
         }
-        __syncthreads();
+        sync();
         {
             const int rt = T - 1 - tid;
             const int rs = min(NS, rt * chunk);
@@ -767,7 +787,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
                 agg.M = fmin(s.U[q], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, f.scratch);
+            double carry = mp_block_exclusive(agg, f.scratch, tid, sync);
             for (int q = re - 1; q >= rs; --q) {
                 const double dsn = s.X[q];
                 const double c = (q + 1 < NS && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
@@ -775,7 +795,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
                 s.U[q] = carry;
             }
         }
-        __syncthreads();
+        sync();
     }
 
     // ------------------------------------------------------------------------------------
@@ -827,7 +847,7 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
         }
         finish_point(act, act ? (i < 2 ? i : i - n_skip) : 0, u_lim, vl);
     }
-    __syncthreads();
+    sync();
     // ------------------------------------------------------------------------------------
     // phase 5b: work time with the adjusted speeds (mlp3:423-431, :1298-1311)
     // ------------------------------------------------------------------------------------
@@ -844,8 +864,8 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
     }
     double sums[9] = {acc_len_m, acc_len_h, acc_tpre_m, acc_tpre_h, acc_t_m,
                       acc_t_h,   (double)n_aviol, (double)n_bviol, (double)n_oviol};
-    block_reduce<9, false, T / 32>(sums, f.scratch);
-    block_reduce<3, true, T / 32>(mx, f.scratch);
+    block_reduce<9, false, T / 32>(sums, f.scratch, tid, sync);
+    block_reduce<3, true, T / 32>(mx, f.scratch, tid, sync);
     if (tid == 0 && sum) {
         // the regular chains: one chain's sums times their number
         const double nreg = (double)(n_skip / CHAIN_POINTS);
@@ -869,6 +889,12 @@ __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs 
             for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
         }
     }
+}
+
+__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    plan_gen_body(a, smem_raw, threadIdx.x, blockIdx.x, CtaSync());
 }
 
 // One caller-supplied path (A7 / A8 / A13 of the drop-in API): every point from its coordinates.
@@ -975,7 +1001,7 @@ __device__ __forceinline__ void plan_body_path(const PlanArgs &a, const Smem &s,
                 agg.M = fmin(s.U[i], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, s.scratch);
+            double carry = mp_block_exclusive(agg, s.scratch, tid, CtaSync());
             for (int i = cs; i < ce; ++i) {
                 const double dsp = (i > 0) ? s.X[i - 1] : 0.0;
                 const double c = (i > 0 && !(dsp < FCPP_ZERO_LEN)) ? two_a * dsp : INFINITY;
@@ -997,7 +1023,7 @@ __device__ __forceinline__ void plan_body_path(const PlanArgs &a, const Smem &s,
                 agg.M = fmin(s.U[i], agg.M + c);
                 agg.C = agg.C + c;
             }
-            double carry = mp_block_exclusive(agg, s.scratch);
+            double carry = mp_block_exclusive(agg, s.scratch, tid, CtaSync());
             for (int i = re - 1; i >= rs; --i) {
                 const double dsn = s.X[i];
                 const double c = (i + 1 < N && !(dsn < FCPP_ZERO_LEN)) ? two_a * dsn : INFINITY;
@@ -1043,8 +1069,8 @@ __device__ __forceinline__ void plan_body_path(const PlanArgs &a, const Smem &s,
     for (int i = tid; i + 1 < N; i += T)
         acc_t_m += div_z(s.X[i], fmax(div36((s.U[i] + s.U[i + 1]) / 2), FCPP_MIN_SPEED_MS));
     double sums[4] = {acc_len_m, acc_tpre_m, acc_t_m, (double)n_aviol};
-    block_reduce<4, false, T / 32>(sums, s.scratch);
-    block_reduce<3, true, T / 32>(mx, s.scratch);
+    block_reduce<4, false, T / 32>(sums, s.scratch, tid, CtaSync());
+    block_reduce<3, true, T / 32>(mx, s.scratch, tid, CtaSync());
     if (tid == 0 && sum) {
         sum->status = 0;
         sum->n_passes = 0;
@@ -1185,11 +1211,9 @@ cudaError_t launch_big(fcpp_handle *h, PlanArgs &a, int64_t n_items, int max_poi
 // Generated plans: one CTA per candidate.  Only the first 2 + last 22 main points and the headland are staged in
 // shared memory (~25 B per point), so the staging depends on the longest HEADLAND of the batch, not on the plan
 // length: no length tiers, no HBM staging, 7-8 CTAs of 128 threads per SM at every field size.
-cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
-                             int *ncap_out)
+static size_t plan_gen_args(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, PlanArgs &a)
 {
-    if (b.n_cand == 0) return cudaSuccess;
-    PlanArgs a{};
+    a = PlanArgs{};
     a.b = b;
     a.recs = h->d_rec;
     a.trig = h->d_trig;
@@ -1197,9 +1221,17 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     a.obs_cap_verts = b.obs_poly_start ? b.max_obs_verts : 0;
     a.obs_cap_polys = b.obs_poly_start ? b.max_obs_polys : 0;
     a.ncap = (MAIN_STAGED + (h->cover_pcap > 0 ? h->cover_pcap : 0) + 63) / 64 * 64;
-    if (ncap_out) *ncap_out = a.ncap;
     a.n_items = b.n_cand;
-    const size_t bytes = gen_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+    return gen_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys);
+}
+
+cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_outputs &o, cudaStream_t st,
+                             int *ncap_out)
+{
+    if (b.n_cand == 0) return cudaSuccess;
+    PlanArgs a;
+    const size_t bytes = plan_gen_args(h, b, o, a);
+    if (ncap_out) *ncap_out = a.ncap;
     if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;  // obstacle tables / headland beyond shared memory
     cudaError_t e = cudaFuncSetAttribute(plan_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;

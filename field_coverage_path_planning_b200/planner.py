@@ -22,7 +22,7 @@ import torch
 
 from . import _geometry as G
 from . import _lib
-from .batch import DeviceBatch, _dev, prepare_batch, run_device_batch
+from .batch import DeviceBatch, _dev, corner_grids, prepare_batch, run_device_batch
 from .vehicle import VehicleParams
 
 APPROACH_POINTS = 50  # mlp3:1317
@@ -55,6 +55,7 @@ class TwoLayerPathPlannerV37:
         self.start_point = self._validate_point(start_point)
         self.end_point = self._validate_point(end_point)
         self._last = None
+        self._last_grids = None
 
     # ---- A2: field set-up (host, FP64) -----------------------------------------------------
     def _process_field_input(self, field_length, field_width, field_vertices):
@@ -139,7 +140,7 @@ class TwoLayerPathPlannerV37:
         if not self.start_point:
             pb.arrays["cand_flags"] &= ~np.int32(_lib.FLAG_REVERSE_ORDER | _lib.FLAG_START_FROM_RIGHT)
         db = DeviceBatch(pb, _dev(self._device), pin=False)
-        res = run_device_batch(db, outputs="paths")
+        res = run_device_batch(db, outputs="paths", corner_bits=True)
         s = res.summary[0]
         if s["status"] & _lib.CAND_INSET_EMPTY:
             raise ValueError(f"田头宽度{self.headland_width}m过大，无法定义主作业区域")  # mlp3:598
@@ -172,6 +173,8 @@ class TwoLayerPathPlannerV37:
         if self.end_point:     # mlp3:443-447
             departure = self._generate_departure_path(head['path'][-1], self.end_point)
         self._last = s
+        self._last_grids = corner_grids(res.extras["corner_bits"][0].cpu().numpy().view(np.uint32), int(s["corner_g"])) \
+            if not (s["status"] & _lib.CAND_GRID_TOO_LARGE) else None
         result = {'main_work': main, 'headland': head, 'approach_path': approach, 'departure_path': departure,
                   'total_time': time.time() - t0, 'version': 'V3.5.1',
                   'features': ['真正两层', '切线倒车', '网格验证', '强制降速', '智能起点'],
@@ -284,10 +287,20 @@ class TwoLayerPathPlannerV37:
             self.plan_complete_coverage()
         s = self._last
         g2 = float(int(s["corner_g"]) ** 2)
+        R, hw = self.vehicle.min_turn_radius, self.headland_width
+        # mlp3:1531-1536 corner positions and mlp3:1461-1468 window origins
+        pos = [(hw, hw), (self.field_length - hw, hw), (self.field_length - hw, self.field_width - hw),
+               (hw, self.field_width - hw)]
         corners = []
         for c in range(4):
             b, a = int(s["corner_before"][c]) / g2 * 100, int(s["corner_after"][c]) / g2 * 100
+            x, y = pos[c]
+            origin = (x if c in (0, 3) else x - 2 * R, y if c in (0, 1) else y - 2 * R)
             corners.append({'coverage_before': b, 'coverage_after': a, 'improvement': a - b,
+                            # the occupancy grid after the reverse fill, grid[j, i] (mlp3:1477, :1503-1510): written
+                            # out by the coverage kernel from its shared-memory tile
+                            'grid': self._last_grids[c] if self._last_grids is not None else None,
+                            'grid_origin': origin,
                             'cells_before': int(s["corner_before"][c]), 'cells_after': int(s["corner_after"][c]),
                             'grid_resolution': GRID_RESOLUTION})
         ab = float(np.mean([c['coverage_before'] for c in corners]))

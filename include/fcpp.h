@@ -163,6 +163,13 @@ typedef struct {
     int64_t path_capacity;  /* > 0: points the path buffers hold.  A caller that keeps buffers from an earlier batch
                                (no read-back of the layout's total) sets it: a plan whose points would not fit gets
                                status FCPP_CAND_TOO_LARGE instead of being written; 0 = unchecked */
+    uint32_t *corner_bits;  /* optional: the occupancy bits of the four verification corner windows AFTER the reverse
+                               fill (the 'grid' of mlp3:1503-1510).  Candidate b, corner c, lattice row j (g =
+                               corner_g rows of rw = (g + 31) / 32 words): word corner_bits[b * corner_bits_stride
+                               + (c * g + j) * rw + w], bit i & 31 of word i >> 5 = lattice point (i, j).  Written
+                               only for candidates whose corner windows are rasterised (every candidate when
+                               cover_dedupe = 0). */
+    int64_t corner_bits_stride; /* words per candidate, >= 4 * g * rw of the largest window */
 } fcpp_outputs;
 
 int fcpp_abi_version(void);
@@ -332,6 +339,9 @@ int64_t fcpp_last_total_points(const fcpp_handle *h);
  * CUDA events on the launching stream; fcpp_kernel_times (call after synchronising the stream)
  * returns the milliseconds of the last call: [0] layout (+scan), [1] plan, [2] coverage. */
 int fcpp_set_profiling(fcpp_handle *h, int on);
+/* 1 when the last fcpp_plan_batch ran plan and coverage as ONE fused kernel (CTA roles, fcpp_hot.cu): the kernel
+ * times then are [0] layout, [1] ~0, [2] the fused kernel.  fcpp_set_cover_mode bit 2 forces two launches. */
+int32_t fcpp_last_fused(const fcpp_handle *h);
 int fcpp_kernel_times(fcpp_handle *h, float *ms3);
 
 /* Diagnostics: coverage-kernel evaluation mode of the following fcpp_plan_batch calls.  0 = automatic
@@ -339,7 +349,8 @@ int fcpp_kernel_times(fcpp_handle *h, float *ms3);
  * (bitmap around the corners, closed form elsewhere), any other field row-tiled.  Bit 0 set = always
  * row-tiled.  Bit 1 set = no coverage de-duplication (by default candidates whose coverage inputs are
  * identical — same field, R, start corner; e.g. the headings of a heading search — are rasterised once
- * and share the counts).  All modes give identical counts (tests/test_gpu_parity.py compares them). */
+ * and share the counts).  Bit 2 set = plan and coverage kernels as two launches instead of the fused kernel.
+ * All modes give identical results (tests/test_gpu_parity.py compares them). */
 int fcpp_set_cover_mode(fcpp_handle *h, int mode);
 
 #ifdef __cplusplus

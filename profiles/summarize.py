@@ -84,7 +84,7 @@ def main(rep, traffic_out=None, workload="c2"):
                     pass
         print("\nTop warp stall reasons (warps stalled per issue-active cycle): " +
               ", ".join(f"{n} {v:.2f}" for v, n in sorted(st, reverse=True)[:6]) + "\n")
-    for pat in ("cover_kernel", "plan_kernel"):
+    for pat in ("cover_kernel", "plan_gen_kernel", "path_kernel"):
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv",
                               "--kernel-name", f"regex:{pat}"], capture_output=True, text=True).stdout
         if "Instructions Executed" not in src:

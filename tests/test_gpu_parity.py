@@ -588,3 +588,29 @@ def test_big_plan_workspace_survives_layout_passes(fc):
         res = fc.plan_batch([RECT], fc.VehicleParams(), cand, coverage=False)
         assert (res.summary["status"] == 0).all()
         assert np.abs(pl._apply_curvature_based_speed_limit(path, speeds) - want).max() <= 1e-9
+
+
+def test_verify_all_corners_returns_grid_and_origin(fc):
+    """mlp3:1503-1510, :1561: every corner record of verify_all_corners_coverage carries 'grid' (occupancy after
+    the reverse fill) and 'grid_origin' — written out by the coverage kernel, compared bit for bit with the
+    brute-force oracle's window raster of the same verification polylines."""
+    from oracle import raster, ref_planner as rp
+    for R, L, Wd in ((8.0, 500, 200), (9.6, 300, 150), (5.0, 100, 80)):
+        pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(min_turn_radius=R), field_length=L, field_width=Wd)
+        r = pl.plan_complete_coverage()
+        cov = pl.verify_all_corners_coverage(r["headland"])
+        fs = rp.setup_field(rp.VehicleParams(min_turn_radius=R), field_length=L, field_width=Wd)
+        g = int(2 * R / 0.1)
+        for k, ((cx, cy), ci, arc, rev) in enumerate(rp.verification_corner_paths(fs)):
+            c = cov["corners"][k]
+            ox = cx if ci in (0, 3) else cx - 2 * R
+            oy = cy if ci in (0, 1) else cy - 2 * R
+            assert c["grid_origin"] == (ox, oy) and c["grid_resolution"] == 0.1
+            n1, bits = raster.raster_window(arc, 3.2 / 2, (ox, oy), 0.1, g, g)
+            n2 = n1
+            if rev is not None and len(rev) > 0:
+                n2, bits = raster.raster_window(rev, 3.2 / 2, (ox, oy), 0.1, g, g, bits)
+            want = np.unpackbits(bits, bitorder="little")[:g * g].reshape(g, g).astype(bool)
+            assert c["grid"].shape == (g, g) and c["grid"].dtype == bool
+            assert np.array_equal(c["grid"], want), (R, k)
+            assert (c["cells_before"], c["cells_after"]) == (n1, n2) and int(c["grid"].sum()) == n2
