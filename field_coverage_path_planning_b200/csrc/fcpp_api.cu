@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fcpp_internal.cuh"
@@ -122,6 +123,9 @@ int fcpp_create(int device, fcpp_handle **out)
         fcpp_destroy(h);
         return FCPP_ERR_CUDA;
     }
+#ifdef FCPP_COVER_EXPERIMENT
+    if (getenv("FCPP_EXP")) h->cover_mode = atoi(getenv("FCPP_EXP"));
+#endif
     *out = h;
     return FCPP_OK;
 }
@@ -269,13 +273,13 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
     cudaError_t e;
     h->last_fused = 0;
     if (batch->do_coverage) {
-        // plan + coverage: ONE fused kernel with CTA roles when it fits (fcpp_hot.cu), else two launches — the
-        // second event then sits between them
+        // plan + coverage: two launches (the profiling event sits between them), or — opt-in, cover mode bit 2 —
+        // ONE fused kernel with CTA roles when it fits (fcpp_hot.cu)
         int fused = 0;
-        if (prof && (h->cover_mode & 4)) {
+        if (!(h->cover_mode & 4)) {
             e = fcpp_launch_plan(h, *batch, *out, st, nullptr);
             if (e != cudaSuccess) return cuda_fail(h, e, "plan kernel");
-            cudaEventRecord(h->ev[2], st);
+            if (prof) cudaEventRecord(h->ev[2], st);
             e = fcpp_launch_cover(h, *batch, *out, st);
         } else {
             if (prof) cudaEventRecord(h->ev[2], st);

@@ -596,7 +596,7 @@ __device__ __forceinline__ int rect_cover(const CoverFixed &s, int nr, int j, in
 // Returns false (nothing counted) when the zones overlap or are too large; the caller then runs
 // the row-tiled evaluation of the whole band.
 __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_ent, int rq, int H, double invH, int nx, int ny,
-                           unsigned long long &my_total, unsigned long long &my_cov)
+                           unsigned long long &my_total, unsigned long long &my_cov, int mode)
 {
     const int tid = threadIdx.x;
     const int nr = min(s.nrect, RECT_CAP);
@@ -690,6 +690,9 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
             zrow = 0;
         }
         if (nt == 0) break;
+#ifdef FCPP_COVER_EXPERIMENT
+        if (mode & 16) continue;  // timing experiment: no zone bitmaps (wrong counts)
+#endif
         __syncthreads();
         // row windows of the resident rows, clipped to their zone's columns
         for (int k = tid; k < used_r; k += T) {
@@ -726,6 +729,9 @@ __device__ __noinline__ bool band_zoned(CoverFixed &s, const CoverDyn &d, int n_
     // the same lattice index on the first and the last row of the run it has it on every row, and
     // the run is counted once and multiplied.  Runs with slanted boundaries go row by row. ----
     __syncthreads();  // the last pass is done with the tile: reuse it for the breakpoints
+#ifdef FCPP_COVER_EXPERIMENT
+    if (mode & 32) return true;  // timing experiment: no closed-form rows (wrong counts)
+#endif
     int *bp = reinterpret_cast<int *>(s.tile);  // [nb] sorted breakpoints, then [nb] slow runs (lo, hi)
     const int nb = 10 + 2 * nr + 8;
     static_assert(T >= 2 * (10 + 2 * RECT_CAP + 8), "one thread per (run, end)");
@@ -869,7 +875,11 @@ __device__ __forceinline__ void cover_body(const fcpp_batch &b, const CandRec *_
     // =====================================================================================
     // A10: four verification corner windows (lattice POINTS, h = 0.1 m)
     // =====================================================================================
+#ifdef FCPP_COVER_EXPERIMENT
+    if (do10 && !(mode & 8)) {
+#else
     if (do10) {
+#endif
         const double fl = b.field_extent[2 * r.field], fw = b.field_extent[2 * r.field + 1];
         const int g = r.corner_g;
         const int rw = (g + 31) >> 5;
@@ -1040,7 +1050,7 @@ __device__ __forceinline__ void cover_body(const fcpp_batch &b, const CandRec *_
             if (tid == 0) s.next_w0 = 0;
             // axis-aligned straights: bitmap only around the corners, the rest in closed form
             if (FCPP_COVER_RECT && !(mode & 1) && s.nrect > 0 &&
-                band_zoned(s, d, nh - 1, rq, H, invH, nx, ny, my_total, my_cov))
+                band_zoned(s, d, nh - 1, rq, H, invH, nx, ny, my_total, my_cov, mode))
                 j0 = ny;
             while (j0 < ny) {
                 // --- how many rows to try: from the word count of the first row.  The previous pass

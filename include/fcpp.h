@@ -340,7 +340,7 @@ int64_t fcpp_last_total_points(const fcpp_handle *h);
  * returns the milliseconds of the last call: [0] layout (+scan), [1] plan, [2] coverage. */
 int fcpp_set_profiling(fcpp_handle *h, int on);
 /* 1 when the last fcpp_plan_batch ran plan and coverage as ONE fused kernel (CTA roles, fcpp_hot.cu): the kernel
- * times then are [0] layout, [1] ~0, [2] the fused kernel.  fcpp_set_cover_mode bit 2 forces two launches. */
+ * times then are [0] layout, [1] ~0, [2] the fused kernel.  Opt-in: fcpp_set_cover_mode bit 2. */
 int32_t fcpp_last_fused(const fcpp_handle *h);
 int fcpp_kernel_times(fcpp_handle *h, float *ms3);
 
@@ -349,7 +349,8 @@ int fcpp_kernel_times(fcpp_handle *h, float *ms3);
  * (bitmap around the corners, closed form elsewhere), any other field row-tiled.  Bit 0 set = always
  * row-tiled.  Bit 1 set = no coverage de-duplication (by default candidates whose coverage inputs are
  * identical — same field, R, start corner; e.g. the headings of a heading search — are rasterised once
- * and share the counts).  Bit 2 set = plan and coverage kernels as two launches instead of the fused kernel.
+ * and share the counts).  Bit 2 set = plan and coverage as ONE fused kernel with CTA roles (measured slower on
+ * config 2, see fcpp_hot.cu; default: two launches).
  * All modes give identical results (tests/test_gpu_parity.py compares them). */
 int fcpp_set_cover_mode(fcpp_handle *h, int mode);
 
