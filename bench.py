@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true", help="skip the argmin check against the whole job")
+    ap.add_argument("--e2e-explicit", action="store_true",
+                    help="e2e leg with explicit per-candidate arrays instead of the factored candidate axes")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -401,7 +403,13 @@ def main():
                      "clocks": ck}
 
     # ---- e2e through the public API (host numpy in, host numpy out, winners' paths included) ----
-    host_cands = {k: v.copy() for k, v in (w.cands if world > 1 else cands).items()}
+    # the candidate set in factored form (field x heading x radius x start corner axes, decoded on the device):
+    # the same candidates in the same order as the explicit arrays of the device-timed loop (asserted in
+    # tests/test_host_cpu.py); --e2e-explicit passes the per-candidate arrays instead
+    if args.e2e_explicit:
+        host_cands = {k: v.copy() for k, v in (w.cands if world > 1 else cands).items()}
+    else:
+        host_cands = w.axes                 # the whole job; plan_batch(distributed=True) takes each rank's range
 
     def step_e2e():
         return fc.plan_batch(w.fields, veh, host_cands, obstacles=w.obstacles, outputs=w.outputs, grid_h=w.grid_h,
@@ -472,8 +480,9 @@ def main():
             "clocks": clocks, "sustained": sustained, "argmin_ok": argmin_ok,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "argmin_ok": e2e_ok,
-                    "api": "plan_batch(host numpy, winners=True) -> summaries + argmin + every field's winning path "
-                           "and speeds on the host"},
+                    "api": "plan_batch(host numpy fields + "
+                           + ("per-candidate arrays" if args.e2e_explicit else "candidate axes (candidate_axes)")
+                           + ", winners=True) -> summaries + argmin + every field's winning path and speeds on the host"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

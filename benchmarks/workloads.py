@@ -31,6 +31,7 @@ class Workload:
     obstacles: Optional[List]
     grid_h: float
     outputs: str                        # 'paths' | 'summary'
+    axes: Optional[Dict[str, object]] = None   # the same candidates, same order, in factored form (batch.candidate_axes)
 
     @property
     def n_cand(self) -> int:
@@ -53,14 +54,15 @@ def _radius_corner(radii: np.ndarray, n_gpus: int):
     radii = np.concatenate([radii[r::n_gpus] for r in range(n_gpus)])
     R = np.repeat(radii, len(CORNERS))
     c = np.tile(np.asarray(CORNERS, dtype=np.int32), len(radii))
-    return {"field_id": np.zeros(len(R), dtype=np.int32), "R": R, "start_corner": c}
+    return {"field_id": np.zeros(len(R), dtype=np.int32), "R": R, "start_corner": c}, \
+        {"axes": True, "n_fields": 1, "R": radii, "start_corner": np.asarray(CORNERS, dtype=np.int32)}
 
 
 def c2(n_gpus: int = 1, radii_per_gpu: int = 1024) -> Workload:
-    cands = _radius_corner(np.linspace(5.0, 12.0, radii_per_gpu * n_gpus), n_gpus)
+    cands, axes = _radius_corner(np.linspace(5.0, 12.0, radii_per_gpu * n_gpus), n_gpus)
     return Workload("c2", f"config2: 500x200 m field + 2 obstacles, {4 * radii_per_gpu} candidates/GPU "
                     f"(4 start corners x {radii_per_gpu} radii 5..12 m), h=0.1 m",
-                    np.asarray([RECT]), cands, [OBST2], 0.1, "paths")
+                    np.asarray([RECT]), cands, [OBST2], 0.1, "paths", axes)
 
 
 def c3_fields(F: int = 4096, seed: int = 1234) -> np.ndarray:
@@ -82,16 +84,17 @@ def c3(n_gpus: int = 1, fields_per_gpu: int = 4096, n_headings: int = 180) -> Wo
     fid = np.repeat(np.arange(F, dtype=np.int32), n_headings)
     cands = {"field_id": fid, "heading": np.tile(heads, F)}
     return Workload("c3", f"config3: {fields_per_gpu} tilted parallelograms/GPU x {n_headings} headings, h=0.1 m, "
-                    "summary only, argmin per field", c3_fields(F), cands, None, 0.1, "summary")
+                    "summary only, argmin per field", c3_fields(F), cands, None, 0.1, "summary",
+                    {"axes": True, "n_fields": F, "heading": heads})
 
 
 def c5(n_gpus: int = 1, cands_per_gpu: int = 8192) -> Workload:
     n_r = cands_per_gpu // 4 * n_gpus
     # the radii of the 65 536-candidate job are linspace(5, 12, 16384); fewer GPUs take the same range coarser
-    cands = _radius_corner(np.linspace(5.0, 12.0, n_r), n_gpus)
+    cands, axes = _radius_corner(np.linspace(5.0, 12.0, n_r), n_gpus)
     return Workload("c5", f"config5: 2000x1000 m field, h=0.05 m, {cands_per_gpu} candidates/GPU "
                     f"(4 start corners x {cands_per_gpu // 4} radii 5..12 m), summary only",
-                    np.asarray([BIG]), cands, None, 0.05, "summary")
+                    np.asarray([BIG]), cands, None, 0.05, "summary", axes)
 
 
 WORKLOADS = {"c2": c2, "c3": c3, "c5": c5}

@@ -6,7 +6,7 @@ No CPU fallback: importing works anywhere, computing needs libfcpp.so and a CUDA
 """
 from .vehicle import VehicleParams  # noqa: F401
 from ._lib import FcppError  # noqa: F401
-from .batch import BatchResult, make_candidates, plan_batch, prepare_batch  # noqa: F401
+from .batch import BatchResult, candidate_axes, expand_axes, make_candidates, plan_batch, prepare_batch  # noqa: F401
 from .planner import (TwoLayerPathPlannerV35, TwoLayerPathPlannerV36, TwoLayerPathPlannerV37,  # noqa: F401
                       TwoLayerPlannerV35, TwoLayerPlannerV36, TwoLayerPlannerV37)
 from .ga import GAConfig, GeneticAlgorithmSolver, tour_lengths  # noqa: F401
@@ -15,6 +15,6 @@ from .multi_field import (Connection, FieldData, MultiFieldPlannerV38, Optimized
 
 __all__ = ["VehicleParams", "TwoLayerPathPlannerV37", "TwoLayerPathPlannerV35", "TwoLayerPathPlannerV36",
            "TwoLayerPlannerV35", "TwoLayerPlannerV36", "TwoLayerPlannerV37", "plan_batch", "prepare_batch",
-           "make_candidates", "BatchResult", "tour_lengths", "GeneticAlgorithmSolver", "GAConfig", "FcppError",
+           "make_candidates", "candidate_axes", "expand_axes", "BatchResult", "tour_lengths", "GeneticAlgorithmSolver", "GAConfig", "FcppError",
            "MultiFieldPlannerV38", "FieldData", "Connection", "OptimizedRoute", "distance_matrix",
            "connection_matrix"]

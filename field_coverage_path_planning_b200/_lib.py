@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCPP_LIB selects another build of the same library (A/B timing of kernel variants); there is still
 # no fallback: the file must exist and export the ABI
 LIB_PATH = os.environ.get("FCPP_LIB") or os.path.join(_HERE, "libfcpp.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FLAG_CORNER_MASK = 3
 FLAG_REVERSE_ORDER = 4
@@ -67,6 +67,19 @@ class Batch(C.Structure):
         ("turn_model", C.c_int32),
         ("cover_dedupe", C.c_int32),
         ("clothoid_share", C.c_double),
+        ("n_ax_headings", C.c_int32),
+        ("n_ax_radii", C.c_int32),
+        ("n_ax_corners", C.c_int32),
+        ("ax_default_radius_flags", C.c_int32),
+        ("ax_heading_rot", C.c_void_p),
+        ("ax_heading_flags", C.c_void_p),
+        ("ax_radii", C.c_void_p),
+        ("ax_radius_flags", C.c_void_p),
+        ("ax_corners", C.c_void_p),
+        ("field_rot", C.c_void_p),
+        ("field_rot_flags", C.c_void_p),
+        ("ax_default_radius", C.c_double),
+        ("cand_first", C.c_int64),
     ]
 
 

@@ -126,6 +126,64 @@ def make_candidates(n_fields: int, headings: Optional[Sequence[float]] = None,
     return out
 
 
+def candidate_axes(n_fields: int, headings: Optional[Sequence[float]] = None,
+                   radii: Optional[Sequence[float]] = None,
+                   start_corners: Optional[Sequence[int]] = None) -> Dict[str, object]:
+    """The same candidate set as ``make_candidates`` (same order, same indices) in FACTORED form: only the
+    axes are kept, the library decodes candidate g = ((field * NH + heading) * NR + radius) * NC + corner on
+    the device (fcpp_batch: cand_field == NULL).  Nothing per candidate is computed on or copied from the
+    host — a 737 280-candidate heading search sends its 180 headings, not 36 MB of candidate arrays."""
+    ax: Dict[str, object] = {"axes": True, "n_fields": int(n_fields)}
+    if headings is not None:
+        ax["heading"] = np.ascontiguousarray(headings, dtype=np.float64).reshape(-1)
+    if radii is not None:
+        ax["R"] = np.ascontiguousarray(radii, dtype=np.float64).reshape(-1)
+    if start_corners is not None:
+        ax["start_corner"] = np.ascontiguousarray(start_corners, dtype=np.int32).reshape(-1)
+    for k in ("heading", "R", "start_corner"):
+        if k in ax and len(ax[k]) == 0:
+            raise ValueError(f"empty candidate axis {k!r}")
+    return ax
+
+
+def is_axes(candidates) -> bool:
+    return isinstance(candidates, dict) and bool(candidates.get("axes", False))
+
+
+def axes_per_field(ax) -> int:
+    return (len(ax["heading"]) if "heading" in ax else 1) * (len(ax["R"]) if "R" in ax else 1) * \
+        (len(ax["start_corner"]) if "start_corner" in ax else 1)
+
+
+def axes_count(ax) -> int:
+    """Number of candidates of a factored set (or of its ``range``)."""
+    if "range" in ax:
+        return int(ax["range"][1] - ax["range"][0])
+    return int(ax["n_fields"]) * axes_per_field(ax)
+
+
+def expand_axes(ax, index: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """Explicit candidate arrays (the ``make_candidates`` form) of a factored set, or of the product indices
+    ``index`` only (the winners of a search)."""
+    nh = len(ax["heading"]) if "heading" in ax else 1
+    nr = len(ax["R"]) if "R" in ax else 1
+    nc = len(ax["start_corner"]) if "start_corner" in ax else 1
+    per = nh * nr * nc
+    if index is None:
+        lo, hi = ax.get("range", (0, int(ax["n_fields"]) * per))
+        index = np.arange(lo, hi, dtype=np.int64)
+    g = np.asarray(index, dtype=np.int64)
+    rem = g % per
+    out: Dict[str, np.ndarray] = {"field_id": (g // per).astype(np.int32)}
+    if "heading" in ax:
+        out["heading"] = ax["heading"][rem // (nr * nc)]
+    if "R" in ax:
+        out["R"] = ax["R"][(rem // nc) % nr]
+    if "start_corner" in ax:
+        out["start_corner"] = ax["start_corner"][rem % nc]
+    return out
+
+
 @dataclass
 class PreparedBatch:
     """Host (numpy) side of one batch, ready to be copied to a device."""
@@ -140,9 +198,18 @@ class PreparedBatch:
     turn_model: str = "arc"
     clothoid_share: float = 0.5
     dedupe: bool = False
+    axes: Optional[Dict[str, object]] = None     # factored candidate set (candidate_axes): no per-candidate arrays
+    cand_first: int = 0                          # product index of the batch's first candidate
 
     def h2d_bytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays.values()))
+
+    def max_radius(self) -> float:
+        if "cand_R" in self.arrays:
+            return float(self.arrays["cand_R"].max())
+        if self.axes is not None and "R" in self.axes:
+            return float(self.axes["R"].max())
+        return float(self.vehicle.min_turn_radius)
 
 
 def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str, np.ndarray]] = None,
@@ -155,51 +222,88 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
     reference's defaults); ``start_points`` [B,2] makes the pass order follow mlp3:631-668."""
     fv = np.ascontiguousarray(np.asarray(fields, dtype=np.float64).reshape(-1, 4, 2))
     F = len(fv)
-    if candidates is None:
-        candidates = {"field_id": np.arange(F, dtype=np.int32)}
-    fid = np.ascontiguousarray(candidates["field_id"], dtype=np.int32)
-    B = len(fid)
-    if B and (fid.min() < 0 or fid.max() >= F):
-        raise ValueError("candidate field_id out of range")
     W = float(vehicle.working_width)
     # ---- per field: bbox extents (mlp3:120-122), reverse-fill permission bits (mlp3:224-242) ----
     ext = np.stack([fv[:, :, 0].max(1) - fv[:, :, 0].min(1), fv[:, :, 1].max(1) - fv[:, :, 1].min(1)], axis=1)
     ang = G.corner_angles_deg(fv)
     fflags = ((ang >= 60).astype(np.int32) << np.arange(4, dtype=np.int32)).sum(axis=1).astype(np.int32)
-    # ---- per candidate ----
-    R = np.ascontiguousarray(candidates.get("R", np.full(B, vehicle.min_turn_radius)), dtype=np.float64)
-    if "heading" in candidates:
-        ang_c = np.ascontiguousarray(candidates["heading"], dtype=np.float64)
-        rot = np.stack([np.cos(-ang_c), np.sin(-ang_c), np.cos(ang_c), np.sin(ang_c)], axis=1)
-        rotated = np.abs(ang_c) > ROT_THRESHOLD
-    else:
-        # the reference's heading is a property of the field (mlp3:244-263): trig per field, gathered
+    arrays = {"field_verts": fv, "field_extent": np.ascontiguousarray(ext), "field_flags": fflags}
+    axes = None
+    cand_first = 0
+
+    def rot_of(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return (np.ascontiguousarray(np.stack([np.cos(-a), np.sin(-a), np.cos(a), np.sin(a)], axis=1)),
+                np.abs(a) > ROT_THRESHOLD)
+
+    def field_rot():
+        # the reference's heading is a property of the field (direction of edge 0, mlp3:244-263)
         e0 = fv[:, 1, :] - fv[:, 0, :]
-        ang_f = np.arctan2(e0[:, 1], e0[:, 0])
-        rot = np.take(np.stack([np.cos(-ang_f), np.sin(-ang_f), np.cos(ang_f), np.sin(ang_f)], axis=1), fid, axis=0)
-        rotated = np.take(np.abs(ang_f) > ROT_THRESHOLD, fid)
-    if "start_corner" in candidates:
-        c = np.asarray(candidates["start_corner"], dtype=np.int32)
-        if B and (c.min() < 0 or c.max() > 3):
-            raise ValueError("start_corner must be 0..3")
-        # corner c in {0: LB, 1: RB, 2: RT, 3: LT}: reverse order iff c in {2, 3}, start from the right
-        # iff c in {1, 2} (mlp3:650-658)
-        hi = c >> 1
-        flags = c | (hi * _lib.FLAG_REVERSE_ORDER) | (((c ^ hi) & 1) * _lib.FLAG_START_FROM_RIGHT)
-        flags = flags.astype(np.int32, copy=False)
+        return rot_of(np.arctan2(e0[:, 1], e0[:, 0]))
+
+    if is_axes(candidates):
+        # ---- factored candidate set: per AXIS value what the explicit form computes per candidate ----
+        axes = candidates
+        if int(axes["n_fields"]) != F:
+            raise ValueError("candidate axes were made for another number of fields")
+        if start_points is not None:
+            raise ValueError("start_points need explicit candidate arrays (make_candidates)")
+        per = axes_per_field(axes)
+        cand_first, hi = axes.get("range", (0, F * per))
+        if not (0 <= cand_first <= hi <= F * per):
+            raise ValueError("candidate range beyond the product of the axes")
+        B = int(hi - cand_first)
+        if "heading" in axes:
+            rot, rotated = rot_of(axes["heading"])
+            arrays["ax_heading_rot"] = rot
+            arrays["ax_heading_flags"] = (rotated.astype(np.int32) * _lib.FLAG_ROTATED).astype(np.int32)
+        else:
+            rot, rotated = field_rot()
+            arrays["field_rot"] = rot
+            arrays["field_rot_flags"] = (rotated.astype(np.int32) * _lib.FLAG_ROTATED).astype(np.int32)
+        if "R" in axes:
+            arrays["ax_radii"] = axes["R"]
+            arrays["ax_radius_flags"] = (G.gap_gate(axes["R"], W).astype(np.int32) * _lib.FLAG_GAP_GATE).astype(np.int32)
+        if "start_corner" in axes:
+            c = axes["start_corner"]
+            if c.min() < 0 or c.max() > 3:
+                raise ValueError("start_corner must be 0..3")
+            arrays["ax_corners"] = c
+        dedupe = B > F and ("heading" in axes or "start_corner" in axes)
     else:
-        flags = np.zeros(B, dtype=np.int32)
-    flags |= rotated.astype(np.int32) * _lib.FLAG_ROTATED
-    flags |= G.gap_gate(R, W).astype(np.int32) * _lib.FLAG_GAP_GATE
-    arrays = {
-        "field_verts": fv, "field_extent": np.ascontiguousarray(ext), "field_flags": fflags,
-        "cand_field": fid, "cand_R": R, "cand_rot": np.ascontiguousarray(rot), "cand_flags": flags,
-    }
-    if start_points is not None:
-        sp = np.ascontiguousarray(start_points, dtype=np.float64).reshape(B, 2)
-        use = ~np.isnan(sp[:, 0])
-        flags |= np.where(use, _lib.FLAG_START_POINT, 0).astype(np.int32)
-        arrays["cand_start"] = np.where(use[:, None], sp, 0.0)
+        if candidates is None:
+            candidates = {"field_id": np.arange(F, dtype=np.int32)}
+        fid = np.ascontiguousarray(candidates["field_id"], dtype=np.int32)
+        B = len(fid)
+        if B and (fid.min() < 0 or fid.max() >= F):
+            raise ValueError("candidate field_id out of range")
+        R = np.ascontiguousarray(candidates.get("R", np.full(B, vehicle.min_turn_radius)), dtype=np.float64)
+        if "heading" in candidates:
+            rot, rotated = rot_of(candidates["heading"])
+        else:
+            rot_f, rotated_f = field_rot()            # trig per field, gathered
+            rot = np.take(rot_f, fid, axis=0)
+            rotated = np.take(rotated_f, fid)
+        if "start_corner" in candidates:
+            c = np.asarray(candidates["start_corner"], dtype=np.int32)
+            if B and (c.min() < 0 or c.max() > 3):
+                raise ValueError("start_corner must be 0..3")
+            # corner c in {0: LB, 1: RB, 2: RT, 3: LT}: reverse order iff c in {2, 3}, start from the right
+            # iff c in {1, 2} (mlp3:650-658)
+            hi_ = c >> 1
+            flags = c | (hi_ * _lib.FLAG_REVERSE_ORDER) | (((c ^ hi_) & 1) * _lib.FLAG_START_FROM_RIGHT)
+            flags = flags.astype(np.int32, copy=False)
+        else:
+            flags = np.zeros(B, dtype=np.int32)
+        flags |= rotated.astype(np.int32) * _lib.FLAG_ROTATED
+        flags |= G.gap_gate(R, W).astype(np.int32) * _lib.FLAG_GAP_GATE
+        arrays.update({"cand_field": fid, "cand_R": R, "cand_rot": np.ascontiguousarray(rot), "cand_flags": flags})
+        if start_points is not None:
+            sp = np.ascontiguousarray(start_points, dtype=np.float64).reshape(B, 2)
+            use = ~np.isnan(sp[:, 0])
+            flags |= np.where(use, _lib.FLAG_START_POINT, 0).astype(np.int32)
+            arrays["cand_start"] = np.where(use[:, None], sp, 0.0)
+        dedupe = B > F and ("heading" in candidates or "start_corner" in candidates)
     # ---- obstacles (mlp3:600-609): flattened polygon tables + D2 round-buffer moments ----
     max_v = max_p = 0
     if obstacles is not None and any(len(o) for o in obstacles):
@@ -227,8 +331,7 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
     if turn_model not in ("arc", "clothoid"):
         raise ValueError("turn_model must be 'arc' (the reference's sampled arcs) or 'clothoid'")
     return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage), turn_model,
-                         float(clothoid_share),
-                         dedupe=B > F and ("heading" in candidates or "start_corner" in candidates))
+                         float(clothoid_share), dedupe=dedupe, axes=axes, cand_first=int(cand_first))
 
 
 class DeviceBatch:
@@ -260,6 +363,19 @@ class DeviceBatch:
         # corner-window verification: identical coverage work is done once per group on the device
         b.cover_dedupe = 1 if pb.dedupe else 0
         b.clothoid_share = pb.clothoid_share
+        if pb.axes is not None:
+            ax = pb.axes
+            b.n_ax_headings = len(ax["heading"]) if "heading" in ax else 0
+            b.n_ax_radii = len(ax["R"]) if "R" in ax else 0
+            b.n_ax_corners = len(ax["start_corner"]) if "start_corner" in ax else 0
+            b.ax_default_radius = float(v.min_turn_radius)
+            b.ax_default_radius_flags = _lib.FLAG_GAP_GATE if bool(G.gap_gate(np.array([v.min_turn_radius]),
+                                                                              float(v.working_width))[0]) else 0
+            b.cand_first = pb.cand_first
+            for name in ("ax_heading_rot", "ax_heading_flags", "ax_radii", "ax_radius_flags", "ax_corners",
+                         "field_rot", "field_rot_flags"):
+                t = self.t.get(name)
+                setattr(b, name, t.data_ptr() if t is not None else None)
         self.c = b
 
 
@@ -372,7 +488,7 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
         out.summary = buffers.d_sum.data_ptr()
         if corner_bits:
             # occupancy bits of the four verification corner windows (mlp3:1503-1510 'grid'), sized by the largest R
-            g = int(2 * float(db.pb.arrays["cand_R"].max()) / 0.1) if B else 1
+            g = int(2 * db.pb.max_radius() / 0.1) if B else 1
             stride = 4 * g * ((g + 31) // 32)
             if getattr(buffers, "d_cbits", None) is None or buffers.d_cbits.numel() < B * stride:
                 buffers.d_cbits = torch.zeros(max(B * stride, 1), dtype=torch.int32, device=dev)
@@ -389,7 +505,8 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
         if db.c.max_points_hint == 0:
             db.max_points = int(L.fcpp_last_max_points(h.h))
             db.max_head_points = int(L.fcpp_last_max_head_points(h.h))
-        h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), db.t["cand_field"].data_ptr(), B, F,
+        cf = db.t.get("cand_field")     # factored sets: the library's candidate records carry the field
+        h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), cf.data_ptr() if cf is not None else None, B, F,
                                     0 if cost == "length" else 1, cand_base, buffers.d_cost.data_ptr(),
                                     buffers.d_best.data_ptr(), stream))
     return buffers, offsets
@@ -466,10 +583,20 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
             offs = np.concatenate([[0], np.cumsum(o1 - o0)])
             nbytes = tot * 24
         else:
-            arrays = dict(db.pb.arrays)
-            for k in ("cand_field", "cand_R", "cand_rot", "cand_flags", "cand_start"):
-                if k in arrays:
-                    arrays[k] = np.ascontiguousarray(arrays[k][local])
+            if db.pb.axes is not None:
+                # the winners of a factored set as explicit candidates (a few values per field from the axes)
+                keep = {k: v for k, v in db.pb.arrays.items() if k.startswith(("field_", "obs_")) and
+                        k not in ("field_rot", "field_rot_flags")}
+                pbx = prepare_batch(db.pb.arrays["field_verts"], db.pb.vehicle,
+                                    expand_axes(db.pb.axes, db.pb.cand_first + local), None, None, db.pb.grid_h, False,
+                                    db.pb.turn_model, db.pb.clothoid_share)
+                arrays = dict(pbx.arrays)
+                arrays.update(keep)
+            else:
+                arrays = dict(db.pb.arrays)
+                for k in ("cand_field", "cand_R", "cand_rot", "cand_flags", "cand_start"):
+                    if k in arrays:
+                        arrays[k] = np.ascontiguousarray(arrays[k][local])
             pbw = PreparedBatch(db.pb.vehicle, db.pb.n_fields, len(local), arrays, db.pb.max_obs_verts,
                                 db.pb.max_obs_polys, db.pb.grid_h, False, db.pb.turn_model, db.pb.clothoid_share, False)
             dbw = DeviceBatch(pbw, dev, slot=db.slot)

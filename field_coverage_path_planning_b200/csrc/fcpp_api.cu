@@ -71,10 +71,23 @@ int check_batch(fcpp_handle *h, const fcpp_batch *b)
     if (!h) return FCPP_ERR_INVALID;
     if (!b) return fail(h, FCPP_ERR_INVALID, "batch is NULL");
     if (b->n_cand < 0 || b->n_fields < 0) return fail(h, FCPP_ERR_INVALID, "negative sizes");
-    if (b->n_cand > 0 &&
-        (!b->field_verts || !b->field_extent || !b->field_flags || !b->cand_field || !b->cand_R || !b->cand_rot ||
-         !b->cand_flags))
+    if (b->n_cand > 0 && (!b->field_verts || !b->field_extent || !b->field_flags))
         return fail(h, FCPP_ERR_INVALID, "a required batch pointer is NULL");
+    if (b->n_cand > 0 && b->cand_field && (!b->cand_R || !b->cand_rot || !b->cand_flags))
+        return fail(h, FCPP_ERR_INVALID, "a required candidate array is NULL");
+    if (b->n_cand > 0 && !b->cand_field) {  // factored candidate set
+        if (b->n_ax_headings < 0 || b->n_ax_radii < 0 || b->n_ax_corners < 0 || b->cand_first < 0)
+            return fail(h, FCPP_ERR_INVALID, "negative axis size");
+        if ((b->n_ax_headings > 0 && (!b->ax_heading_rot || !b->ax_heading_flags)) ||
+            (b->n_ax_headings == 0 && (!b->field_rot || !b->field_rot_flags)) ||
+            (b->n_ax_radii > 0 && (!b->ax_radii || !b->ax_radius_flags)) || (b->n_ax_corners > 0 && !b->ax_corners))
+            return fail(h, FCPP_ERR_INVALID, "a candidate axis array is NULL");
+        const int64_t per = (int64_t)(b->n_ax_headings > 0 ? b->n_ax_headings : 1) *
+                            (b->n_ax_radii > 0 ? b->n_ax_radii : 1) * (b->n_ax_corners > 0 ? b->n_ax_corners : 1);
+        if (b->cand_first + b->n_cand > (int64_t)b->n_fields * per)
+            return fail(h, FCPP_ERR_INVALID, "candidate range beyond the product of the axes");
+        if (b->cand_start) return fail(h, FCPP_ERR_INVALID, "start points need explicit candidate arrays");
+    }
     if (b->obs_poly_start && (!b->obs_vert_start || !b->obs_verts || !b->obs_moments))
         return fail(h, FCPP_ERR_INVALID, "obstacle tables are incomplete");
     if (!(b->vehicle.working_width > 0.0)) return fail(h, FCPP_ERR_INVALID, "working_width must be > 0");
@@ -239,8 +252,8 @@ int fcpp_layout(fcpp_handle *h, const fcpp_batch *batch, int32_t *d_n_pts, int64
     h->plan_ncap_hint = want;
     h->layout_valid = true;
     h->layout_ncand = batch->n_cand;
-    h->layout_id[0] = batch->cand_R;
-    h->layout_id[1] = batch->cand_flags;
+    h->layout_id[0] = batch->cand_field ? (const void *)batch->cand_R : (const void *)batch->ax_radii;
+    h->layout_id[1] = batch->cand_field ? (const void *)batch->cand_flags : (const void *)(intptr_t)batch->cand_first;
     h->layout_id[2] = batch->field_verts;
     h->layout_id[3] = stream;
     return FCPP_OK;
@@ -261,8 +274,10 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
     if (out->offsets) {
         // the layout is stamped with the batch it was computed for (candidate / field arrays, stream): a
         // layout of another batch of the same size would hand stale records and offsets to the kernels
-        if (!h->layout_valid || h->layout_ncand != batch->n_cand || h->layout_id[0] != batch->cand_R ||
-            h->layout_id[1] != batch->cand_flags || h->layout_id[2] != batch->field_verts || h->layout_id[3] != stream)
+        const void *id0 = batch->cand_field ? (const void *)batch->cand_R : (const void *)batch->ax_radii;
+        const void *id1 = batch->cand_field ? (const void *)batch->cand_flags : (const void *)(intptr_t)batch->cand_first;
+        if (!h->layout_valid || h->layout_ncand != batch->n_cand || h->layout_id[0] != id0 || h->layout_id[1] != id1 ||
+            h->layout_id[2] != batch->field_verts || h->layout_id[3] != stream)
             return fail(h, FCPP_ERR_INVALID, "fcpp_layout must be called for this batch (same arrays, same stream) "
                                              "before fcpp_plan_batch");
     } else {
@@ -302,8 +317,10 @@ int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32
                       int64_t *d_best_cand, void *stream)
 {
     if (!h) return FCPP_ERR_INVALID;
-    if (n_cand < 0 || n_fields < 0 || !d_best_cost || !d_best_cand || (n_cand > 0 && (!d_summary || !d_cand_field)))
+    if (n_cand < 0 || n_fields < 0 || !d_best_cost || !d_best_cand || (n_cand > 0 && !d_summary))
         return fail(h, FCPP_ERR_INVALID, "fcpp_field_argmin: bad argument");
+    if (n_cand > 0 && !d_cand_field && (n_cand > h->rec_cap || !h->d_rec))
+        return fail(h, FCPP_ERR_INVALID, "fcpp_field_argmin: no cand_field and no candidate records of this batch");
     cudaSetDevice(h->device);
     cudaError_t e = fcpp_launch_argmin(h, d_summary, d_cand_field, n_cand, n_fields, cost_kind, cand_base,
                                        d_best_cost, d_best_cand, (cudaStream_t)stream);

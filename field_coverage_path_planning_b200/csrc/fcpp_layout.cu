@@ -68,10 +68,45 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
     tm.model = b.turn_model;
     tm.lam = b.clothoid_share;
     CandRec &r = recs[c];
-    const int f = b.cand_field[c];
-    const double R = b.cand_R[c];
     const double W = b.vehicle.working_width;
-    int flags = b.cand_flags[c];
+    // the candidate's parameters: explicit arrays, or decoded from its index in the Cartesian product of the axes
+    int f, flags;
+    double R;
+    const double *rot;
+    if (b.cand_field) {
+        f = b.cand_field[c];
+        R = b.cand_R[c];
+        flags = b.cand_flags[c];
+        rot = b.cand_rot + 4 * c;
+    } else {
+        const int nh = max(b.n_ax_headings, 1), nr = max(b.n_ax_radii, 1), nc = max(b.n_ax_corners, 1);
+        const int64_t per = (int64_t)nh * nr * nc;
+        const int64_t g = b.cand_first + c;
+        f = (int)(g / per);
+        const int rem = (int)(g - (int64_t)f * per);
+        const int ih = rem / (nr * nc), ir = (rem / nc) % nr, ic = rem % nc;
+        flags = 0;
+        if (b.n_ax_corners > 0) {
+            // corner k in {0: LB, 1: RB, 2: RT, 3: LT}: reverse order iff k in {2, 3}, start from the right iff k in
+            // {1, 2} (mlp3:650-658)
+            const int k = b.ax_corners[ic] & 3, hi = k >> 1;
+            flags = k | (hi ? FCPP_FLAG_REVERSE_ORDER : 0) | (((k ^ hi) & 1) ? FCPP_FLAG_START_FROM_RIGHT : 0);
+        }
+        if (b.n_ax_radii > 0) {
+            R = b.ax_radii[ir];
+            flags |= b.ax_radius_flags[ir];
+        } else {
+            R = b.ax_default_radius;
+            flags |= b.ax_default_radius_flags;
+        }
+        if (b.n_ax_headings > 0) {
+            rot = b.ax_heading_rot + 4 * ih;
+            flags |= b.ax_heading_flags[ih];
+        } else {
+            rot = b.field_rot + 4 * (int64_t)f;
+            flags |= b.field_rot_flags[f];
+        }
+    }
     double v[4][2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -109,7 +144,7 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
             cx = gx;
             cy = gy;
         }
-        const double cn = b.cand_rot[4 * c], sn = b.cand_rot[4 * c + 1];
+        const double cn = rot[0], sn = rot[1];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rotate_pt(mq[k][0], mq[k][1], cn, sn, cx, cy, rv[k][0], rv[k][1]);
     } else {
@@ -130,7 +165,7 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
     if ((flags & FCPP_FLAG_START_POINT) && b.cand_start) {
         // mlp3:689-696 + :649-658: pass order from the (rotated) start point
         double sx = b.cand_start[2 * c], sy = b.cand_start[2 * c + 1];
-        if (flags & FCPP_FLAG_ROTATED) rotate_pt(sx, sy, b.cand_rot[4 * c], b.cand_rot[4 * c + 1], cx, cy, sx, sy);
+        if (flags & FCPP_FLAG_ROTATED) rotate_pt(sx, sy, rot[0], rot[1], cx, cy, sx, sy);
         flags &= ~(FCPP_FLAG_REVERSE_ORDER | FCPP_FLAG_START_FROM_RIGHT);
         if (sy > (min_y + max_y) / 2) flags |= FCPP_FLAG_REVERSE_ORDER;
         if (sx > (min_x + max_x) / 2) flags |= FCPP_FLAG_START_FROM_RIGHT;
@@ -211,8 +246,8 @@ __device__ int layout_one(const fcpp_batch &b, const TrigTables *__restrict__ tr
     r.max_y = max_y;
     r.cx = cx;
     r.cy = cy;
-    r.cos_a = b.cand_rot[4 * c + 2];
-    r.sin_a = b.cand_rot[4 * c + 3];
+    r.cos_a = rot[2];
+    r.sin_a = rot[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         r.main_quad[k][0] = mq[k][0];

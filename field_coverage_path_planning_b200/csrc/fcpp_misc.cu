@@ -79,18 +79,26 @@ __global__ void argmin_init(unsigned long long *key, int64_t *cand, int n_fields
         cand[f] = 0x7fffffffffffffffll;
     }
 }
-__global__ void argmin_cost(const fcpp_summary *__restrict__ sm, const int32_t *__restrict__ cf, int64_t n,
-                            int kind, unsigned long long *key)
+// field of candidate c: the caller's array, or (factored candidate sets) the library's candidate record
+__device__ __forceinline__ int cand_field_of(const int32_t *__restrict__ cf, const CandRec *__restrict__ recs, int64_t c)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n && sm[c].status == 0) atomicMin(&key[cf[c]], order_bits(cand_cost(sm[c], kind)));
+    return cf ? cf[c] : recs[c].field;
 }
-__global__ void argmin_index(const fcpp_summary *__restrict__ sm, const int32_t *__restrict__ cf, int64_t n,
-                             int kind, int64_t base, const unsigned long long *__restrict__ key, int64_t *cand)
+
+__global__ void argmin_cost(const fcpp_summary *__restrict__ sm, const int32_t *__restrict__ cf,
+                            const CandRec *__restrict__ recs, int64_t n, int kind, unsigned long long *key)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n && sm[c].status == 0 && order_bits(cand_cost(sm[c], kind)) == key[cf[c]])
-        atomicMin((long long *)&cand[cf[c]], (long long)(base + c));
+    if (c < n && sm[c].status == 0) atomicMin(&key[cand_field_of(cf, recs, c)], order_bits(cand_cost(sm[c], kind)));
+}
+__global__ void argmin_index(const fcpp_summary *__restrict__ sm, const int32_t *__restrict__ cf,
+                             const CandRec *__restrict__ recs, int64_t n, int kind, int64_t base,
+                             const unsigned long long *__restrict__ key, int64_t *cand)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || sm[c].status != 0) return;
+    const int f = cand_field_of(cf, recs, c);
+    if (order_bits(cand_cost(sm[c], kind)) == key[f]) atomicMin((long long *)&cand[f], (long long)(base + c));
 }
 __global__ void argmin_final(unsigned long long *key, int64_t *cand, int n_fields)
 {
@@ -110,7 +118,8 @@ __global__ void argmin_final(unsigned long long *key, int64_t *cand, int n_field
 // the four phases in ONE CTA (small batches: four dependent launches cost more than the work)
 constexpr int ARGMIN_SMALL_THREADS = 1024;
 __global__ void __launch_bounds__(ARGMIN_SMALL_THREADS) argmin_small(const fcpp_summary *__restrict__ sm,
-                                                                      const int32_t *__restrict__ cf, int64_t n, int kind,
+                                                                      const int32_t *__restrict__ cf,
+                                                                      const CandRec *__restrict__ recs, int64_t n, int kind,
                                                                       int64_t base, unsigned long long *key, int64_t *cand,
                                                                       int n_fields)
 {
@@ -121,12 +130,14 @@ __global__ void __launch_bounds__(ARGMIN_SMALL_THREADS) argmin_small(const fcpp_
     __threadfence();
     __syncthreads();
     for (int64_t c = threadIdx.x; c < n; c += ARGMIN_SMALL_THREADS)
-        if (sm[c].status == 0) atomicMin(&key[cf[c]], order_bits(cand_cost(sm[c], kind)));
+        if (sm[c].status == 0) atomicMin(&key[cand_field_of(cf, recs, c)], order_bits(cand_cost(sm[c], kind)));
     __threadfence();
     __syncthreads();
-    for (int64_t c = threadIdx.x; c < n; c += ARGMIN_SMALL_THREADS)
-        if (sm[c].status == 0 && order_bits(cand_cost(sm[c], kind)) == __ldcg(&key[cf[c]]))
-            atomicMin((long long *)&cand[cf[c]], (long long)(base + c));
+    for (int64_t c = threadIdx.x; c < n; c += ARGMIN_SMALL_THREADS) {
+        if (sm[c].status != 0) continue;
+        const int f = cand_field_of(cf, recs, c);
+        if (order_bits(cand_cost(sm[c], kind)) == __ldcg(&key[f])) atomicMin((long long *)&cand[f], (long long)(base + c));
+    }
     __threadfence();
     __syncthreads();
     for (int f = threadIdx.x; f < n_fields; f += ARGMIN_SMALL_THREADS) {
@@ -369,8 +380,8 @@ cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, co
     if (n_fields == 0) return cudaSuccess;
     unsigned long long *key = reinterpret_cast<unsigned long long *>(d_best_cost);
     if (n_cand <= 16384 && n_fields <= 16384) {
-        argmin_small<<<1, ARGMIN_SMALL_THREADS, 0, st>>>(d_summary, d_cand_field, n_cand, cost_kind, cand_base, key,
-                                                           d_best_cand, n_fields);
+        argmin_small<<<1, ARGMIN_SMALL_THREADS, 0, st>>>(d_summary, d_cand_field, h->d_rec, n_cand, cost_kind, cand_base,
+                                                           key, d_best_cand, n_fields);
         h->launches++;
         return cudaGetLastError();
     }
@@ -380,8 +391,8 @@ cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, co
     h->launches++;
     if (n_cand > 0) {
         const unsigned cb = (unsigned)((n_cand + th - 1) / th);
-        argmin_cost<<<cb, th, 0, st>>>(d_summary, d_cand_field, n_cand, cost_kind, key);
-        argmin_index<<<cb, th, 0, st>>>(d_summary, d_cand_field, n_cand, cost_kind, cand_base, key, d_best_cand);
+        argmin_cost<<<cb, th, 0, st>>>(d_summary, d_cand_field, h->d_rec, n_cand, cost_kind, key);
+        argmin_index<<<cb, th, 0, st>>>(d_summary, d_cand_field, h->d_rec, n_cand, cost_kind, cand_base, key, d_best_cand);
         h->launches += 2;
     }
     argmin_final<<<fb, th, 0, st>>>(key, d_best_cand, n_fields);

@@ -31,6 +31,13 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def shard_candidates(cands: Dict[str, np.ndarray], world: int, rank: int) -> Tuple[Dict[str, np.ndarray], int]:
+    """The rank's contiguous shard of a candidate set + its first global index.  Factored sets
+    (batch.candidate_axes) keep their axes and get a ``range`` — nothing is sliced or copied."""
+    from .batch import axes_count, is_axes
+    if is_axes(cands):
+        first = int(cands.get("range", (0, 0))[0])
+        lo, hi = shard_range(axes_count(cands), world, rank)
+        return dict(cands, range=(first + lo, first + hi)), first + lo
     n = len(cands["field_id"])
     lo, hi = shard_range(n, world, rank)
     return {k: v[lo:hi] for k, v in cands.items()}, lo
@@ -169,9 +176,10 @@ def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, out
     fv = np.asarray(fields, dtype=np.float64).reshape(-1, 4, 2)
     if candidates is None:
         candidates = {"field_id": np.arange(len(fv), dtype=np.int32)}
-    n = len(candidates["field_id"])
+    from .batch import axes_count, is_axes
+    n = axes_count(candidates) if is_axes(candidates) else len(candidates["field_id"])
     local, lo = shard_candidates(candidates, world, rank)
-    hi = lo + len(local["field_id"])
+    hi = lo + (axes_count(local) if is_axes(local) else len(local["field_id"]))
     sp = None if start_points is None else np.asarray(start_points, dtype=np.float64).reshape(n, 2)[lo:hi]
     dev = _dev(device)
     pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage, turn_model, clothoid_share)

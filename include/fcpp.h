@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FCPP_ABI_VERSION 2
+#define FCPP_ABI_VERSION 3
 
 /* hard-coded sample counts of the reference */
 #define FCPP_UTURN_POINTS 20      /* mlp3:807  */
@@ -113,6 +113,24 @@ typedef struct {
                                * headland band (A11) of candidates with the same field, R and start corner (any
                                * heading); 0: every candidate is rasterised.  Same integers either way. */
     double clothoid_share;         /* share of a turn's deflection spent on the two clothoids, (0, 1] */
+    /* ---- factored candidate set (optional): cand_field == NULL selects it.  The candidates are the Cartesian
+     * product field x heading x radius x start corner, field-major (the order of make_candidates): candidate c of
+     * this batch is product index g = cand_first + c, field g / per, heading (g % per) / (NR' NC'), radius
+     * (g / NC') % NR', corner g % NC' with per = NH' NR' NC' and N' = max(N, 1).  The host supplies only the AXES
+     * (a few hundred values) — nothing per candidate is computed or copied by the host. ---- */
+    int32_t n_ax_headings;           /* 0: the axis is absent — every candidate takes its field's own heading */
+    int32_t n_ax_radii;              /* 0: absent — ax_default_radius */
+    int32_t n_ax_corners;            /* 0: absent — start corner 0, no pass-order bits */
+    int32_t ax_default_radius_flags; /* FCPP_FLAG_GAP_GATE or 0 for ax_default_radius */
+    const double *ax_heading_rot;    /* [NH][4] cos(-a), sin(-a), cos(a), sin(a) (host libm / numpy values) */
+    const int32_t *ax_heading_flags; /* [NH] FCPP_FLAG_ROTATED when |a| > 0.01 (mlp3:686), else 0 */
+    const double *ax_radii;          /* [NR] */
+    const int32_t *ax_radius_flags;  /* [NR] FCPP_FLAG_GAP_GATE when the corner gap gate holds for the radius (mlp3:1070) */
+    const int32_t *ax_corners;       /* [NC] start corners 0..3; the pass-order bits follow mlp3:650-658 */
+    const double *field_rot;         /* [F][4] the rotation of the field's own heading (edge 0, mlp3:244-263) */
+    const int32_t *field_rot_flags;  /* [F] FCPP_FLAG_ROTATED or 0 for it */
+    double ax_default_radius;
+    int64_t cand_first;              /* product index of this batch's first candidate (contiguous multi-GPU shards) */
 } fcpp_batch;
 
 #define FCPP_TURN_ARC 0
@@ -200,6 +218,8 @@ int fcpp_plan_batch(fcpp_handle *h, const fcpp_batch *batch, const fcpp_outputs 
  * time_main + time_head (cost_kind 1); candidates with status != 0 are skipped; ties go to the
  * lowest candidate index.  d_best_cost [F] double (+inf when no valid candidate),
  * d_best_cand [F] int64 (-1 when none).  cand_base is added to the indices (multi-GPU shards). */
+/* d_cand_field may be NULL right after fcpp_plan_batch of the same batch on this handle: the candidates' fields
+ * are then taken from the library's candidate records (factored candidate sets have no cand_field array). */
 int fcpp_field_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32_t *d_cand_field,
                       int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
                       double *d_best_cost, int64_t *d_best_cand, void *stream);

@@ -649,3 +649,46 @@ def test_fused_plan_cover_kernel_identical(fc):
         assert np.array_equal(a.offsets, b.offsets)
         assert torch.equal(a.d_path[:n], b.d_path[:n]) and torch.equal(a.d_speeds[:n], b.d_speeds[:n])
     assert n_fused >= 2
+
+
+def test_factored_candidate_sets_identical_to_explicit_arrays(fc):
+    """fcpp_batch with cand_field == NULL (batch.candidate_axes): the layout kernel decodes every candidate from
+    its product index — summaries, offsets, paths, argmin and the winners' paths are byte-identical to the explicit
+    per-candidate arrays of make_candidates; ranges of the product (multi-GPU shards) equal slices."""
+    import torch
+    veh = fc.VehicleParams()
+    tiny = [(0, 0), (30, 0), (30, 15), (0, 15)]
+    para = [(100, 50), (600, 120), (640, 330), (140, 260)]
+    heads = np.deg2rad(np.arange(0.0, 180.0, 11.0))
+    cases = [
+        ([RECT], dict(radii=np.linspace(5.0, 12.0, 67), start_corners=[0, 1, 2, 3]), [OBST2], "paths"),
+        ([RECT, tiny, para], dict(radii=[6.0, 8.0, 11.0], start_corners=[3, 0]), None, "paths"),
+        ([para, RECT], dict(headings=heads, radii=[7.0, 9.0]), None, "summary"),
+        ([para, RECT, tiny], dict(headings=heads, start_corners=[2, 1]), None, "summary"),
+        ([para, RECT], dict(), None, "paths"),
+        ([para, RECT], dict(start_corners=[1]), None, "summary"),
+    ]
+    for fields, axes, obst, outputs in cases:
+        ex = fc.make_candidates(len(fields), **axes)
+        ax = fc.candidate_axes(len(fields), **axes)
+        a = fc.plan_batch(fields, veh, ex, obstacles=obst, outputs=outputs, winners=True)
+        b = fc.plan_batch(fields, veh, ax, obstacles=obst, outputs=outputs, winners=True)
+        assert a.summary.tobytes() == b.summary.tobytes()
+        assert np.array_equal(a.best_cand, b.best_cand) and np.array_equal(a.best_cost, b.best_cost)
+        assert b.extras["h2d_bytes"] < a.extras["h2d_bytes"] or len(ex["field_id"]) <= len(fields)
+        if outputs == "paths":
+            n = int(a.offsets[-1])
+            assert np.array_equal(a.offsets, b.offsets)
+            assert torch.equal(a.d_path[:n], b.d_path[:n]) and torch.equal(a.d_speeds[:n], b.d_speeds[:n])
+        assert a.winner_paths.keys() == b.winner_paths.keys()
+        for f in a.winner_paths:
+            for x, y in zip(a.winner_paths[f], b.winner_paths[f]):
+                assert np.array_equal(x, y)
+        # a range of the product == the same slice of the explicit arrays (local indices, cand_base 0)
+        n = len(ex["field_id"])
+        lo, hi = n // 3, n - n // 4
+        if hi > lo:
+            s = fc.plan_batch(fields, veh, {k: v[lo:hi] for k, v in ex.items()}, obstacles=obst)
+            r = fc.plan_batch(fields, veh, dict(ax, range=(lo, hi)), obstacles=obst, winners=True)
+            assert s.summary.tobytes() == r.summary.tobytes() == a.summary[lo:hi].tobytes()
+            assert np.array_equal(s.best_cand, r.best_cand)

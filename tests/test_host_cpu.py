@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.EXPORTS)
-    assert L.fcpp_abi_version() == _lib.ABI_VERSION == 2
+    assert L.fcpp_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_mirrors_match_c_layout(built, tmp_path):
@@ -159,6 +159,61 @@ def test_prepare_batch_host_setup(built):
     assert pb.dedupe and p2.dedupe
     assert not fc.prepare_batch([rect], fc.VehicleParams(), fc.make_candidates(1, radii=[5.0, 6.0])).dedupe
     assert not fc.prepare_batch([rect, tilted], fc.VehicleParams(), fc.make_candidates(2, start_corners=[1])).dedupe
+
+
+def test_candidate_axes_host_setup(built):
+    """Factored candidate sets (fcpp_batch: cand_field == NULL): the host computes per AXIS value exactly what the
+    explicit form computes per candidate; enumeration order, ranges and shards agree with make_candidates."""
+    fc = built
+    from field_coverage_path_planning_b200 import _lib, batch as B, dist
+    rect = [(0, 0), (500, 0), (500, 200), (0, 200)]
+    tilted = [(10, 5), (510, 40), (470, 260), (-20, 190)]
+    hs, rs, cs = [0.0, 0.005, 0.3], [5.0, 8.0], [3, 0, 1]
+    ax = fc.candidate_axes(2, headings=hs, radii=rs, start_corners=cs)
+    ex = fc.make_candidates(2, headings=hs, radii=rs, start_corners=cs)
+    got = fc.expand_axes(ax)
+    assert set(got) == set(ex) and all(np.array_equal(got[k], ex[k]) for k in ex)
+    pick = np.array([35, 0, 17, 4])
+    sub = fc.expand_axes(ax, pick)
+    assert all(np.array_equal(sub[k], ex[k][pick]) for k in ex)
+    pa = fc.prepare_batch([rect, tilted], fc.VehicleParams(), ax)
+    pe = fc.prepare_batch([rect, tilted], fc.VehicleParams(), ex)
+    assert pa.n_cand == pe.n_cand == 36 and pa.dedupe == pe.dedupe and pa.cand_first == 0
+    assert "cand_field" not in pa.arrays and pa.h2d_bytes() < pe.h2d_bytes()
+    g = np.arange(36)
+    ih, ir, ic = g % 18 // 6, g // 3 % 2, g % 3
+    np.testing.assert_array_equal(pa.arrays["ax_heading_rot"][ih], pe.arrays["cand_rot"])
+    c = np.asarray(cs)[ic]
+    want = (c | np.where(c >= 2, _lib.FLAG_REVERSE_ORDER, 0) | np.where(np.isin(c, (1, 2)), _lib.FLAG_START_FROM_RIGHT, 0)
+            | pa.arrays["ax_heading_flags"][ih] | pa.arrays["ax_radius_flags"][ir])
+    np.testing.assert_array_equal(want, pe.arrays["cand_flags"])          # the device decodes exactly this
+    np.testing.assert_array_equal(pa.arrays["ax_radii"][ir], pe.arrays["cand_R"])
+    # no heading axis: the field's own rotation per FIELD
+    ax2 = fc.candidate_axes(2, radii=rs)
+    p2 = fc.prepare_batch([rect, tilted], fc.VehicleParams(), ax2)
+    e2 = fc.prepare_batch([rect, tilted], fc.VehicleParams(), fc.make_candidates(2, radii=rs))
+    np.testing.assert_array_equal(p2.arrays["field_rot"][[0, 0, 1, 1]], e2.arrays["cand_rot"])
+    assert p2.arrays["field_rot_flags"].tolist() == [0, _lib.FLAG_ROTATED]
+    # contiguous shards: ranges of the product, nothing sliced
+    parts = [dist.shard_candidates(ax, 3, r) for r in range(3)]
+    assert [p[1] for p in parts] == [0, 12, 24] and [B.axes_count(p[0]) for p in parts] == [12, 12, 12]
+    pr = fc.prepare_batch([rect, tilted], fc.VehicleParams(), parts[1][0])
+    assert (pr.n_cand, pr.cand_first) == (12, 12)
+    again, lo = dist.shard_candidates(parts[1][0], 2, 1)                   # a shard of a shard
+    assert lo == 18 and again["range"] == (18, 24)
+    with pytest.raises(ValueError):
+        fc.prepare_batch([rect], fc.VehicleParams(), ax)                   # made for two fields
+    with pytest.raises(ValueError):
+        fc.prepare_batch([rect, tilted], fc.VehicleParams(), ax, start_points=np.zeros((36, 2)))
+    with pytest.raises(ValueError):
+        fc.prepare_batch([rect, tilted], fc.VehicleParams(), dict(ax, range=(30, 40)))
+    with pytest.raises(ValueError):
+        fc.candidate_axes(1, radii=[])
+    # the bench workloads: the factored form enumerates the same candidates in the same order as the explicit arrays
+    from benchmarks import workloads as wl
+    for w in (wl.c2(1), wl.c2(2, 16), wl.c3(2, 8), wl.c5(1, 64), wl.c5(8, 64)):
+        e = fc.expand_axes(w.axes)
+        assert set(e) == set(w.cands) and all(np.array_equal(e[k], w.cands[k]) for k in e), w.name
 
 
 def test_first_handle_call_in_a_fresh_process_returns():
