@@ -63,6 +63,48 @@ class _Staging:
         return self.h_out
 
 
+class _PinnedView:
+    """numpy's owner object of a view into a pinned buffer: alive exactly as long as some array views it."""
+
+    def __init__(self, t: torch.Tensor, nbytes: int):
+        self.t = t
+        self.__array_interface__ = {"data": (t.data_ptr(), False), "shape": (int(nbytes),), "typestr": "|u1",
+                                    "version": 3}
+
+
+class _ResultPool:
+    """Pinned host buffers that results are read back INTO and handed to the caller as numpy views — no host
+    memcpy out of a staging buffer (at 737 280 candidates that copy cost more than the PCIe transfer).  A buffer
+    is reused only when no array views it any more (weak reference to the views' owner object), so a caller that
+    drops the previous BatchResult runs allocation-free; one that keeps many results gets new buffers up to
+    ``MAX_BYTES`` and ordinary pageable copies beyond (``get`` returns None)."""
+    MAX_BYTES = 4 << 30
+    _bufs: List[list] = []          # [tensor, weakref to the _PinnedView handed out last | None]
+
+    @staticmethod
+    def _free(e) -> bool:
+        return e[1] is None or e[1]() is None
+
+    @classmethod
+    def get(cls, nbytes: int):
+        """-> (pinned uint8 tensor, numpy uint8 view of its first nbytes) or None."""
+        import weakref
+        nbytes = max(int(nbytes), 256)
+        best = None
+        for e in cls._bufs:
+            if e[0].numel() >= nbytes and cls._free(e) and (best is None or e[0].numel() < best[0].numel()):
+                best = e
+        if best is None:
+            cls._bufs = [e for e in cls._bufs if not cls._free(e)]      # free ones were too small
+            if sum(e[0].numel() for e in cls._bufs) + nbytes > cls.MAX_BYTES:
+                return None
+            best = [torch.empty(max(nbytes + (nbytes >> 2), 1 << 20), dtype=torch.uint8).pin_memory(), None]
+            cls._bufs.append(best)
+        pv = _PinnedView(best[0], nbytes)
+        best[1] = weakref.ref(pv)
+        return best[0], np.asarray(pv)
+
+
 _TORCH_DTYPE = {np.dtype(np.float64).str: torch.float64, np.dtype(np.int32).str: torch.int32,
                 np.dtype(np.int64).str: torch.int64, np.dtype(np.uint8).str: torch.uint8}
 
@@ -525,7 +567,8 @@ def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, 
         o_best = o_cost + ((F * 8 + 255) & ~255)
         o_off = o_best + ((F * 8 + 255) & ~255)
         total_out = o_off + ((B + 1) * 8 if need_off else 0)
-        ho = _Staging.get(dev, db.slot).host_out(max(total_out, 256))
+        pooled = _ResultPool.get(total_out)
+        ho = pooled[0] if pooled is not None else _Staging.get(dev, db.slot).host_out(max(total_out, 256))
         if nb_sum:
             ho[:nb_sum].copy_(buffers.d_sum[:nb_sum], non_blocking=True)
         if F:
@@ -534,12 +577,13 @@ def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, 
         if need_off:
             ho[o_off:o_off + (B + 1) * 8].view(torch.int64).copy_(buffers.d_off[:B + 1], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        hv = ho.numpy()
-        summary = hv[:nb_sum].copy().view(_lib.SUMMARY_DTYPE)[:B] if nb_sum else np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
-        best_cost = hv[o_cost:o_cost + F * 8].copy().view(np.float64)
-        best_cand = hv[o_best:o_best + F * 8].copy().view(np.int64)
+        hv = pooled[1] if pooled is not None else ho.numpy()
+        own = (lambda a: a) if pooled is not None else (lambda a: a.copy())   # pooled: the views ARE the result
+        summary = own(hv[:nb_sum]).view(_lib.SUMMARY_DTYPE)[:B] if nb_sum else np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
+        best_cost = own(hv[o_cost:o_cost + F * 8]).view(np.float64)
+        best_cand = own(hv[o_best:o_best + F * 8]).view(np.int64)
         if need_off:
-            offsets = hv[o_off:o_off + (B + 1) * 8].copy().view(np.int64)
+            offsets = own(hv[o_off:o_off + (B + 1) * 8]).view(np.int64)
     res = BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
                       d_path=buffers.d_path, d_speeds=buffers.d_spd, d_curvature=buffers.d_kap,
                       d_summary=buffers.d_sum, cand_base=cand_base)
@@ -569,7 +613,8 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
         if outputs == "paths" and len(own) <= 16 and res.offsets is not None:
             o0, o1 = res.offsets[local], res.offsets[local + 1]
             tot = int((o1 - o0).sum())
-            ho = _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
+            pooled = _ResultPool.get(tot * 24 + 256)
+            ho = pooled[0] if pooled is not None else _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
             hp = ho[:tot * 16].view(torch.float64).view(tot, 2)
             hs = ho[tot * 16:tot * 24].view(torch.float64)
             at = 0
@@ -579,7 +624,10 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
                 hs[at:at + n].copy_(res.d_speeds[int(a):int(b)], non_blocking=True)
                 at += n
             torch.cuda.current_stream(dev).synchronize()
-            P, S = hp.numpy().copy(), hs.numpy().copy()
+            if pooled is not None:
+                P, S = pooled[1][:tot * 16].view(np.float64).reshape(tot, 2), pooled[1][tot * 16:tot * 24].view(np.float64)
+            else:
+                P, S = hp.numpy().copy(), hs.numpy().copy()
             offs = np.concatenate([[0], np.cumsum(o1 - o0)])
             nbytes = tot * 24
         else:
@@ -602,13 +650,17 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
             dbw = DeviceBatch(pbw, dev, slot=db.slot)
             rw = run_device_batch(dbw, "paths", copy_summary=False)
             tot = int(rw.offsets[-1])
-            ho = _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
+            pooled = _ResultPool.get(tot * 24 + 256)
+            ho = pooled[0] if pooled is not None else _Staging.get(dev, db.slot).host_out(tot * 24 + 256)
             hp = ho[:tot * 16].view(torch.float64).view(tot, 2)
             hs = ho[tot * 16:tot * 24].view(torch.float64)
             hp.copy_(rw.d_path[:tot], non_blocking=True)
             hs.copy_(rw.d_speeds[:tot], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-            P, S = hp.numpy().copy(), hs.numpy().copy()
+            if pooled is not None:
+                P, S = pooled[1][:tot * 16].view(np.float64).reshape(tot, 2), pooled[1][tot * 16:tot * 24].view(np.float64)
+            else:
+                P, S = hp.numpy().copy(), hs.numpy().copy()
             offs = rw.offsets
             nbytes = tot * 24 + (len(local) + 1) * 8 + 16 * db.pb.n_fields
             res.extras["h2d_bytes"] = res.extras.get("h2d_bytes", 0) + pbw.h2d_bytes()

@@ -692,3 +692,30 @@ def test_factored_candidate_sets_identical_to_explicit_arrays(fc):
             r = fc.plan_batch(fields, veh, dict(ax, range=(lo, hi)), obstacles=obst, winners=True)
             assert s.summary.tobytes() == r.summary.tobytes() == a.summary[lo:hi].tobytes()
             assert np.array_equal(s.best_cand, r.best_cand)
+
+
+def test_results_are_views_of_pinned_buffers_that_outlive_later_calls(fc):
+    """The read-back hands out numpy views of pooled pinned buffers (no host copy): a result stays intact while any
+    of its arrays is alive, however many calls follow, and its buffer is reused once the last view is gone."""
+    import gc
+    from field_coverage_path_planning_b200.batch import _ResultPool
+    veh = fc.VehicleParams()
+    ca = fc.candidate_axes(1, radii=np.linspace(5.0, 9.0, 33), start_corners=[0, 1])
+    cb = fc.candidate_axes(1, radii=np.linspace(6.0, 12.0, 33), start_corners=[2, 3])
+    a = fc.plan_batch([RECT], veh, ca, outputs="paths", winners=True)
+    keep = (a.summary.copy(), a.best_cost.copy(), a.offsets.copy(), a.winner_paths[0][0].copy(), a.winner_paths[0][1].copy())
+    only_summary = a.summary            # one array of the result kept, the BatchResult itself dropped below
+    wp = a.winner_paths[0]
+    del a
+    others = [fc.plan_batch([RECT], veh, cb, outputs="paths", winners=True) for _ in range(3)]
+    assert only_summary.tobytes() == keep[0].tobytes()
+    assert np.array_equal(wp[0], keep[3]) and np.array_equal(wp[1], keep[4])
+    assert others[0].summary.tobytes() == others[2].summary.tobytes() != keep[0].tobytes()
+    del others, only_summary, wp
+    gc.collect()
+    n_before = len(_ResultPool._bufs)
+    for _ in range(4):
+        r = fc.plan_batch([RECT], veh, ca, outputs="paths", winners=True)
+        assert r.summary.tobytes() == keep[0].tobytes() and np.array_equal(r.offsets, keep[2])
+        del r
+    assert len(_ResultPool._bufs) <= n_before        # steady state: no new pinned allocations
