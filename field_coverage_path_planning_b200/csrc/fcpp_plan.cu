@@ -269,12 +269,16 @@ static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 
 
 // shared memory of the generated-plan kernel: fixed part (compile-time offsets) + obstacle tables + the staging of
 // the `ncap` staged points (first 2 + last 22 main points + headland): ds, kappa, u (FP64) and the structure tag
+constexpr int PASS_WORDS = 128;  // main passes covered by the per-pass cull bits (4096; later passes: per point)
 struct GenFixed {
     CandRec rec;
     TrigTables tt;
     Tpl tbl[N_SLOTS];
     double tpts[2 * TPL_PTS];
     double geo[20];              // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
+    double gelen[4];             // |e| of the four edges
+    uint32_t pass_safe[PASS_WORDS];  // bit idx: every turn sample of main pass idx passes all point tests
+    uint32_t pass_out[PASS_WORDS];   // bit idx: every turn sample lies outside the field and clear of the obstacles
     double gvl[N_GENERIC];       // curvature-limited speed of the generic points
     double scratch[9 * (FCPP_PLAN_GEN_THREADS / 32) + 8];  // group reductions: 9 values per warp; scans: 2 per warp
     double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
@@ -509,7 +513,9 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         f.geo[5 * k + 1] = ay;
         f.geo[5 * k + 2] = ex;
         f.geo[5 * k + 3] = ey;
-        f.geo[5 * k + 4] = -FCPP_GEOFENCE_EPS * sqrt(ex * ex + ey * ey);
+        const double el = sqrt(ex * ex + ey * ey);
+        f.geo[5 * k + 4] = -FCPP_GEOFENCE_EPS * el;
+        f.gelen[k] = el;
     }
     // early-reject boxes: a point outside an obstacle's bbox grown by W/2 (+1e-6 m, far above any rounding of the
     // exact test) can neither be inside it nor within W/2 of an edge
@@ -590,6 +596,55 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         }
     }
     sync();
+
+    // ------------------------------------------------------------------------------------
+    // phase 0c (summary-only batches): per-pass cull bits.  The 20 turn samples of main pass idx and the swath end
+    // they start from lie on the circle of radius R around (min_x or max_x, y of the pass) in the swath frame
+    // (mlp3:815-823).  When that disc, grown by 1e-6 m (six orders of magnitude above the rounding of either test),
+    // misses every obstacle's grown box and
+    //   * is inside all four field edges (cross(e, c - v) >= (R + 1e-6) |e|): none of the 21 points fails a test;
+    //   * is outside one edge (cross <= -(R + 1e-6) |e|): every one of them is a boundary violation, nothing else;
+    // either way they are not generated.  The swath's far end is always tested.  Swaths span the bounding box of
+    // the rotated work area (mlp3:736-737), so on sheared or rotated fields most turns are of the second kind.
+    // (Clothoid turns are wider than the disc: no culling.  With materialised paths every point is generated
+    // anyway and the per-point tests are cheaper than the bit look-up: no culling either.)
+    // ------------------------------------------------------------------------------------
+    const bool cull = n_skip > 0 && !a.out.path_xy && !a.out.speeds_kmh && !a.out.curvature &&
+                      tm.model != FCPP_TURN_CLOTHOID;
+    if (cull) {
+        const int n_bits = min(r.P, 32 * PASS_WORDS);
+        const double rad = r.R + 1e-6;
+        for (int base = 0; base < n_bits; base += T) {  // warp-uniform trip count (ballot)
+            const int idx = base + tid;
+            bool safe = false, out = false;
+            if (idx < n_bits) {
+                const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
+                const double py = r.min_y + pi * W;
+                const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
+                const double px = go_left ? r.min_x : r.max_x;
+                double x = px, y = py;
+                if (r.flags & FCPP_FLAG_ROTATED) rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);
+                bool clear = true;
+                for (int p = 0; p < n_obs_poly && clear; ++p)
+                    clear = x + rad < s.obs_bb[4 * p] || y + rad < s.obs_bb[4 * p + 1] || x - rad > s.obs_bb[4 * p + 2] ||
+                            y - rad > s.obs_bb[4 * p + 3];
+                safe = clear;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double cr = f.geo[5 * k + 2] * (y - f.geo[5 * k + 1]) - f.geo[5 * k + 3] * (x - f.geo[5 * k]);
+                    const double lim = rad * f.gelen[k];
+                    safe = safe && (cr >= lim);
+                    out = out || (cr <= -lim);
+                }
+                out = out && clear;
+            }
+            const unsigned ms = __ballot_sync(0xffffffffu, safe), mo = __ballot_sync(0xffffffffu, out);
+            if (lane == 0 && idx < 32 * PASS_WORDS) {
+                f.pass_safe[idx >> 5] = ms;
+                f.pass_out[idx >> 5] = mo;
+            }
+        }
+    }
 
     // ------------------------------------------------------------------------------------
     // phase 0b (warp 0): the regular chain once — acceleration passes over its 22 points (a zero-length segment
@@ -689,6 +744,14 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     for (int i = 2 + tid; i < 2 + n_skip; i += T) {
         const int idx = i / CHAIN_POINTS;
         const int j = i - idx * CHAIN_POINTS;
+        if (cull && j != 0 && idx < 32 * PASS_WORDS) {
+            const unsigned bit = 1u << (idx & 31);
+            if (f.pass_safe[idx >> 5] & bit) continue;
+            if (f.pass_out[idx >> 5] & bit) {
+                ++n_bviol;
+                continue;
+            }
+        }
         double px, py, x, y;
         main_local_pt(r, f.tt, tm, W, idx, j, px, py);
         if (r.flags & FCPP_FLAG_ROTATED)

@@ -242,7 +242,13 @@ class MultiFieldPlannerV38:
                               optimization_method=self.optimization_method, optimization_stats=stats)
 
     def optimize_multi_vehicle(self):
-        """mfp:235-261 hands over to MultiVehiclePlanner (KMeans split) — out of scope."""
+        """mfp:235-261: field data (centroid, area, vertices) handed to MultiVehiclePlanner.plan — KMeans split on
+        the device, one GA per vehicle (multi_vehicle.py)."""
         if self.num_vehicles == 1:
             raise ValueError("单机优化请使用 optimize_sequence() 方法")
-        raise NotImplementedError("multi-vehicle scheduling (multi_vehicle_planner.py) is outside the hot path")
+        from .multi_vehicle import MultiVehiclePlanner
+        fields_data = {fid: {'centroid': f.centroid, 'area': f.area, 'vertices': f.vertices}
+                       for fid, f in self.fields.items()}
+        mvp = MultiVehiclePlanner(num_vehicles=self.num_vehicles, optimization_method=self.optimization_method,
+                                  device=self._device, seed=self._seed, verbose=self.verbose)
+        return mvp.plan(fields_data, tuple(self.depot), self.vehicle_params, self.optimization_method == "genetic")

@@ -290,6 +290,23 @@ int fcpp_connection_matrix(fcpp_handle *h, const double *d_field_verts, int32_t 
                            double depot_y, double *d_C, int32_t *d_arg, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-vehicle split ("mvp" = multi_vehicle_planner.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* mvp:186-209 _cluster_fields = sklearn.cluster.KMeans(n_clusters=V, random_state=42).fit_predict(centroids):
+ * the Lloyd iteration of scikit-learn's `_kmeans_single_lloyd` on 2-D points, batched — problem p owns the points
+ * d_xy[d_pt_start[p] .. d_pt_start[p+1]) and the centres d_centers[d_center_start[p] .. d_center_start[p+1])
+ * (k-means++ seeds in, final centres out; max_clusters = the largest centre count of a problem, <= 4096).  Per
+ * problem: data centred on its mean; E step = first minimum of ||c||^2 - 2 x.c; M step = member mean, an empty
+ * cluster takes the point farthest from its centre; stop on unchanged labels, or when the summed squared centre
+ * shift <= tol * mean per-axis variance (sklearn: tol = 1e-4), or after max_iter (sklearn: 300) iterations, then
+ * one more E step unless the labels were unchanged.  d_labels [sum n] int32, d_n_iter [P], d_inertia [P]
+ * (sum of squared distances to the assigned centre).  One CTA per problem, deterministic reductions. */
+int fcpp_kmeans_lloyd(fcpp_handle *h, int32_t n_problems, const int64_t *d_pt_start, const double *d_xy,
+                      const int64_t *d_center_start, int32_t max_clusters, double *d_centers, int32_t *d_labels,
+                      int32_t max_iter, double tol, int32_t *d_n_iter, double *d_inertia, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GA evolution on the device ("ga" = genetic_algorithm_solver.py)
  * ------------------------------------------------------------------------------------------- */
 #define FCPP_GA_MAX_TOURNAMENT 16

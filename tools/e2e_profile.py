@@ -17,7 +17,8 @@ veh = fc.VehicleParams()
 
 
 def T(f, n):
-    f()
+    keep = [f() for _ in range(3)]      # warm-up incl. the pinned result pool (a kept result pins its buffer)
+    del keep
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n):
@@ -43,3 +44,18 @@ for name in (sys.argv[1:] or ["c2", "c3", "c5"]):
               f"+ launch+kernels {t_launch:.3f} + fetch {t_fetch:.3f} + winners {t_win:.3f}   "
               f"[h2d {pb.h2d_bytes()} B; run without summary copy {t_nosum:.3f} ms]  "
               f"-> {w.n_cand / t_all / 1e3:.3f} M plans/s", flush=True)
+
+if os.environ.get("FCPP_CPROFILE"):
+    import cProfile
+    import pstats
+    w = wl.WORKLOADS[os.environ["FCPP_CPROFILE"]](1)
+    call = lambda: fc.plan_batch(w.fields, veh, w.axes, obstacles=w.obstacles, outputs=w.outputs, grid_h=w.grid_h,  # noqa: E731
+                                 device=dev, winners=True)
+    for _ in range(5):
+        r = call()
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(200):
+        r = call()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
