@@ -269,7 +269,7 @@ static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 
 
 // shared memory of the generated-plan kernel: fixed part (compile-time offsets) + obstacle tables + the staging of
 // the `ncap` staged points (first 2 + last 22 main points + headland): ds, kappa, u (FP64) and the structure tag
-constexpr int PASS_WORDS = 128;  // main passes covered by the per-pass cull bits (4096; later passes: per point)
+constexpr int MIXED_CAP = 510;  // listed passes; a pass beyond the list is tested by the thread that classified it
 struct GenFixed {
     CandRec rec;
     TrigTables tt;
@@ -277,8 +277,8 @@ struct GenFixed {
     double tpts[2 * TPL_PTS];
     double geo[20];              // [4][5] field edges of the geofence test: ax, ay, ex, ey, threshold
     double gelen[4];             // |e| of the four edges
-    uint32_t pass_safe[PASS_WORDS];  // bit idx: every turn sample of main pass idx passes all point tests
-    uint32_t pass_out[PASS_WORDS];   // bit idx: every turn sample lies outside the field and clear of the obstacles
+    uint16_t mixed[MIXED_CAP];   // main passes whose turn samples need the per-point tests (phase 0c)
+    int32_t n_mixed;
     double gvl[N_GENERIC];       // curvature-limited speed of the generic points
     double scratch[9 * (FCPP_PLAN_GEN_THREADS / 32) + 8];  // group reductions: 9 values per warp; scans: 2 per warp
     double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
@@ -598,50 +598,73 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     sync();
 
     // ------------------------------------------------------------------------------------
-    // phase 0c (summary-only batches): per-pass cull bits.  The 20 turn samples of main pass idx and the swath end
-    // they start from lie on the circle of radius R around (min_x or max_x, y of the pass) in the swath frame
-    // (mlp3:815-823).  When that disc, grown by 1e-6 m (six orders of magnitude above the rounding of either test),
-    // misses every obstacle's grown box and
+    // phase 0c (summary-only batches): the turns of the regular main passes, classified per PASS.  The 20 turn samples
+    // of main pass idx and the swath end they start from lie on the circle of radius R around (min_x or max_x, y of
+    // the pass) in the swath frame (mlp3:815-823).  When that disc, grown by 1e-6 m (six orders of magnitude above
+    // the rounding of either test), misses every obstacle's grown box and
     //   * is inside all four field edges (cross(e, c - v) >= (R + 1e-6) |e|): none of the 21 points fails a test;
-    //   * is outside one edge (cross <= -(R + 1e-6) |e|): every one of them is a boundary violation, nothing else;
-    // either way they are not generated.  The swath's far end is always tested.  Swaths span the bounding box of
-    // the rotated work area (mlp3:736-737), so on sheared or rotated fields most turns are of the second kind.
-    // (Clothoid turns are wider than the disc: no culling.  With materialised paths every point is generated
-    // anyway and the per-point tests are cheaper than the bit look-up: no culling either.)
+    //   * is outside one edge (cross <= -(R + 1e-6) |e|): every one of them is a boundary violation, nothing else
+    //     (swaths span the bounding box of the rotated work area, mlp3:736-737, so on sheared or rotated fields most
+    //     turns are of this kind);
+    // either way the points are only COUNTED.  Every other pass goes on a list and phase 1b generates and tests the
+    // points of the listed passes only — a dense index space, so warps stay full.  The swaths' far ends are always
+    // tested.  (Clothoid turns are wider than the disc, and with materialised paths every point is generated
+    // anyway: no classification then.)
     // ------------------------------------------------------------------------------------
     const bool cull = n_skip > 0 && !a.out.path_xy && !a.out.speeds_kmh && !a.out.curvature &&
                       tm.model != FCPP_TURN_CLOTHOID;
+    const int i_end = 2 + n_skip;  // regular chain points: i in [2, i_end)
+    int n_bviol = 0, n_oviol = 0;
+    auto main_pt = [&](int idx, int j, double &x, double &y) {
+        double px, py;
+        main_local_pt(r, f.tt, tm, W, idx, j, px, py);
+        if (r.flags & FCPP_FLAG_ROTATED)
+            rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
+        else {
+            x = px;
+            y = py;
+        }
+    };
     if (cull) {
-        const int n_bits = min(r.P, 32 * PASS_WORDS);
+        if (tid == 0) f.n_mixed = 0;
+        sync();
         const double rad = r.R + 1e-6;
-        for (int base = 0; base < n_bits; base += T) {  // warp-uniform trip count (ballot)
-            const int idx = base + tid;
-            bool safe = false, out = false;
-            if (idx < n_bits) {
-                const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
-                const double py = r.min_y + pi * W;
-                const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
-                const double px = go_left ? r.min_x : r.max_x;
-                double x = px, y = py;
-                if (r.flags & FCPP_FLAG_ROTATED) rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);
-                bool clear = true;
-                for (int p = 0; p < n_obs_poly && clear; ++p)
-                    clear = x + rad < s.obs_bb[4 * p] || y + rad < s.obs_bb[4 * p + 1] || x - rad > s.obs_bb[4 * p + 2] ||
-                            y - rad > s.obs_bb[4 * p + 3];
-                safe = clear;
+        for (int idx = tid; idx * CHAIN_POINTS + 1 < i_end; idx += T) {
+            // the pass's points j >= 1 inside the regular range (pass 0: its two ends are staged)
+            const int lo = idx == 0 ? 2 : 1, hi = min(CHAIN_POINTS, i_end - idx * CHAIN_POINTS);
+            if (hi <= lo) continue;
+            const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
+            const double py = r.min_y + pi * W;
+            const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
+            const double px = go_left ? r.min_x : r.max_x;
+            double x = px, y = py;
+            if (r.flags & FCPP_FLAG_ROTATED) rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);
+            bool clear = true;
+            for (int p = 0; p < n_obs_poly && clear; ++p)
+                clear = x + rad < s.obs_bb[4 * p] || y + rad < s.obs_bb[4 * p + 1] || x - rad > s.obs_bb[4 * p + 2] ||
+                        y - rad > s.obs_bb[4 * p + 3];
+            bool in = clear, out = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double cr = f.geo[5 * k + 2] * (y - f.geo[5 * k + 1]) - f.geo[5 * k + 3] * (x - f.geo[5 * k]);
-                    const double lim = rad * f.gelen[k];
-                    safe = safe && (cr >= lim);
-                    out = out || (cr <= -lim);
-                }
-                out = out && clear;
+            for (int k = 0; k < 4; ++k) {
+                const double cr = f.geo[5 * k + 2] * (y - f.geo[5 * k + 1]) - f.geo[5 * k + 3] * (x - f.geo[5 * k]);
+                const double lim = rad * f.gelen[k];
+                in = in && (cr >= lim);
+                out = out || (cr <= -lim);
             }
-            const unsigned ms = __ballot_sync(0xffffffffu, safe), mo = __ballot_sync(0xffffffffu, out);
-            if (lane == 0 && idx < 32 * PASS_WORDS) {
-                f.pass_safe[idx >> 5] = ms;
-                f.pass_out[idx >> 5] = mo;
+            if (in) continue;
+            if (out && clear) {
+                n_bviol += hi - lo;
+                continue;
+            }
+            const int pos = idx < 65536 ? atomicAdd(&f.n_mixed, 1) : MIXED_CAP;
+            if (pos < MIXED_CAP) {
+                f.mixed[pos] = (uint16_t)idx;
+            } else {  // (a plan with more than MIXED_CAP unclassifiable passes, or more than 65 535 passes)
+                for (int j = lo; j < hi; ++j) {
+                    double qx, qy;
+                    main_pt(idx, j, qx, qy);
+                    point_tests(s, n_obs_poly, r2, qx, qy, n_bviol, n_oviol);
+                }
             }
         }
     }
@@ -712,7 +735,6 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     // materialised) + point tests; ds / kappa / U of every point inside a congruent headland piece from the
     // table; the generic points are listed by their fixed ordinal
     // ------------------------------------------------------------------------------------
-    int n_bviol = 0, n_oviol = 0;
     double acc_len_m = 0.0, acc_len_h = 0.0, acc_tpre_m = 0.0, acc_tpre_h = 0.0;
     double2 *gp = a.out.path_xy ? reinterpret_cast<double2 *>(a.out.path_xy) + off : nullptr;
     double *gs = a.out.speeds_kmh ? a.out.speeds_kmh + off : nullptr;
@@ -741,30 +763,34 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     // ------------------------------------------------------------------------------------
     // phase 1b: the regular chains' points (most of a plan): generated, tested, written with the chain's speeds
     // ------------------------------------------------------------------------------------
-    for (int i = 2 + tid; i < 2 + n_skip; i += T) {
-        const int idx = i / CHAIN_POINTS;
-        const int j = i - idx * CHAIN_POINTS;
-        if (cull && j != 0 && idx < 32 * PASS_WORDS) {
-            const unsigned bit = 1u << (idx & 31);
-            if (f.pass_safe[idx >> 5] & bit) continue;
-            if (f.pass_out[idx >> 5] & bit) {
-                ++n_bviol;
-                continue;
-            }
+    if (!cull) {
+        for (int i = 2 + tid; i < i_end; i += T) {
+            const int idx = i / CHAIN_POINTS;
+            const int j = i - idx * CHAIN_POINTS;
+            double x, y;
+            main_pt(idx, j, x, y);
+            const int c = j >= 2 ? j - 2 : j + FCPP_UTURN_POINTS;  // position in its chain
+            if (gp) gp[i] = make_double2(x, y);
+            if (gs) gs[i] = f.chain_v[c];
+            if (gk) gk[i] = f.tbl[SLOT_CHAIN + c].kap;
+            point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
         }
-        double px, py, x, y;
-        main_local_pt(r, f.tt, tm, W, idx, j, px, py);
-        if (r.flags & FCPP_FLAG_ROTATED)
-            rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
-        else {
-            x = px;
-            y = py;
+    } else {
+        // the swaths' far ends (j = 0) of passes 1 ...; then the points of the listed passes, densely indexed
+        for (int idx = 1 + tid; idx * CHAIN_POINTS < i_end; idx += T) {
+            double x, y;
+            main_pt(idx, 0, x, y);
+            point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
         }
-        const int c = j >= 2 ? j - 2 : j + FCPP_UTURN_POINTS;  // position in its chain
-        if (gp) gp[i] = make_double2(x, y);
-        if (gs) gs[i] = f.chain_v[c];
-        if (gk) gk[i] = f.tbl[SLOT_CHAIN + c].kap;
-        point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
+        const int n_listed = min(f.n_mixed, MIXED_CAP);
+        for (int k = tid; k < n_listed * (CHAIN_POINTS - 1); k += T) {
+            const int m = k / (CHAIN_POINTS - 1);
+            const int idx = f.mixed[m], j = 1 + (k - m * (CHAIN_POINTS - 1));
+            if ((idx == 0 && j < 2) || idx * CHAIN_POINTS + j >= i_end) continue;
+            double x, y;
+            main_pt(idx, j, x, y);
+            point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
+        }
     }
     // ------------------------------------------------------------------------------------
     // phase 2: the generic points (where two pieces meet, the irregular main points) from their coordinates
