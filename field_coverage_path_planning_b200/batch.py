@@ -239,7 +239,7 @@ class PreparedBatch:
     coverage: bool
     turn_model: str = "arc"
     clothoid_share: float = 0.5
-    dedupe: bool = False
+    dedupe: int = 0          # fcpp_batch.cover_dedupe (0 / 1 / 2)
     axes: Optional[Dict[str, object]] = None     # factored candidate set (candidate_axes): no per-candidate arrays
     cand_first: int = 0                          # product index of the batch's first candidate
 
@@ -312,6 +312,8 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
                 raise ValueError("start_corner must be 0..3")
             arrays["ax_corners"] = c
         dedupe = B > F and ("heading" in axes or "start_corner" in axes)
+        if dedupe and "heading" in axes and B >= 4 * F:
+            dedupe = 2          # a heading search: few coverage representatives (fcpp_batch.cover_dedupe = 2)
     else:
         if candidates is None:
             candidates = {"field_id": np.arange(F, dtype=np.int32)}
@@ -346,6 +348,8 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
             flags |= np.where(use, _lib.FLAG_START_POINT, 0).astype(np.int32)
             arrays["cand_start"] = np.where(use[:, None], sp, 0.0)
         dedupe = B > F and ("heading" in candidates or "start_corner" in candidates)
+        if dedupe and "heading" in candidates and B >= 4 * F:
+            dedupe = 2          # a heading search: few coverage representatives (fcpp_batch.cover_dedupe = 2)
     # ---- obstacles (mlp3:600-609): flattened polygon tables + D2 round-buffer moments ----
     max_v = max_p = 0
     if obstacles is not None and any(len(o) for o in obstacles):
@@ -403,7 +407,7 @@ class DeviceBatch:
         b.turn_model = 1 if pb.turn_model == "clothoid" else 0
         # the headings of a field repeat its headland (hence its coverage), its start corners repeat the
         # corner-window verification: identical coverage work is done once per group on the device
-        b.cover_dedupe = 1 if pb.dedupe else 0
+        b.cover_dedupe = int(pb.dedupe)
         b.clothoid_share = pb.clothoid_share
         if pb.axes is not None:
             ax = pb.axes
@@ -466,6 +470,7 @@ class BatchBuffers:
         self.d_cost = self.d_cb[:nf].view(torch.float64)
         self.d_best = self.d_cb[nf:]
         self.d_off = self.d_path = self.d_spd = self.d_kap = None
+        self.speculative = False     # sized from remembered maxima (_Hints), not from this batch's layout pass
         if total_points > 0:
             self.d_off = torch.empty(n_cand + 1, dtype=torch.int64, device=dev)
             if path_storage is not None:
@@ -486,12 +491,50 @@ def corner_grids(words: np.ndarray, g: int) -> np.ndarray:
     return bits[:, :, :g].astype(bool)
 
 
+class _Hints:
+    """Sizes of earlier batches of the same shape (same fields, vehicle width, grid, candidate count): the longest
+    plan, the longest headland, the total number of points.  A batch that finds its shape here is launched WITHOUT
+    the layout pass's synchronous read-back — staging sized by the remembered maxima, path buffers by the remembered
+    total (fcpp_outputs.path_capacity guards them).  A candidate that needs more is flagged FCPP_CAND_TOO_LARGE /
+    FCPP_CAND_GRID_TOO_LARGE by the kernels; the caller (PendingBatch.result) then runs the batch once more with
+    sizes from its own layout pass, so results never depend on the cache."""
+    _c: Dict[tuple, list] = {}
+
+    @staticmethod
+    def key(db: "DeviceBatch", outputs: str, want_curvature: bool) -> tuple:
+        pb = db.pb
+        fv = pb.arrays["field_verts"]
+        return (db.dev.index, outputs, bool(want_curvature), pb.n_fields, pb.n_cand, float(fv.sum()) if fv.size else 0.0,
+                float(pb.vehicle.working_width), pb.grid_h, pb.turn_model, pb.coverage, pb.max_obs_verts)
+
+    @classmethod
+    def get(cls, key):
+        return cls._c.get(key)
+
+    @classmethod
+    def update(cls, key, max_points: int, max_head: int, total: int):
+        e = cls._c.get(key)
+        if e is None:
+            if len(cls._c) > 64:
+                cls._c.clear()
+            cls._c[key] = [int(max_points), int(max_head), int(total)]
+        else:
+            e[0], e[1], e[2] = max(e[0], int(max_points)), max(e[1], int(max_head)), max(e[2], int(total))
+
+    @classmethod
+    def drop(cls, key):
+        cls._c.pop(key, None)
+
+
 def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, cost: str, cand_base: int,
-                         buffers: Optional["BatchBuffers"], path_alloc=None, corner_bits: bool = False):
+                         buffers: Optional["BatchBuffers"], path_alloc=None, corner_bits: bool = False,
+                         speculate: bool = False):
     """Enqueue layout, prefix sum, plan, coverage and argmin kernels of one batch on torch's current
     stream.  Returns (buffers, offsets or None).  Without ``buffers`` the path storage is sized from
-    the layout pass (one small synchronous read-back); ``path_alloc(total) -> BatchBuffers | None``
-    lets the caller provide it."""
+    the layout pass (one small synchronous read-back) — or, with ``speculate`` and a batch of this shape seen
+    before, from the remembered sizes with no synchronisation at all (``buffers.speculative`` is then True and the
+    caller must check the status flags, see ``_Hints``); ``path_alloc(total) -> BatchBuffers | None`` lets the
+    caller provide the storage."""
     if outputs not in ("summary", "paths"):
         raise ValueError("outputs must be 'summary' or 'paths'")
     dev = db.dev
@@ -499,10 +542,20 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
     L = h.lib
     B, F = db.pb.n_cand, db.pb.n_fields
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    hint_key = _Hints.key(db, outputs, want_curvature) if buffers is None and B > 0 else None
+    hint = _Hints.get(hint_key) if (speculate and hint_key is not None and path_alloc is None) else None
     with torch.cuda.device(dev):
         out = _lib.Outputs()
         offsets = None
-        if buffers is None:
+        if hint is not None and hint[0] > 0 and hint[1] > 0:
+            db.c.max_points_hint, db.c.max_head_points_hint = hint[0], hint[1]
+            total = max(hint[2], 1) if outputs == "paths" else 0
+            buffers = BatchBuffers(dev, B, F, total, want_curvature)
+            buffers.speculative = True
+            if outputs == "paths":
+                h.check(L.fcpp_layout(h.h, C.byref(db.c), None, buffers.d_off.data_ptr(), stream))
+                out.path_capacity = total
+        elif buffers is None:
             db.c.max_points_hint = 0
             db.c.max_head_points_hint = 0
             total = 0
@@ -547,6 +600,8 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
         if db.c.max_points_hint == 0:
             db.max_points = int(L.fcpp_last_max_points(h.h))
             db.max_head_points = int(L.fcpp_last_max_head_points(h.h))
+            if hint_key is not None:
+                _Hints.update(hint_key, db.max_points, db.max_head_points, buffers.total_points)
         cf = db.t.get("cand_field")     # factored sets: the library's candidate records carry the field
         h.check(L.fcpp_field_argmin(h.h, buffers.d_sum.data_ptr(), cf.data_ptr() if cf is not None else None, B, F,
                                     0 if cost == "length" else 1, cand_base, buffers.d_cost.data_ptr(),
@@ -554,12 +609,18 @@ def _launch_device_batch(db: DeviceBatch, outputs: str, want_curvature: bool, co
     return buffers, offsets
 
 
-def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, offsets, copy_summary: bool,
-                        cand_base: int) -> "BatchResult":
-    """Copy summaries + argmin (+ offsets) of a launched batch back: one pinned staging buffer, async
-    copies on torch's current stream, ONE synchronisation."""
+class _PendingFetch:
+    """The read-back of a launched batch, enqueued but not waited for."""
+    __slots__ = ("db", "buffers", "outputs", "offsets", "cand_base", "pooled", "ho", "lay", "event")
+
+
+def _enqueue_fetch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, offsets, copy_summary: bool,
+                   cand_base: int) -> _PendingFetch:
+    """Enqueue the copies of summaries + argmin (+ offsets) into ONE pinned buffer on torch's current stream and
+    record an event behind them; nothing is waited for."""
     dev = db.dev
     B, F = db.pb.n_cand, db.pb.n_fields
+    pf = _PendingFetch()
     with torch.cuda.device(dev):
         nb_sum = B * _lib.SUMMARY_DTYPE.itemsize if copy_summary else 0
         need_off = outputs == "paths" and offsets is None
@@ -576,22 +637,55 @@ def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, 
             ho[o_best:o_best + F * 8].view(torch.int64).copy_(buffers.d_best[:F], non_blocking=True)
         if need_off:
             ho[o_off:o_off + (B + 1) * 8].view(torch.int64).copy_(buffers.d_off[:B + 1], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        hv = pooled[1] if pooled is not None else ho.numpy()
-        own = (lambda a: a) if pooled is not None else (lambda a: a.copy())   # pooled: the views ARE the result
-        summary = own(hv[:nb_sum]).view(_lib.SUMMARY_DTYPE)[:B] if nb_sum else np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
-        best_cost = own(hv[o_cost:o_cost + F * 8]).view(np.float64)
-        best_cand = own(hv[o_best:o_best + F * 8]).view(np.int64)
-        if need_off:
-            offsets = own(hv[o_off:o_off + (B + 1) * 8]).view(np.int64)
+        pf.event = torch.cuda.Event()
+        pf.event.record(torch.cuda.current_stream(dev))
+    pf.db, pf.buffers, pf.outputs, pf.offsets, pf.cand_base = db, buffers, outputs, offsets, cand_base
+    pf.pooled, pf.ho, pf.lay = pooled, ho, (nb_sum, need_off, o_cost, o_best, o_off)
+    return pf
+
+
+def _finish_fetch(pf: _PendingFetch) -> "BatchResult":
+    """Wait for the read-back of ``_enqueue_fetch`` (ONE synchronisation, on its event) and assemble the result."""
+    db, buffers, offsets = pf.db, pf.buffers, pf.offsets
+    B, F = db.pb.n_cand, db.pb.n_fields
+    nb_sum, need_off, o_cost, o_best, o_off = pf.lay
+    pf.event.synchronize()
+    pooled = pf.pooled
+    hv = pooled[1] if pooled is not None else pf.ho.numpy()
+    own = (lambda a: a) if pooled is not None else (lambda a: a.copy())   # pooled: the views ARE the result
+    summary = own(hv[:nb_sum]).view(_lib.SUMMARY_DTYPE)[:B] if nb_sum else np.zeros(0, dtype=_lib.SUMMARY_DTYPE)
+    best_cost = own(hv[o_cost:o_cost + F * 8]).view(np.float64)
+    best_cand = own(hv[o_best:o_best + F * 8]).view(np.int64)
+    if need_off:
+        offsets = own(hv[o_off:o_off + (B + 1) * 8]).view(np.int64)
     res = BatchResult(summary=summary, best_cand=best_cand, best_cost=best_cost, n_fields=F, offsets=offsets,
                       d_path=buffers.d_path, d_speeds=buffers.d_spd, d_curvature=buffers.d_kap,
-                      d_summary=buffers.d_sum, cand_base=cand_base)
+                      d_summary=buffers.d_sum, cand_base=pf.cand_base)
     res.extras["buffers"] = buffers
     return res
 
 
-def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_cand: Optional[np.ndarray] = None) -> int:
+def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, offsets, copy_summary: bool,
+                        cand_base: int) -> "BatchResult":
+    """Copy summaries + argmin (+ offsets) of a launched batch back: one pinned buffer, async copies on torch's
+    current stream, ONE synchronisation."""
+    return _finish_fetch(_enqueue_fetch(db, buffers, outputs, offsets, copy_summary, cand_base))
+
+
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """A second stream per device for the winners' read-back of a finished batch: it must not queue behind the
+    kernels of the NEXT batch, which a pipelining caller has already launched on the main stream."""
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_cand: Optional[np.ndarray] = None,
+                       slot: Optional[int] = None) -> int:
     """Bring the path and the speed profile of every field's best candidate to the host
     (``res.winner_paths``); returns the bytes copied device -> host.  ``best_cand`` (default: the batch's own
     argmin) holds GLOBAL candidate indices; winners outside this batch's range (other ranks' candidates in a
@@ -599,9 +693,12 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
 
     outputs='paths' and a few winners: slices of the materialised paths, one synchronisation.  Otherwise (the
     search configurations, which run summary-only) the winners are planned again as their own small batch
-    with materialised paths — the candidate arrays are slices of the prepared batch, coverage off."""
+    with materialised paths — the candidate arrays are slices of the prepared batch, coverage off.  ``slot``: the
+    handle / staging slot of that second batch (a caller that runs this on a side stream next to batches in flight
+    on the main stream must not share their handle's workspace)."""
     dev = db.dev
     B = db.pb.n_cand
+    slot = db.slot if slot is None else slot
     best = res.best_cand if best_cand is None else best_cand
     own = np.nonzero((best >= res.cand_base) & (best < res.cand_base + B))[0]
     res.winner_paths = {}
@@ -647,7 +744,7 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
                         arrays[k] = np.ascontiguousarray(arrays[k][local])
             pbw = PreparedBatch(db.pb.vehicle, db.pb.n_fields, len(local), arrays, db.pb.max_obs_verts,
                                 db.pb.max_obs_polys, db.pb.grid_h, False, db.pb.turn_model, db.pb.clothoid_share, False)
-            dbw = DeviceBatch(pbw, dev, slot=db.slot)
+            dbw = DeviceBatch(pbw, dev, slot=slot)
             rw = run_device_batch(dbw, "paths", copy_summary=False)
             tot = int(rw.offsets[-1])
             pooled = _ResultPool.get(tot * 24 + 256)
@@ -672,35 +769,84 @@ def fetch_winner_paths(db: DeviceBatch, res: BatchResult, outputs: str, best_can
     return nbytes
 
 
+_SIZE_FLAGS = 8 | 16      # FCPP_CAND_TOO_LARGE | FCPP_CAND_GRID_TOO_LARGE (include/fcpp.h)
+
+
+class PendingBatch:
+    """A batch whose kernels and read-back are enqueued (``plan_batch(..., wait=False)``); ``result()`` waits for
+    them and returns the BatchResult.  A caller that submits batch k+1 before asking for the result of batch k
+    overlaps its host work (set-up, packed copy, launches) with the kernels of batch k:
+
+        pend = plan_batch(..., wait=False)
+        for next_candidates in search:
+            nxt = plan_batch(..., candidates=next_candidates, wait=False)
+            res = pend.result()
+            pend = nxt
+    """
+
+    def __init__(self, db, pf, outputs, want_curvature, cost, cand_base, copy_summary, winners, corner_bits):
+        self.db, self.pf, self.outputs = db, pf, outputs
+        self.args = (want_curvature, cost, cand_base, copy_summary, winners, corner_bits)
+        self._res = None
+
+    def result(self) -> "BatchResult":
+        if self._res is not None:
+            return self._res
+        db, pf, outputs = self.db, self.pf, self.outputs
+        want_curvature, cost, cand_base, copy_summary, winners, corner_bits = self.args
+        buffers = pf.buffers
+        res = _finish_fetch(pf)
+        if buffers.speculative and (not copy_summary or (res.summary["status"] & _SIZE_FLAGS).any()):
+            # remembered sizes (see _Hints) did not fit this batch, or cannot be checked: once more, sized from its
+            # own layout pass.  (A batch with candidates that are genuinely too large takes this path too and comes
+            # back with the same flags.)
+            _Hints.drop(_Hints.key(db, outputs, want_curvature))
+            self._res = run_device_batch(db, outputs, want_curvature, cost, cand_base, copy_summary, None, True,
+                                         winners, corner_bits, speculate=False)
+            return self._res
+        B = db.pb.n_cand
+        if corner_bits:   # [B, stride] words on the device; batch.corner_grids() unpacks one candidate's
+            res.extras["corner_bits"] = buffers.d_cbits[:B * buffers.cbits_stride].view(B, -1)
+        res.extras["h2d_bytes"] = db.pb.h2d_bytes()
+        res.extras["d2h_bytes"] = (len(res.summary) * _lib.SUMMARY_DTYPE.itemsize + 16 * db.pb.n_fields
+                                   + ((B + 1) * 8 if outputs == "paths" else 0))
+        res.extras["speculative"] = bool(buffers.speculative)
+        if winners:
+            # on the side stream: behind this batch (its event has completed), not behind later batches in flight
+            dev = db.dev
+            side = _side_stream(dev)
+            with torch.cuda.stream(side):
+                res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs, slot=db.slot + 1)
+        self._res = res
+        return res
+
+
 def run_device_batch(db: DeviceBatch, outputs: str = "summary", want_curvature: bool = False,
                      cost: str = "length", cand_base: int = 0, copy_summary: bool = True,
                      buffers: Optional[BatchBuffers] = None, fetch: bool = True,
-                     winners: bool = False, corner_bits: bool = False) -> Optional[BatchResult]:
+                     winners: bool = False, corner_bits: bool = False, speculate: bool = False, wait: bool = True):
     """Enqueue one batch on torch's current stream and (``fetch``) copy summaries + argmin back.
 
     With ``buffers`` (from a previous run of the same batch shape) and ``db.max_points`` known the
     whole step is asynchronous: layout, prefix sum, plan, coverage and argmin kernels only.
-    ``winners``: also bring every field's winning path and speeds to the host (``fetch_winner_paths``)."""
+    ``winners``: also bring every field's winning path and speeds to the host (``fetch_winner_paths``).
+    ``speculate``: size the launch from remembered batches of the same shape instead of a synchronous layout
+    read-back (``_Hints``; checked and repeated when the sizes do not fit).  ``wait=False`` returns a
+    ``PendingBatch``."""
     buffers, offsets = _launch_device_batch(db, outputs, want_curvature, cost, cand_base, buffers,
-                                            corner_bits=corner_bits)
+                                            corner_bits=corner_bits, speculate=speculate and copy_summary)
     if not fetch:
         return None
-    res = _fetch_device_batch(db, buffers, outputs, offsets, copy_summary, cand_base)
-    if corner_bits:   # [B, stride] words on the device; batch.corner_grids() unpacks one candidate's
-        res.extras["corner_bits"] = buffers.d_cbits[:db.pb.n_cand * buffers.cbits_stride].view(db.pb.n_cand, -1)
-    res.extras["h2d_bytes"] = db.pb.h2d_bytes()
-    res.extras["d2h_bytes"] = (len(res.summary) * _lib.SUMMARY_DTYPE.itemsize + 16 * db.pb.n_fields
-                               + ((db.pb.n_cand + 1) * 8 if outputs == "paths" else 0))
-    if winners:
-        res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs)
-    return res
+    pf = _enqueue_fetch(db, buffers, outputs, offsets, copy_summary, cand_base)
+    pend = PendingBatch(db, pf, outputs, want_curvature, cost, cand_base, copy_summary, winners, corner_bits)
+    return pend if not wait else pend.result()
 
 
 def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Optional[Dict[str, np.ndarray]] = None,
                obstacles=None, start_points=None, outputs: str = "summary", grid_h: float = 0.1,
                coverage: bool = True, cost: str = "length", device=None, want_curvature: bool = False,
                distributed: bool = False, turn_model: str = "arc", clothoid_share: float = 0.5,
-               winners: bool = False) -> BatchResult:
+               winners: bool = False, wait: bool = True):
     """Evaluate B candidate plans.  See ``prepare_batch`` for the inputs.
 
     Returns a ``BatchResult``: per-candidate ``summary`` records (layout counts, path lengths and
@@ -716,6 +862,10 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     ``winners=True`` also returns every field's winning path and speed profile on the host
     (``BatchResult.winner_paths``) — what a search caller needs from a batch.
 
+    ``wait=False`` returns a ``PendingBatch`` as soon as the batch is enqueued; its ``result()`` gives the
+    BatchResult.  Submitting the next batch before collecting the previous one overlaps the host side of a call with
+    the kernels of the other (see ``PendingBatch``).
+
     ``distributed=True`` (inside a torch.distributed job): the candidates are sharded over the
     ranks in contiguous ranges, each rank plans its shard on its own GPU and the per-field best
     is merged with ONE all-gather of the (cost, candidate) words + a merge kernel (see ``dist.py``);
@@ -729,5 +879,5 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage, turn_model,
                        clothoid_share)
     db = DeviceBatch(pb, dev)
-    return run_device_batch(db, outputs, want_curvature, cost, winners=winners)
+    return run_device_batch(db, outputs, want_curvature, cost, winners=winners, speculate=True, wait=wait)
 

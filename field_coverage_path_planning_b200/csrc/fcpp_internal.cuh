@@ -82,7 +82,8 @@ struct fcpp_handle {
     int64_t last_total;      // total points of the last synchronous layout pass with offsets (-1: unknown)
     int cover_pcap;          // point capacity of the coverage kernel's staging for the next launch
     int cover_mode;          // diagnostics (fcpp_set_cover_mode): bit 0 = never use the zoned band evaluation,
-                             // bit 1 = no coverage de-duplication, bit 2 = plan and coverage as ONE fused kernel
+                             // bit 1 = no coverage de-duplication, bit 2 = plan and coverage as ONE fused kernel,
+                             // bits 6 / 7 = de-duplicated batches: force one coverage CTA per candidate / the persistent work list
     int last_fused;          // the last fcpp_plan_batch ran the fused plan + coverage kernel
     void *d_dedupe;          // coverage de-duplication: hash table, hashes, representatives
     size_t dedupe_bytes;

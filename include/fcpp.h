@@ -111,7 +111,10 @@ typedef struct {
     int32_t cover_dedupe;     /* 1: coverage work with identical inputs is done once and shared — the corner windows
                                * (A10) of candidates with the same field and R (any start corner, any heading), the
                                * headland band (A11) of candidates with the same field, R and start corner (any
-                               * heading); 0: every candidate is rasterised.  Same integers either way. */
+                               * heading); 0: every candidate is rasterised.  2: as 1, and the caller expects FEW
+                               * representatives (a heading search: many headings per field): the coverage kernel then
+                               * runs as a persistent grid over the list of representatives instead of one (mostly
+                               * empty) CTA per candidate.  Same integers either way. */
     double clothoid_share;         /* share of a turn's deflection spent on the two clothoids, (0, 1] */
     /* ---- factored candidate set (optional): cand_field == NULL selects it.  The candidates are the Cartesian
      * product field x heading x radius x start corner, field-major (the order of make_candidates): candidate c of
@@ -387,7 +390,8 @@ int fcpp_kernel_times(fcpp_handle *h, float *ms3);
  * row-tiled.  Bit 1 set = no coverage de-duplication (by default candidates whose coverage inputs are
  * identical — same field, R, start corner; e.g. the headings of a heading search — are rasterised once
  * and share the counts).  Bit 2 set = plan and coverage as ONE fused kernel with CTA roles (measured slower on
- * config 2, see fcpp_hot.cu; default: two launches).
+ * config 2, see fcpp_hot.cu; default: two launches).  Bits 6 / 7 override fcpp_batch.cover_dedupe's choice
+ * between one coverage CTA per candidate (bit 6) and the persistent grid over the listed representatives (bit 7).
  * All modes give identical results (tests/test_gpu_parity.py compares them). */
 int fcpp_set_cover_mode(fcpp_handle *h, int mode);
 

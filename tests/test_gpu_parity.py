@@ -719,3 +719,51 @@ def test_results_are_views_of_pinned_buffers_that_outlive_later_calls(fc):
         assert r.summary.tobytes() == keep[0].tobytes() and np.array_equal(r.offsets, keep[2])
         del r
     assert len(_ResultPool._bufs) <= n_before        # steady state: no new pinned allocations
+
+
+def test_pipelined_and_speculatively_sized_batches_identical(fc):
+    """plan_batch(..., wait=False) / PendingBatch.result() with several batches in flight, and launches sized from
+    remembered batches of the same shape (no layout read-back): byte-identical to the synchronous, layout-sized
+    call; a batch that does not fit the remembered sizes is detected through the status flags and repeated."""
+    import torch
+    from field_coverage_path_planning_b200 import batch as B
+    veh = fc.VehicleParams()
+    B._Hints._c.clear()
+    small = fc.candidate_axes(1, radii=np.linspace(5.0, 6.0, 64), start_corners=[0, 1, 2, 3])
+    big = fc.candidate_axes(1, radii=np.linspace(11.0, 12.0, 64), start_corners=[0, 1, 2, 3])     # more headland loops
+    heads = fc.candidate_axes(2, headings=np.deg2rad(np.arange(0.0, 180.0, 7.0)))
+    para = [(100, 50), (600, 120), (640, 330), (140, 260)]
+    for outputs in ("paths", "summary"):
+        ref_small = fc.plan_batch([RECT], veh, small, obstacles=[OBST2], outputs=outputs, winners=True)     # sized by its layout
+        assert not ref_small.extras["speculative"]
+        again = fc.plan_batch([RECT], veh, small, obstacles=[OBST2], outputs=outputs, winners=True)         # remembered sizes
+        assert again.extras["speculative"]
+        assert again.summary.tobytes() == ref_small.summary.tobytes()
+        assert np.array_equal(again.winner_paths[0][0], ref_small.winner_paths[0][0])
+        # same shape, longer plans: the remembered sizes are too small -> flagged -> repeated from its own layout
+        r_big = fc.plan_batch([RECT], veh, big, obstacles=[OBST2], outputs=outputs, winners=True)
+        assert not r_big.extras["speculative"] and (r_big.summary["status"] == 0).all()
+        assert r_big.summary["n_head"].max() > ref_small.summary["n_head"].max()
+        B._Hints._c.clear()
+        want_big = fc.plan_batch([RECT], veh, big, obstacles=[OBST2], outputs=outputs, winners=True)
+        assert want_big.summary.tobytes() == r_big.summary.tobytes()
+        if outputs == "paths":
+            n = int(want_big.offsets[-1])
+            assert np.array_equal(want_big.offsets, r_big.offsets) and torch.equal(want_big.d_path[:n], r_big.d_path[:n])
+    # several batches in flight, collected out of order
+    B._Hints._c.clear()
+    jobs = [([RECT], small, [OBST2], "paths"), ([para, RECT], heads, None, "summary"), ([RECT], big, [OBST2], "paths"),
+            ([RECT], small, [OBST2], "summary")]
+    want = [fc.plan_batch(f, veh, c, obstacles=o, outputs=out, winners=True) for f, c, o, out in jobs]
+    for rounds in range(2):          # second round: every shape is remembered
+        pend = [fc.plan_batch(f, veh, c, obstacles=o, outputs=out, winners=True, wait=False) for f, c, o, out in jobs]
+        assert all(isinstance(p, B.PendingBatch) for p in pend)
+        for k in (2, 0, 3, 1):
+            got = pend[k].result()
+            assert got is pend[k].result()
+            assert got.summary.tobytes() == want[k].summary.tobytes()
+            assert np.array_equal(got.best_cand, want[k].best_cand) and np.array_equal(got.best_cost, want[k].best_cost)
+            assert got.winner_paths.keys() == want[k].winner_paths.keys()
+            for f in got.winner_paths:
+                assert np.array_equal(got.winner_paths[f][0], want[k].winner_paths[f][0])
+                assert np.array_equal(got.winner_paths[f][1], want[k].winner_paths[f][1])

@@ -156,7 +156,7 @@ def test_prepare_batch_host_setup(built):
     assert (((f2 & _lib.FLAG_REVERSE_ORDER) != 0) == (c2["start_corner"] == 3)).all()
     assert ((f2 & _lib.FLAG_START_FROM_RIGHT) == 0).all()
     # coverage de-duplication is requested when a candidate axis repeats coverage work (fcpp_batch.cover_dedupe)
-    assert pb.dedupe and p2.dedupe
+    assert pb.dedupe == 2 and p2.dedupe == 1     # 2: a heading axis (few coverage representatives expected)
     assert not fc.prepare_batch([rect], fc.VehicleParams(), fc.make_candidates(1, radii=[5.0, 6.0])).dedupe
     assert not fc.prepare_batch([rect, tilted], fc.VehicleParams(), fc.make_candidates(2, start_corners=[1])).dedupe
 
