@@ -132,7 +132,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
-    "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_field_argmin_merge", "fcpp_field_argmin_exchange", "fcpp_winner_records", "fcpp_speed_verify", "fcpp_raster_window",
+    "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_field_argmin_merge", "fcpp_field_argmin_exchange", "fcpp_winner_records", "fcpp_status_count", "fcpp_speed_verify", "fcpp_raster_window",
     "fcpp_tour_lengths", "fcpp_distance_matrix", "fcpp_connection_matrix", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve", "fcpp_kmeans_lloyd",
     "fcpp_launch_count", "fcpp_last_fused", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_last_total_points", "fcpp_set_profiling", "fcpp_kernel_times", "fcpp_set_cover_mode",
 ]
@@ -177,6 +177,8 @@ def load():
         L.fcpp_field_argmin_merge.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.fcpp_winner_records.restype = C.c_int
         L.fcpp_winner_records.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
+        L.fcpp_status_count.restype = C.c_int
+        L.fcpp_status_count.argtypes = [vp, vp, i64, i32, vp, vp]
         L.fcpp_speed_verify.restype = C.c_int
         L.fcpp_speed_verify.argtypes = [vp, C.POINTER(Vehicle), vp, vp, vp, i64, i64, C.c_int, vp, vp, vp, vp]
         L.fcpp_raster_window.restype = C.c_int

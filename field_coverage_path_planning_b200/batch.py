@@ -874,7 +874,7 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     if distributed:
         from . import dist
         return dist.plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h,
-                                       coverage, cost, device, want_curvature, turn_model, clothoid_share, winners)
+                                       coverage, cost, device, want_curvature, turn_model, clothoid_share, winners, wait)
     dev = _dev(device)
     pb = prepare_batch(fields, vehicle, candidates, obstacles, start_points, grid_h, coverage, turn_model,
                        clothoid_share)

@@ -354,6 +354,17 @@ int fcpp_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t c
     return FCPP_OK;
 }
 
+int fcpp_status_count(fcpp_handle *h, const fcpp_summary *d_summary, int64_t n_cand, int32_t mask, int32_t *d_count,
+                      void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (n_cand < 0 || !d_count || (n_cand > 0 && !d_summary)) return fail(h, FCPP_ERR_INVALID, "fcpp_status_count: bad argument");
+    cudaSetDevice(h->device);
+    cudaError_t e = fcpp_launch_status_count(h, d_summary, n_cand, mask, d_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "status count kernel");
+    return FCPP_OK;
+}
+
 int fcpp_field_argmin_exchange(fcpp_handle *h, int32_t world, int32_t rank, int32_t n_fields, uint32_t epoch,
                                const uint64_t *peer_bufs, const uint64_t *peer_flags, double *d_best_cost,
                                int64_t *d_best_cand, void *stream)

@@ -623,6 +623,8 @@ cudaError_t fcpp_launch_argmin_exchange(fcpp_handle *h, int32_t world, int32_t r
 cudaError_t fcpp_launch_distance_matrix(fcpp_handle *h, const double *d_pos, int32_t n, double *d_D, cudaStream_t st);
 cudaError_t fcpp_launch_connection_matrix(fcpp_handle *h, const double *d_verts, int32_t n_fields, double depot_x,
                                           double depot_y, double *d_C, int32_t *d_arg, cudaStream_t st);
+cudaError_t fcpp_launch_status_count(fcpp_handle *h, const fcpp_summary *d_summary, int64_t n, int mask, int32_t *d_count,
+                                     cudaStream_t st);
 cudaError_t fcpp_launch_argmin(fcpp_handle *h, const fcpp_summary *d_summary, const int32_t *d_cand_field,
                                int64_t n_cand, int32_t n_fields, int cost_kind, int64_t cand_base,
                                double *d_best_cost, int64_t *d_best_cand, cudaStream_t st);

@@ -318,6 +318,28 @@ cudaError_t fcpp_launch_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, 
     return cudaGetLastError();
 }
 
+// number of candidates whose status has one of the bits of `mask`
+__global__ void status_count_kernel(const fcpp_summary *__restrict__ sm, int64_t n, int mask, int32_t *__restrict__ count)
+{
+    int hits = 0;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x)
+        hits += (sm[c].status & mask) != 0;
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(count, hits);
+}
+
+cudaError_t fcpp_launch_status_count(fcpp_handle *h, const fcpp_summary *d_summary, int64_t n, int mask, int32_t *d_count,
+                                     cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess || n == 0) return e;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 4 * (int64_t)h->sm_count) blocks = 4 * (int64_t)h->sm_count;
+    status_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_summary, n, mask, d_count);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t fcpp_launch_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t lo, int64_t hi,
                                        const int64_t *d_best_cand, int32_t n_fields, void *d_out, cudaStream_t st)
 {

@@ -135,23 +135,31 @@ def reduce_best(best_cost: torch.Tensor, best_cand: torch.Tensor, group=None, pe
 
 
 def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, lo: int, hi: int,
-                          group=None) -> torch.Tensor:
+                          group=None, count_mask: int = 0) -> torch.Tensor:
     """[F, 176] uint8: the summary record of every field's global winner.
     ``summary_bytes`` = this rank's records as a flat uint8 tensor ((hi-lo)*176 bytes).
     CUDA: one library kernel writes the records this rank owns (zeros elsewhere), one all-reduce sums them;
-    CPU tensors (gloo tests): the same with torch ops."""
+    CPU tensors (gloo tests): the same with torch ops.
+    ``count_mask`` != 0 (CUDA): the returned tensor is flat, F * 176 + 16 bytes — behind the records rides one
+    int32 word, the number of candidates OF ALL RANKS whose status has a bit of the mask (fcpp_status_count; the
+    same all-reduce sums it): every rank learns in the same read-back whether any rank's launch sizes were too
+    small, so that all of them repeat the batch together."""
     rec = _lib.SUMMARY_DTYPE.itemsize
     F = best_cand.numel()
     if best_cand.is_cuda:
         import ctypes as C
         dev = best_cand.device
-        out = torch.empty((F, rec), dtype=torch.uint8, device=dev)
+        out = torch.empty(F * rec + (16 if count_mask else 0), dtype=torch.uint8, device=dev)
         h = _lib.handle(dev.index)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         h.check(h.lib.fcpp_winner_records(h.h, summary_bytes.data_ptr() if hi > lo else None, lo, hi,
                                           best_cand.data_ptr(), F, out.data_ptr(), st))
+        if count_mask:
+            out[F * rec + 4:].zero_()
+            h.check(h.lib.fcpp_status_count(h.h, summary_bytes.data_ptr() if hi > lo else None, hi - lo, count_mask,
+                                            out.data_ptr() + F * rec, st))
         dist.all_reduce(out.view(torch.int32), op=dist.ReduceOp.SUM, group=group)
-        return out
+        return out if count_mask else out.view(F, rec)
     own = (best_cand >= lo) & (best_cand < hi)
     idx = torch.where(own, best_cand - lo, torch.zeros_like(best_cand))
     rows = summary_bytes.view(-1, rec)[idx] if hi > lo else torch.zeros((F, rec), dtype=torch.uint8,
@@ -162,21 +170,82 @@ def gather_winner_records(summary_bytes: torch.Tensor, best_cand: torch.Tensor, 
     return words.view(torch.uint8).view(F, rec)
 
 
+class PendingShardedBatch:
+    """A sharded batch in flight on every rank (``plan_batch(..., distributed=True, wait=False)``).  ``result()`` is
+    COLLECTIVE in one case only: when some rank's remembered launch sizes did not fit its shard (every rank sees
+    that in the flag word that rides on the winners' records), all ranks repeat the batch together."""
+
+    def __init__(self, db, pf, hw, outputs, args, lo, hi, speculated):
+        self.db, self.pf, self.hw, self.outputs, self.args = db, pf, hw, outputs, args
+        self.lo, self.hi, self.speculated = lo, hi, speculated
+        self._res = None
+
+    def result(self):
+        from .batch import _Hints, _finish_fetch, _side_stream, fetch_winner_paths
+        if self._res is not None:
+            return self._res
+        db, pf, outputs = self.db, self.pf, self.outputs
+        want_curvature, cost, winners = self.args
+        pb = db.pb
+        F = pb.n_fields
+        rec = _lib.SUMMARY_DTYPE.itemsize
+        res = _finish_fetch(pf)                                    # ONE synchronisation
+        hv = self.hw[1]
+        if self.speculated and int(hv[F * rec:F * rec + 4].view(np.int32)[0]) != 0:
+            # a rank's remembered sizes were too small (or a candidate is genuinely too large): every rank sees the
+            # same word and launches the batch again, sized from its own layout pass
+            _Hints.drop(_Hints.key(db, outputs, want_curvature))
+            self._res = _submit_sharded(db, outputs, want_curvature, cost, winners, self.lo, self.hi, False).result()
+            return self._res
+        res.extras["winner_summary"] = hv[:F * rec].view(_lib.SUMMARY_DTYPE).reshape(-1)[:F]
+        res.extras["shard"] = (self.lo, self.hi)
+        res.extras["h2d_bytes"] = pb.h2d_bytes()
+        res.extras["d2h_bytes"] = (len(res.summary) * rec + 16 * F + F * rec + 16
+                                   + ((pb.n_cand + 1) * 8 if outputs == "paths" else 0))
+        res.extras["speculative"] = bool(pf.buffers.speculative)
+        if winners:
+            with torch.cuda.stream(_side_stream(db.dev)):      # not behind later batches in flight
+                res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs, slot=db.slot + 1)
+        self._res = res
+        return res
+
+
+def _submit_sharded(db, outputs, want_curvature, cost, winners, lo, hi, speculate):
+    """Kernels of this rank's shard, the two collectives and the read-back, all enqueued on the current stream."""
+    from .batch import _SIZE_FLAGS, _ResultPool, _Staging, _enqueue_fetch, _launch_device_batch
+    dev = db.dev
+    F = db.pb.n_fields
+    rec = _lib.SUMMARY_DTYPE.itemsize
+    bufs, offsets = _launch_device_batch(db, outputs, want_curvature, cost, lo, None, speculate=speculate)
+    reduce_best(bufs.d_cost, bufs.d_best)                   # in place: d_cost / d_best now hold the GLOBAL result
+    # every rank passes the mask whether or not IT speculated: the all-reduce must have the same shape everywhere
+    win = gather_winner_records(bufs.d_sum, bufs.d_best, lo, hi, count_mask=_SIZE_FLAGS)
+    with torch.cuda.device(dev):                            # the winners' records ride on the same read-back
+        nb = F * rec + 16
+        pooled = _ResultPool.get(nb)
+        if pooled is None:
+            t = torch.empty(nb, dtype=torch.uint8).pin_memory()
+            pooled = (t, t.numpy())
+        pooled[0][:nb].copy_(win, non_blocking=True)
+    pf = _enqueue_fetch(db, bufs, outputs, offsets, True, lo)
+    # (the numpy view of a pooled buffer must stay referenced: the pool hands a buffer out again once its view is gone)
+    return PendingShardedBatch(db, pf, pooled, outputs, (want_curvature, cost, winners), lo, hi, bool(speculate))
+
+
 def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, outputs, grid_h, coverage, cost,
-                       device, want_curvature, turn_model="arc", clothoid_share=0.5, winners=False):
+                       device, want_curvature, turn_model="arc", clothoid_share=0.5, winners=False, wait=True):
     """plan_batch over all ranks of the default process group (see batch.plan_batch): every rank plans its
     contiguous shard; ONE all-gather + merge kernel gives every rank the per-field argmin, one kernel + one
     all-reduce every winner's summary record; the local summaries, the merged argmin and the winners' records
-    come back to the host with ONE synchronisation."""
-    from .batch import (DeviceBatch, _Staging, _dev, _fetch_device_batch, _launch_device_batch, fetch_winner_paths,
-                        prepare_batch)
+    come back to the host with ONE synchronisation.  Launch sizes are remembered from earlier batches of the same
+    shape (no layout read-back); ``wait=False`` returns a ``PendingShardedBatch``."""
+    from .batch import DeviceBatch, _dev, axes_count, is_axes, prepare_batch
     if not dist.is_initialized():
         raise RuntimeError("distributed=True needs torch.distributed.init_process_group (backend 'nccl')")
     world, rank = dist.get_world_size(), dist.get_rank()
     fv = np.asarray(fields, dtype=np.float64).reshape(-1, 4, 2)
     if candidates is None:
         candidates = {"field_id": np.arange(len(fv), dtype=np.int32)}
-    from .batch import axes_count, is_axes
     n = axes_count(candidates) if is_axes(candidates) else len(candidates["field_id"])
     local, lo = shard_candidates(candidates, world, rank)
     hi = lo + (axes_count(local) if is_axes(local) else len(local["field_id"]))
@@ -184,20 +253,5 @@ def plan_batch_sharded(fields, vehicle, candidates, obstacles, start_points, out
     dev = _dev(device)
     pb = prepare_batch(fv, vehicle, local, obstacles, sp, grid_h, coverage, turn_model, clothoid_share)
     db = DeviceBatch(pb, dev)
-    F = pb.n_fields
-    bufs, offsets = _launch_device_batch(db, outputs, want_curvature, cost, lo, None)
-    reduce_best(bufs.d_cost, bufs.d_best)                   # in place: d_cost / d_best now hold the GLOBAL result
-    win = gather_winner_records(bufs.d_sum, bufs.d_best, lo, hi)
-    rec = _lib.SUMMARY_DTYPE.itemsize
-    with torch.cuda.device(dev):                            # the winners' records ride on the same read-back
-        hw = _Staging.get(dev, 7).host_out(max(F * rec, 256))
-        if F:
-            hw[:F * rec].copy_(win.view(-1), non_blocking=True)
-    res = _fetch_device_batch(db, bufs, outputs, offsets, True, lo)     # ONE synchronisation
-    res.extras["winner_summary"] = hw.numpy()[:F * rec].copy().view(_lib.SUMMARY_DTYPE).reshape(-1)[:F]
-    res.extras["shard"] = (lo, hi)
-    res.extras["h2d_bytes"] = pb.h2d_bytes()
-    res.extras["d2h_bytes"] = (len(res.summary) * rec + 16 * F + F * rec + ((pb.n_cand + 1) * 8 if outputs == "paths" else 0))
-    if winners:
-        res.extras["d2h_bytes"] += fetch_winner_paths(db, res, outputs)
-    return res
+    pend = _submit_sharded(db, outputs, want_curvature, cost, winners, lo, hi, True)
+    return pend if not wait else pend.result()

@@ -241,6 +241,12 @@ int fcpp_field_argmin_merge(fcpp_handle *h, const int64_t *d_gathered, int32_t w
 int fcpp_winner_records(fcpp_handle *h, const fcpp_summary *d_summary, int64_t cand_lo, int64_t cand_hi,
                         const int64_t *d_best_cand, int32_t n_fields, void *d_out, void *stream);
 
+/* *d_count = number of candidates whose status has a bit of `mask` (e.g. FCPP_CAND_TOO_LARGE |
+ * FCPP_CAND_GRID_TOO_LARGE: a caller that sized a launch from hints of an earlier batch learns on the device —
+ * and, summed over the ranks, collectively — whether the sizes were sufficient). */
+int fcpp_status_count(fcpp_handle *h, const fcpp_summary *d_summary, int64_t n_cand, int32_t mask, int32_t *d_count,
+                      void *stream);
+
 /* Multi-GPU, fused form of all-gather + fcpp_field_argmin_merge: ONE kernel writes this rank's (cost, candidate)
  * words into every rank's symmetric buffer over peer memory (NVLink P2P stores), publishes a flag per rank,
  * waits for the other ranks' flags and merges — no NCCL call.  d_best_cost / d_best_cand hold the local result

@@ -21,6 +21,9 @@ from field_coverage_path_planning_b200 import dist as fdist  # noqa: E402
 
 
 def main():
+    import faulthandler
+    # a hang (a collective some rank never reaches) must not hold the GPUs: stacks of all threads, then exit
+    faulthandler.dump_traceback_later(int(os.environ.get("FCPP_WORKER_WATCHDOG_S", "150")), exit=True)
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
@@ -76,10 +79,37 @@ def main():
         if not good:
             ok = False
             print("SHARDED MISMATCH rank", rank, flush=True)
+    # ---- 3. factored candidate sets, remembered launch sizes, two sharded batches in flight, collective repeat ----
+    from field_coverage_path_planning_b200 import batch as fbatch
+    fbatch._Hints._c.clear()
+    small_ax = fc.candidate_axes(1, radii=np.linspace(5.0, 6.0, 16 * world), start_corners=[0, 1, 2, 3])
+    # same shape, but ONE rank's shard holds longer headlands: its remembered sizes do not fit -> all ranks repeat
+    radii = np.linspace(5.0, 6.0, 16 * world)
+    radii[-8:] = np.linspace(11.0, 12.0, 8)
+    odd_ax = fc.candidate_axes(1, radii=radii, start_corners=[0, 1, 2, 3])
+    heads_ax = fc.candidate_axes(3, headings=np.deg2rad(np.arange(0.0, 180.0, 5.0)))
+    jobs = [([rect], small_ax, "paths"), ([rect], odd_ax, "paths"), ([rect, small, tiny], heads_ax, "summary"),
+            ([rect], small_ax, "summary")]
+    want = [fc.plan_batch(f, veh, fc.expand_axes(c), outputs=o, device=dev) for f, c, o in jobs]
+    for rounds in range(2):
+        pend = [fc.plan_batch(f, veh, c, outputs=o, device=dev, distributed=True, winners=True, wait=False) for f, c, o in jobs]
+        for k in (1, 0, 2, 3):                      # the same order on every rank (a repeat is collective)
+            got = pend[k].result()
+            lo, hi = got.extras["shard"]
+            good = (np.array_equal(got.best_cand, want[k].best_cand) and np.array_equal(got.best_cost, want[k].best_cost)
+                    and got.summary.tobytes() == want[k].summary[lo:hi].tobytes())
+            for f, (pth, spd, _) in got.winner_paths.items():
+                wp, ws, _ = want[k].path(int(want[k].best_cand[f])) if want[k].d_path is not None else (None, None, None)
+                if wp is not None:
+                    good = good and np.array_equal(pth, wp) and np.array_equal(spd, ws)
+            if not good:
+                ok = False
+                print("PIPELINED SHARDED MISMATCH rank", rank, "job", k, "round", rounds, flush=True)
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI GPU CHECK", "OK" if t.item() else "FAILED", flush=True)
+    faulthandler.cancel_dump_traceback_later()
     dist.destroy_process_group()
     return 0 if t.item() else 1
 

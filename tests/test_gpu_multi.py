@@ -23,5 +23,13 @@ def test_exchange_and_sharded_plan_batch_on_two_or_more_gpus():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "_multi_gpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
-    assert r.returncode == 0 and "MULTI GPU CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # own process group: a timeout must take the ranks down with the launcher (they would keep the GPUs busy)
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=root, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(p.pid, signal.SIGKILL)
+        out, err = p.communicate()
+        raise AssertionError("multi-GPU worker timed out\n" + out[-2000:] + err[-4000:])
+    assert p.returncode == 0 and "MULTI GPU CHECK OK" in out, out[-2000:] + err[-4000:]
