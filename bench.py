@@ -305,11 +305,16 @@ def main():
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step_device()
-    sync_all()
     # ---- the K timed steps (CUDA events per step; per-kernel event times at N = 1) ----
+    # everything that takes host time (NVML initialisation, event creation) happens BEFORE the barrier: ranks that
+    # leave it at different times would spend the difference inside the first step's collective
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    sampler.sm.clear()
+    sampler.power.clear()
+    sampler.reasons.clear()
     ktimes = []
     l0 = h.launches
     t_wall0 = time.perf_counter()
@@ -376,10 +381,13 @@ def main():
             t = torch.tensor([n_sus], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             n_sus = int(t.item())
-        sync_all()
         s2 = ClockSampler(local_rank)
         s2.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        s2.sm.clear()
+        s2.power.clear()
+        s2.reasons.clear()
         t0 = time.perf_counter()
         e0.record()
         for _ in range(n_sus):
@@ -465,7 +473,7 @@ def main():
         dom, ach = "cover_kernel", bytes_cover / (k_cover * 1e-3) / 1e9
     else:
         dom, ach = "plan_kernel", bytes_plan / (k_plan * 1e-3) / 1e9
-    nm = ncu_metrics(dom, w.name)
+    nm = ncu_metrics("plan_gen_kernel" if dom == "plan_kernel" else dom, w.name) or ncu_metrics(dom, w.name)
     roofline = {"bound": "issue", "kernel": dom,
                 "issue_slot_frac": nm.get("issue_slot_frac"), "fp64_pipe_frac": nm.get("fp64_pipe_frac"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -499,7 +507,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "detail": {"points_per_plan": n_pts_mean, "fields": F,
-                       "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
+                       "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+                       "step_ms_rank0": [round(a.elapsed_time(b), 4) for a, b in ev]},
             "clocks": clocks, "sustained": sustained, "argmin_ok": argmin_ok,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "argmin_ok": e2e_ok, "mode": e2e_mode, "serial_value": e2e_serial,
