@@ -1152,7 +1152,9 @@ __device__ __forceinline__ void cover_body(const fcpp_batch &b, const CandRec *_
             sum->cov_cells = (ok && !err11) ? (int64_t)s.acc[1] : 0;
         }
     }
-    if (tid == 0 && (err10 | err11)) sum->status |= FCPP_CAND_GRID_TOO_LARGE;
+    if (tid == 0 && (err10 | err11))
+        sum->status |= FCPP_CAND_GRID_TOO_LARGE | (err10 ? FCPP_CAND_CORNER_GRID_TOO_LARGE : 0) |
+                       (err11 ? FCPP_CAND_BAND_GRID_TOO_LARGE : 0);
 }
 
 __global__ void __launch_bounds__(T, FCPP_COVER_MINBLOCKS) cover_kernel(const fcpp_batch b, const CandRec *__restrict__ recs,
@@ -1296,13 +1298,16 @@ __global__ void __launch_bounds__(128) cover_copy_kernel(fcpp_summary *__restric
             dst.corner_before[k] = src.corner_before[k];
             dst.corner_after[k] = src.corner_after[k];
         }
-        if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+        // only the part that was shared: the representative's detail bit of THIS part is final since the coverage
+        // kernel (this kernel only ever adds the other part's bits to a candidate that represents a part)
+        if (src.status & FCPP_CAND_CORNER_GRID_TOO_LARGE)
+            dst.status |= FCPP_CAND_GRID_TOO_LARGE | FCPP_CAND_CORNER_GRID_TOO_LARGE;
     }
     if (q1 != (int32_t)c) {
         const fcpp_summary &src = summary[q1];
         dst.cov_cells = src.cov_cells;
         dst.cov_total = src.cov_total;
-        if (src.status & FCPP_CAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE;
+        if (src.status & FCPP_CAND_BAND_GRID_TOO_LARGE) dst.status |= FCPP_CAND_GRID_TOO_LARGE | FCPP_CAND_BAND_GRID_TOO_LARGE;
     }
 }
 

@@ -55,7 +55,9 @@ typedef enum {
 #define FCPP_CAND_TOO_MANY_LOOPS 4
 #define FCPP_CAND_TOO_LARGE 8     /* the staged part exceeds the shared-memory capacity, or the plan's points the
                                      caller's path buffers (fcpp_outputs.path_capacity) */
-#define FCPP_CAND_GRID_TOO_LARGE 16
+#define FCPP_CAND_GRID_TOO_LARGE 16 /* a coverage grid does not fit the kernel's tiles; detail in the next two bits */
+#define FCPP_CAND_CORNER_GRID_TOO_LARGE 32 /* ... the corner windows (A10); set together with 16 */
+#define FCPP_CAND_BAND_GRID_TOO_LARGE 64   /* ... the headland band (A11); set together with 16 */
 
 typedef struct fcpp_handle fcpp_handle;
 
