@@ -374,8 +374,8 @@ def prepare_batch(fields, vehicle: VehicleParams, candidates: Optional[Dict[str,
         arrays["obs_vert_start"] = np.asarray(vert_start, dtype=np.int32)
         arrays["obs_verts"] = np.asarray(verts, dtype=np.float64).reshape(-1, 2)
         arrays["obs_moments"] = np.asarray(moms, dtype=np.float64).reshape(-1, 3)
-    if turn_model not in ("arc", "clothoid"):
-        raise ValueError("turn_model must be 'arc' (the reference's sampled arcs) or 'clothoid'")
+    if turn_model not in ("arc", "clothoid", "omega"):
+        raise ValueError("turn_model must be 'arc' (the reference's sampled arcs), 'clothoid' or 'omega'")
     return PreparedBatch(vehicle, F, B, arrays, max_v, max_p, float(grid_h), bool(coverage), turn_model,
                          float(clothoid_share), dedupe=dedupe, axes=axes, cand_first=int(cand_first))
 
@@ -404,7 +404,7 @@ class DeviceBatch:
         b.max_obs_polys = pb.max_obs_polys
         b.grid_h = pb.grid_h
         b.do_coverage = 1 if pb.coverage else 0
-        b.turn_model = 1 if pb.turn_model == "clothoid" else 0
+        b.turn_model = {"arc": 0, "clothoid": 1, "omega": 2}[pb.turn_model]
         # the headings of a field repeat its headland (hence its coverage), its start corners repeat the
         # corner-window verification: identical coverage work is done once per group on the device
         b.cover_dedupe = int(pb.dedupe)
@@ -858,6 +858,12 @@ def plan_batch(fields, vehicle: Optional[VehicleParams] = None, candidates: Opti
     U-turns and headland corners by clothoid -> arc -> clothoid turns (same sample counts) whose
     Fresnel integrals are evaluated per sample point on the device; ``clothoid_share`` in (0, 1] is
     the share of each turn's deflection spent on the clothoids.
+
+    ``turn_model='omega'`` (opt-in, the "Ω型跨行" pattern the reference only names, mlp3:312-320; build-defined and
+    parity-unpinned like the clothoid): the rows of the main work are visited in skip order (blocks of 2 s rows,
+    s = ceil(2 R / W), lower and upper half alternating) and every 20-sample turn connects the two swath ends — a
+    half circle of radius gap / 2, or the Ω (bulb) turn of three radius-R arcs where the gap is below 2 R.  Rows,
+    swath ends, sample counts and the headland are the U pattern's.
 
     ``winners=True`` also returns every field's winning path and speed profile on the host
     (``BatchResult.winner_paths``) — what a search caller needs from a batch.

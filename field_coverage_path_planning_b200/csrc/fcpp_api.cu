@@ -91,8 +91,8 @@ int check_batch(fcpp_handle *h, const fcpp_batch *b)
     if (b->obs_poly_start && (!b->obs_vert_start || !b->obs_verts || !b->obs_moments))
         return fail(h, FCPP_ERR_INVALID, "obstacle tables are incomplete");
     if (!(b->vehicle.working_width > 0.0)) return fail(h, FCPP_ERR_INVALID, "working_width must be > 0");
-    if (b->turn_model != FCPP_TURN_ARC && b->turn_model != FCPP_TURN_CLOTHOID)
-        return fail(h, FCPP_ERR_INVALID, "turn_model must be 0 (arc) or 1 (clothoid)");
+    if (b->turn_model != FCPP_TURN_ARC && b->turn_model != FCPP_TURN_CLOTHOID && b->turn_model != FCPP_TURN_OMEGA)
+        return fail(h, FCPP_ERR_INVALID, "turn_model must be 0 (arc), 1 (clothoid) or 2 (omega skip-row pattern)");
     if (b->turn_model == FCPP_TURN_CLOTHOID && !(b->clothoid_share > 0.0 && b->clothoid_share <= 1.0))
         return fail(h, FCPP_ERR_INVALID, "clothoid_share must be in (0, 1]");
     if (b->do_coverage) {

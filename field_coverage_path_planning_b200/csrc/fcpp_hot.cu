@@ -73,7 +73,7 @@ cudaError_t fcpp_launch_plan_cover(fcpp_handle *h, const fcpp_batch &b, const fc
     // two CTAs per SM: the limit a CTA's shared memory must stay under
     const size_t limit = ((size_t)h->max_smem_sm - 2 * 1024) / 2;
     int pc = cover_point_capacity(h->cover_pcap);
-    const bool fuse = (h->cover_mode & 4) && 4 * plan_bytes <= limit && cover_smem_bytes(pc) <= limit &&
+    const bool fuse = (h->cover_mode & 4) && b.turn_model != FCPP_TURN_OMEGA && 4 * plan_bytes <= limit && cover_smem_bytes(pc) <= limit &&
                       4 * plan_bytes <= (size_t)h->max_smem_optin;
     if (!fuse) {
         cudaError_t e = fcpp_launch_plan(h, b, o, st, nullptr);

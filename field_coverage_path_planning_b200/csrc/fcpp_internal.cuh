@@ -439,11 +439,87 @@ __host__ __device__ __forceinline__ int main_skip(int n_main) { return n_main > 
 constexpr int GEN_PER_LOOP = 21;
 constexpr int N_GENERIC = MAIN_STAGED + GEN_PER_LOOP * FCPP_MAX_LOOPS;
 
-// main-work point (visit index idx, position j in the pass) in the swath frame, before the rotate-back
+// ---- Ω (skip-row) pattern, FCPP_TURN_OMEGA: build-defined, restated in oracle/ref_planner.py (omega_*) ----
+__device__ __forceinline__ int omega_skip(double R, double W)
+{
+    const int s = (int)ceil(2.0 * R / W - 1e-9);
+    return s < 1 ? 1 : s;
+}
+// row of visit idx: blocks of 2 s rows, inside a block of m rows the lower and the upper half alternate
+__device__ __forceinline__ int omega_row(int idx, int P, int s)
+{
+    const int base = (idx / (2 * s)) * (2 * s);
+    const int m = min(2 * s, P - base);
+    const int h = (m + 1) >> 1;
+    const int k = idx - base;
+    return base + (k >> 1) + ((k & 1) ? h : 0);
+}
+// sample a of the connecting turn between two rows d_abs apart, in the turn's frame (u outwards, v towards the next
+// row): half circle of radius d_abs / 2 (table angles) or, below 2 R, the bulb turn of three radius-R arcs
+__device__ __forceinline__ void omega_turn_local(const TrigTables &tt, double d_abs, double R, int a, double &u, double &v)
+{
+    if (d_abs >= 2.0 * R) {
+        const double rho = d_abs / 2.0;
+        u = rho * tt.sin20[a];
+        v = rho - rho * tt.cos20[a];
+        return;
+    }
+    const double xc = sqrt(4.0 * R * R - (R + d_abs / 2.0) * (R + d_abs / 2.0));
+    const double alpha = atan2(xc, R + d_abs / 2.0);
+    const double pi = 3.141592653589793;
+    const double total = pi + 4.0 * alpha;
+    const double phi = (a == FCPP_UTURN_POINTS - 1) ? total : a * (total / (FCPP_UTURN_POINTS - 1));
+    if (phi <= alpha) {
+        u = R * sin(phi);
+        v = -R + R * cos(phi);
+    } else if (phi <= pi + 3.0 * alpha) {
+        const double hd = -alpha + (phi - alpha);
+        u = 2.0 * R * sin(alpha) + R * sin(hd);
+        v = (-R + 2.0 * R * cos(alpha)) - R * cos(hd);
+    } else {
+        const double hd = pi + alpha - (phi - (pi + 3.0 * alpha));
+        u = -R * sin(hd);
+        v = d_abs + R + R * cos(hd);
+    }
+}
+
+// main-work point of the Ω pattern (visit index idx, position j in the pass) in the swath frame
+static __device__ __noinline__ void omega_main_local_pt(const CandRec &r, const TrigTables &tt, double W, int idx, int j,
+                                                        double &px, double &py)
+{
+    const int os = omega_skip(r.R, W);
+    const int row = omega_row(idx, r.P, os);
+    const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - row) : row;
+    const double yy = r.min_y + pi * W;
+    const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
+    if (j < 2) {
+        const double xs = r.min_x + r.R, xe = r.max_x - r.R;
+        px = (go_left == (j == 0)) ? xe : xs;
+        py = yy;
+        return;
+    }
+    const int row2 = omega_row(idx + 1, r.P, os);
+    const int pi2 = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - row2) : row2;
+    const double d = (r.min_y + pi2 * W) - yy;
+    double u, v;
+    omega_turn_local(tt, fabs(d), r.R, j - 2, u, v);
+    const double xe = go_left ? r.min_x + r.R : r.max_x - r.R;
+    px = xe + (go_left ? -1.0 : 1.0) * u;
+    py = yy + (d >= 0.0 ? 1.0 : -1.0) * v;
+}
+
+// main-work point (visit index idx, position j in the pass) in the swath frame, before the rotate-back.
+// OMEGA is a compile-time switch (the plan kernel has an instance per pattern): a run-time test with an out-of-line
+// call at every inlined copy cost the default patterns 5-9 % (measured).
+template <bool OMEGA = false>
 __device__ __forceinline__ void main_local_pt(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W,
                                               int idx, int j, double &px, double &py)
 {
     // mlp3:744-780: visit index idx, pass index pi, 2 endpoints + 20 arc samples per pass
+    if constexpr (OMEGA) {
+        omega_main_local_pt(r, tt, W, idx, j, px, py);
+        return;
+    }
     const int pi = (r.flags & FCPP_FLAG_REVERSE_ORDER) ? (r.P - 1 - idx) : idx;
     const double yy = r.min_y + pi * W;  // mlp3:751
     const bool go_left = (r.flags & FCPP_FLAG_START_FROM_RIGHT) ? ((idx & 1) == 0) : ((idx & 1) == 1);
@@ -470,6 +546,7 @@ __device__ __forceinline__ void main_local_pt(const CandRec &r, const TrigTables
     }
 }
 
+template <bool OMEGA = false>
 __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W,
                                               int i, double &x, double &y, uint8_t &cls, int &tag, int &gord)
 {
@@ -479,7 +556,7 @@ __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables
         const int idx = i / per;
         const int j = i - idx * per;
         double px, py;
-        main_local_pt(r, tt, tm, W, idx, j, px, py);
+        main_local_pt<OMEGA>(r, tt, tm, W, idx, j, px, py);
         cls = (j < 2) ? CLS_WORK : CLS_TURN;
         if (r.flags & FCPP_FLAG_ROTATED)
             rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
@@ -576,11 +653,12 @@ __device__ __forceinline__ void gen_point_tag(const CandRec &r, const TrigTables
     gord = 0;
 }
 
+template <bool OMEGA = false>
 __device__ __forceinline__ void gen_point(const CandRec &r, const TrigTables &tt, const TurnModel &tm, double W, int i,
                                           double &x, double &y, uint8_t &cls)
 {
     int tag, gord;
-    gen_point_tag(r, tt, tm, W, i, x, y, cls, tag, gord);
+    gen_point_tag<OMEGA>(r, tt, tm, W, i, x, y, cls, tag, gord);
 }
 
 

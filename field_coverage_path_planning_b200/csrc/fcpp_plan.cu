@@ -281,9 +281,15 @@ struct GenFixed {
     int32_t n_mixed;
     double gvl[N_GENERIC];       // curvature-limited speed of the generic points
     double scratch[9 * (FCPP_PLAN_GEN_THREADS / 32) + 8];  // group reductions: 9 values per warp; scans: 2 per warp
-    double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
-    double chain_sum[8];           // per regular chain: length, time (initial speeds), time (final speeds),
-                                   // accel violations, max kappa, max a_lat, max kappa jump
+    union {
+        struct {
+            double chain_v[CHAIN_POINTS];  // final speed (km/h) of the regular chain's points
+            double chain_sum[8];           // per regular chain: length, time (initial speeds), time (final speeds),
+                                           // accel violations, max kappa, max a_lat, max kappa jump
+        };
+        double omega_part[8 * (FCPP_PLAN_GEN_THREADS / 32)];  // Ω pattern (no regular chain): the same sums of all
+                                                              // chains, per warp
+    };
     int32_t glist[N_GENERIC];    // point index of generic ordinal g (-1: none)
     uint64_t bar;
 };
@@ -350,26 +356,26 @@ __device__ __forceinline__ double final_speed(bool act, double u, double u_lim, 
     return v;
 }
 
-// geofence (D3) and obstacle (D2/D3) point tests of one generated point
-__device__ __forceinline__ void point_tests(const GenSmem &s, int n_obs_poly, double r2, double x, double y, int &n_bviol,
-                                            int &n_oviol)
+// geofence (D3) and obstacle (D2/D3) point tests of one generated point.  The tables are handed over as four
+// __restrict__ pointers instead of through the GenSmem struct: measured 2-5 % on the plan kernel (a non-inlined
+// single copy, tried against the instruction-fetch stalls, cost 15-30 %).
+__device__ __forceinline__ int point_tests_impl(const double *__restrict__ geo, const double *__restrict__ obs_xy,
+                                                const double *__restrict__ obs_bb, const int32_t *__restrict__ obs_vs,
+                                                int n_obs_poly, double r2, double x, double y)
 {
-    const double *geo = s.f->geo;
     bool outb = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         outb = outb || (geo[5 * k + 2] * (y - geo[5 * k + 1]) - geo[5 * k + 3] * (x - geo[5 * k]) < geo[5 * k + 4]);
-    n_bviol += outb;
     bool hit = false;
     for (int p = 0; p < n_obs_poly && !hit; ++p) {
-        if (x < s.obs_bb[4 * p] || y < s.obs_bb[4 * p + 1] || x > s.obs_bb[4 * p + 2] || y > s.obs_bb[4 * p + 3])
-            continue;
-        const int vs = s.obs_vs[p], ve = s.obs_vs[p + 1];
+        if (x < obs_bb[4 * p] || y < obs_bb[4 * p + 1] || x > obs_bb[4 * p + 2] || y > obs_bb[4 * p + 3]) continue;
+        const int vs = obs_vs[p], ve = obs_vs[p + 1];
         bool inside = false;
         for (int q = vs; q < ve; ++q) {
             const int q1 = (q + 1 < ve) ? q + 1 : vs;
-            const double ax = s.obs_xy[2 * q], ay = s.obs_xy[2 * q + 1];
-            const double bx = s.obs_xy[2 * q1], by = s.obs_xy[2 * q1 + 1];
+            const double ax = obs_xy[2 * q], ay = obs_xy[2 * q + 1];
+            const double bx = obs_xy[2 * q1], by = obs_xy[2 * q1 + 1];
             // even-odd crossing (oracle/geom.py point_in_polygon_crossing)
             if ((ay > y) != (by > y)) {
                 const double xi = ax + (y - ay) * (bx - ax) / (by - ay);
@@ -386,12 +392,19 @@ __device__ __forceinline__ void point_tests(const GenSmem &s, int n_obs_poly, do
         }
         hit = hit || inside;
     }
-    n_oviol += hit;
+    return (outb ? 1 : 0) | (hit ? 2 : 0);
+}
+__device__ __forceinline__ void point_tests(const GenSmem &s, int n_obs_poly, double r2, double x, double y, int &n_bviol,
+                                            int &n_oviol)
+{
+    const int m = point_tests_impl(s.f->geo, s.obs_xy, s.obs_bb, s.obs_vs, n_obs_poly, r2, x, y);
+    n_bviol += m & 1;
+    n_oviol += m >> 1;
 }
 
 
 // One generated plan by the TG threads of a group (tid = 0 .. TG-1) in their own shared-memory region.
-template <class Sync>
+template <class Sync, bool OMEGA = false>
 __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *smem, const int tid, const int64_t cand,
                                               const Sync &sync)
 {
@@ -494,7 +507,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     if (tid < 24) {
         if (r.P >= 2) {
             double px, py;
-            main_local_pt(r, f.tt, tm, W, tid < 22 ? 0 : 1, tid < 22 ? tid : tid - 22, px, py);
+            main_local_pt<OMEGA>(r, f.tt, tm, W, tid < 22 ? 0 : 1, tid < 22 ? tid : tid - 22, px, py);
             f.tpts[2 * tid] = px;
             f.tpts[2 * tid + 1] = py;
         }
@@ -611,13 +624,14 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     // tested.  (Clothoid turns are wider than the disc, and with materialised paths every point is generated
     // anyway: no classification then.)
     // ------------------------------------------------------------------------------------
+    constexpr bool omega = OMEGA;  // the Ω pattern has its own kernel instance (launch: turn_model == FCPP_TURN_OMEGA)
     const bool cull = n_skip > 0 && !a.out.path_xy && !a.out.speeds_kmh && !a.out.curvature &&
-                      tm.model != FCPP_TURN_CLOTHOID;
+                      tm.model == FCPP_TURN_ARC;
     const int i_end = 2 + n_skip;  // regular chain points: i in [2, i_end)
     int n_bviol = 0, n_oviol = 0;
     auto main_pt = [&](int idx, int j, double &x, double &y) {
         double px, py;
-        main_local_pt(r, f.tt, tm, W, idx, j, px, py);
+        main_local_pt<OMEGA>(r, f.tt, tm, W, idx, j, px, py);
         if (r.flags & FCPP_FLAG_ROTATED)
             rotate_pt(px, py, r.cos_a, r.sin_a, r.cx, r.cy, x, y);  // mlp3:709-714
         else {
@@ -673,7 +687,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     // phase 0b (warp 0): the regular chain once — acceleration passes over its 22 points (a zero-length segment
     // precedes and follows it, so it is a closed system, mlp3:560, :576), final speeds, validation, sums
     // ------------------------------------------------------------------------------------
-    if (tid < 32 && n_skip > 0) {
+    if (tid < 32 && n_skip > 0 && !omega) {
         const bool on = lane < CHAIN_POINTS;
         const Tpl e = f.tbl[SLOT_CHAIN + (on ? lane : 0)];
         const double ds_prev = __shfl_up_sync(0xffffffffu, e.ds, 1);
@@ -744,7 +758,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         double x, y;
         uint8_t c;
         int tag, gord;
-        gen_point_tag(r, f.tt, tm, W, i, x, y, c, tag, gord);
+        gen_point_tag<OMEGA>(r, f.tt, tm, W, i, x, y, c, tag, gord);
         if (gp) gp[i] = make_double2(x, y);
         s.TAG[q] = (uint8_t)tag;
         if (gord >= 0) {
@@ -763,7 +777,81 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     // ------------------------------------------------------------------------------------
     // phase 1b: the regular chains' points (most of a plan): generated, tested, written with the chain's speeds
     // ------------------------------------------------------------------------------------
-    if (!cull) {
+    if constexpr (OMEGA) {
+        // Ω pattern: the chains (turn + next swath) are not congruent — the gap between consecutive rows varies —
+        // so every regular chain is evaluated from its coordinates, ONE WARP PER CHAIN (lane = chain point): segment
+        // lengths, curvature, limit, the two acceleration passes by shuffles (the chain is a closed system: a
+        // zero-length segment precedes and follows it), validation, sums, outputs
+        double o_len = 0.0, o_tpre = 0.0, o_t = 0.0, o_av = 0.0, o_k = 0.0, o_a = 0.0, o_j = 0.0;
+        for (int c = tid >> 5; c < n_skip / CHAIN_POINTS; c += T / 32) {
+            const bool on = lane < CHAIN_POINTS;
+            const int i = 2 + c * CHAIN_POINTS + (on ? lane : 0);
+            const int idx = i / CHAIN_POINTS, j = i - idx * CHAIN_POINTS;
+            double x, y;
+            main_pt(idx, j, x, y);
+            const double xp = __shfl_up_sync(0xffffffffu, x, 1), yp = __shfl_up_sync(0xffffffffu, y, 1);
+            const double xn = __shfl_down_sync(0xffffffffu, x, 1), yn = __shfl_down_sync(0xffffffffu, y, 1);
+            // the chain's first point repeats the swath end before it, its last point is repeated by the next turn
+            const double dx1 = lane > 0 ? x - xp : 0.0, dy1 = lane > 0 ? y - yp : 0.0;
+            const double dx2 = lane < CHAIN_POINTS - 1 ? xn - x : 0.0, dy2 = lane < CHAIN_POINTS - 1 ? yn - y : 0.0;
+            const double ds1 = sqrt_z(dx1 * dx1 + dy1 * dy1), ds = sqrt_z(dx2 * dx2 + dy2 * dy2);
+            const double kap = curvature3(dx1, dy1, ds1, dx2, dy2, ds);
+            const double v0 = (lane < FCPP_UTURN_POINTS) ? veh.headland_turn_speed_kmh : veh.max_work_speed_kmh;
+            const double vl = vlimit(v0, kap, veh);
+            const double vms = div36(vl);
+            const double u_lim = vms * vms;
+            const double v0n = __shfl_down_sync(0xffffffffu, v0, 1);
+            MP inc;
+            inc.C = (on && lane > 0 && !(ds1 < FCPP_ZERO_LEN)) ? two_a * ds1 : INFINITY;
+            inc.M = on ? u_lim : INFINITY;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const MP o = mp_shfl_up(inc, d);
+                if (lane >= d) inc = mp_combine(o, inc);
+            }
+            const double fwd = inc.M;
+            const int src = CHAIN_POINTS - 1 - lane;  // backward pass over the mirrored lanes
+            const double f_m = __shfl_sync(0xffffffffu, fwd, src & 31);
+            const double ds_m = __shfl_sync(0xffffffffu, ds, src & 31);
+            MP bk;
+            bk.C = (on && lane > 0 && !(ds_m < FCPP_ZERO_LEN)) ? two_a * ds_m : INFINITY;
+            bk.M = on ? f_m : INFINITY;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const MP o = mp_shfl_up(bk, d);
+                if (lane >= d) bk = mp_combine(o, bk);
+            }
+            const double u_fin = __shfl_sync(0xffffffffu, bk.M, src & 31);
+            const double v = do_scan ? final_speed(on, u_fin, u_lim, vl) : vl;
+            const double v_next = __shfl_down_sync(0xffffffffu, v, 1);
+            const double k_next = __shfl_down_sync(0xffffffffu, kap, 1);
+            if (on) {
+                if (gp) gp[i] = make_double2(x, y);
+                if (gs) gs[i] = v;
+                if (gk) gk[i] = kap;
+                point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
+                if (lane < CHAIN_POINTS - 1) {
+                    o_len += ds;
+                    o_tpre += div_z(ds, fmax(div36((v0 + v0n) / 2), FCPP_MIN_SPEED_MS));
+                    o_t += div_z(ds, fmax(div36((v + v_next) / 2), FCPP_MIN_SPEED_MS));
+                    o_j = fmax(o_j, fabs(k_next - kap));
+                }
+                const double vm = div36(v);
+                const double alat = vm * vm * kap;
+                o_av += (alat > veh.max_lateral_accel) ? 1.0 : 0.0;
+                o_k = fmax(o_k, kap);
+                o_a = fmax(o_a, alat);
+            }
+        }
+        // per-warp partials in a fixed order (deterministic sums); thread 0 adds them to the plan's totals
+        o_len = warp_sum(o_len), o_tpre = warp_sum(o_tpre), o_t = warp_sum(o_t), o_av = warp_sum(o_av);
+        o_k = warp_max(o_k), o_a = warp_max(o_a), o_j = warp_max(o_j);
+        if (lane == 0) {
+            double *part = f.omega_part + 8 * (tid >> 5);
+            part[0] = o_len, part[1] = o_tpre, part[2] = o_t, part[3] = o_av, part[4] = o_k, part[5] = o_a, part[6] = o_j;
+        }
+    }
+    if (!omega && !cull) {
         for (int i = 2 + tid; i < i_end; i += T) {
             const int idx = i / CHAIN_POINTS;
             const int j = i - idx * CHAIN_POINTS;
@@ -775,7 +863,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
             if (gk) gk[i] = f.tbl[SLOT_CHAIN + c].kap;
             point_tests(s, n_obs_poly, r2, x, y, n_bviol, n_oviol);
         }
-    } else {
+    } else if (!omega) {
         // the swaths' far ends (j = 0) of passes 1 ...; then the points of the listed passes, densely indexed
         for (int idx = 1 + tid; idx * CHAIN_POINTS < i_end; idx += T) {
             double x, y;
@@ -805,7 +893,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
 #pragma unroll 1
         for (int d = 0; d < 3; ++d) {
             const int qq = i - 1 + d;
-            if (qq >= 0 && qq < N) gen_point(r, f.tt, tm, W, qq, P3[d][0], P3[d][1], C3[d]);
+            if (qq >= 0 && qq < N) gen_point<OMEGA>(r, f.tt, tm, W, qq, P3[d][0], P3[d][1], C3[d]);
         }
         const double dx1 = P3[1][0] - P3[0][0], dy1 = P3[1][1] - P3[0][1];
         const double dx2 = P3[2][0] - P3[1][0], dy2 = P3[2][1] - P3[1][1];
@@ -958,7 +1046,14 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     if (tid == 0 && sum) {
         // the regular chains: one chain's sums times their number
         const double nreg = (double)(n_skip / CHAIN_POINTS);
-        const bool reg = n_skip > 0;
+        const bool reg = n_skip > 0 && !omega;  // (the Ω pattern's chains went into the sums one by one)
+        if (omega && n_skip > 0) {
+            for (int w = 0; w < T / 32; ++w) {
+                const double *part = f.omega_part + 8 * w;
+                sums[0] += part[0], sums[2] += part[1], sums[4] += part[2], sums[6] += part[3];
+                mx[0] = fmax(mx[0], part[4]), mx[1] = fmax(mx[1], part[5]), mx[2] = fmax(mx[2], part[6]);
+            }
+        }
         sum->status = 0;
         sum->len_main = sums[0] + (reg ? nreg * f.chain_sum[0] : 0.0);
         sum->len_head = sums[1];
@@ -978,6 +1073,12 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
             for (int k = 0; k < 4; ++k) sum->corner_before[k] = sum->corner_after[k] = 0;
         }
     }
+}
+
+__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_omega_kernel(const PlanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    plan_gen_body<CtaSync, true>(a, smem_raw, threadIdx.x, blockIdx.x, CtaSync());
 }
 
 __global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs a)
@@ -1322,9 +1423,14 @@ cudaError_t fcpp_launch_plan(fcpp_handle *h, const fcpp_batch &b, const fcpp_out
     const size_t bytes = plan_gen_args(h, b, o, a);
     if (ncap_out) *ncap_out = a.ncap;
     if (bytes > (size_t)h->max_smem_optin) return cudaErrorInvalidValue;  // obstacle tables / headland beyond shared memory
-    cudaError_t e = cudaFuncSetAttribute(plan_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const bool omega = b.turn_model == FCPP_TURN_OMEGA;  // its own instance: the default patterns do not carry its code
+    cudaError_t e = cudaFuncSetAttribute(omega ? plan_gen_omega_kernel : plan_gen_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    plan_gen_kernel<<<(unsigned)b.n_cand, TG, bytes, st>>>(a);
+    if (omega)
+        plan_gen_omega_kernel<<<(unsigned)b.n_cand, TG, bytes, st>>>(a);
+    else
+        plan_gen_kernel<<<(unsigned)b.n_cand, TG, bytes, st>>>(a);
     h->launches++;
     return cudaGetLastError();
 }

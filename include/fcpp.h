@@ -140,6 +140,13 @@ typedef struct {
 
 #define FCPP_TURN_ARC 0
 #define FCPP_TURN_CLOTHOID 1
+#define FCPP_TURN_OMEGA 2 /* BUILD-DEFINED main-work pattern (the reference only returns the label "Ω型跨行",
+                             mlp3:312-320): same rows, swath ends and sample counts as the U pattern, but the rows are
+                             visited in skip order (blocks of 2 s rows, s = ceil(2 R / W); lower and upper half of a
+                             block alternate) and every 20-sample turn really connects the two swath ends — a half
+                             circle of radius gap / 2 when the gap is >= 2 R, else the Ω (bulb) turn of three radius-R
+                             arcs.  Headland turns stay the reference's arcs.  Parity unpinned (oracle restatement
+                             only). */
 
 #define FCPP_FLAG_CORNER_MASK 3
 #define FCPP_FLAG_REVERSE_ORDER 4

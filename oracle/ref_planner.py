@@ -199,6 +199,84 @@ def uturn_tables():
     return np.cos(a20), np.sin(a20), np.cos(a15), np.sin(a15)
 
 
+def omega_skip(R: float, W: float) -> int:
+    """Rows skipped by a connecting turn of the Ω pattern: the smallest s with s W >= 2 R (a plain half circle of
+    radius s W / 2 >= R joins the two rows), at least 1."""
+    return max(1, int(np.ceil(2.0 * R / W - 1e-9)))
+
+
+def omega_order(P: int, s: int) -> List[int]:
+    """Visit order of the P rows in the Ω (skip-row) pattern: blocks of 2 s rows, inside a block the rows of its
+    lower half and of its upper half alternate (0, h, 1, h + 1, ...; h = ceil(m / 2) for a block of m rows), so
+    consecutive rows are h or h - 1 apart; the blocks follow each other."""
+    order, base = [], 0
+    while base < P:
+        m = min(2 * s, P - base)
+        h = (m + 1) // 2
+        order.extend(base + k // 2 + (h if k % 2 else 0) for k in range(m))
+        base += m
+    return order
+
+
+def omega_turn_local(d_abs: float, R: float, n: int = 20):
+    """The connecting turn of the Ω pattern between two rows |d| apart, in its own frame (u = outward along the swath,
+    v = towards the next row; starts at (0, 0) heading +u, ends at (0, |d|) heading -u), n samples equally spaced in
+    arc length, first and last ON the two swath ends.
+      |d| >= 2 R: a half circle of radius |d| / 2.
+      |d| <  2 R: the Ω (bulb) turn — three arcs of radius R: right by alpha, left by pi + 2 alpha, right by alpha,
+                  cos(alpha) = (R + |d| / 2) / (2 R)."""
+    if d_abs >= 2.0 * R:
+        rho = d_abs / 2.0
+        a = np.linspace(0, np.pi, n)
+        return rho * np.sin(a), rho - rho * np.cos(a)
+    xc = np.sqrt(4.0 * R * R - (R + d_abs / 2.0) ** 2)
+    alpha = np.arctan2(xc, R + d_abs / 2.0)
+    total = np.pi + 4.0 * alpha
+    u = np.empty(n)
+    v_ = np.empty(n)
+    c2 = (2.0 * R * np.sin(alpha), -R + 2.0 * R * np.cos(alpha))
+    for i in range(n):
+        phi = total if i == n - 1 else i * (total / (n - 1))
+        if phi <= alpha:
+            u[i], v_[i] = R * np.sin(phi), -R + R * np.cos(phi)
+        elif phi <= np.pi + 3.0 * alpha:
+            h = -alpha + (phi - alpha)
+            u[i], v_[i] = c2[0] + R * np.sin(h), c2[1] - R * np.cos(h)
+        else:
+            h = np.pi + alpha - (phi - (np.pi + 3.0 * alpha))
+            u[i], v_[i] = -R * np.sin(h), d_abs + R + R * np.cos(h)
+    return u, v_
+
+
+def omega_pattern_in_rotated_space(bnds, v: VehicleParams, reverse_order: bool, start_from_right: bool):
+    """Ω-type skip-row main work (BUILD-DEFINED, parity unpinned: the reference only returns the LABEL 'Ω型跨行',
+    mlp3:312-320, and always generates the U pattern).  Same rows, same swath ends (mlp3:736-751), same sample counts
+    (2 + 20 per pass, mlp3:761-830) as the U pattern; the rows are visited in ``omega_order`` and every turn really
+    connects the two swath ends (``omega_turn_local``), bulging outwards beyond the swath end."""
+    min_x, min_y, max_x, max_y = bnds
+    R, W = v.min_turn_radius, v.working_width
+    line_start_x, line_end_x = min_x + R, max_x - R
+    P = int((max_y - min_y) / W) + 1
+    rows = omega_order(P, omega_skip(R, W))
+    if reverse_order:
+        rows = [P - 1 - r for r in rows]
+    segs, speeds = [], []
+    for idx, i in enumerate(rows):
+        y = min_y + i * W
+        go_left = (idx % 2 == 0) if start_from_right else (idx % 2 == 1)
+        line = np.array([[line_end_x, y], [line_start_x, y]]) if go_left else np.array([[line_start_x, y], [line_end_x, y]])
+        segs.append(line)
+        speeds.extend([v.max_work_speed_kmh] * 2)
+        if idx < P - 1:
+            d = (min_y + rows[idx + 1] * W) - y
+            u, vv = omega_turn_local(abs(d), R, UTURN_POINTS)
+            dir_x = -1.0 if go_left else 1.0
+            sg = 1.0 if d >= 0 else -1.0
+            segs.append(np.column_stack([line[-1][0] + dir_x * u, y + sg * vv]))
+            speeds.extend([v.headland_turn_speed_kmh] * UTURN_POINTS)
+    return np.vstack(segs), np.array(speeds, dtype=np.float64), P
+
+
 def u_pattern_in_rotated_space(bnds, v: VehicleParams, reverse_order: bool, start_from_right: bool,
                                turn_model: str = "arc", clothoid_share: float = 0.5):
     """mlp3:720-830 (swath layout + 20-pt half-circle 'turns', Q3/Q4).  With
@@ -282,8 +360,11 @@ def plan_main_work(fs: FieldSetup, heading: Optional[float] = None,
             reverse_order = True
         if sp[0] > (bnds[0] + bnds[2]) / 2:
             start_from_right = True
-    path, speeds, P = u_pattern_in_rotated_space(bnds, v, reverse_order, start_from_right, fs.turn_model,
-                                                 fs.clothoid_share)
+    if fs.turn_model == "omega":
+        path, speeds, P = omega_pattern_in_rotated_space(bnds, v, reverse_order, start_from_right)
+    else:
+        path, speeds, P = u_pattern_in_rotated_space(bnds, v, reverse_order, start_from_right, fs.turn_model,
+                                                     fs.clothoid_share)
     if rotated:
         cp, sp_ = float(np.cos(angle)), float(np.sin(angle))
         x = path[:, 0] - center[0]

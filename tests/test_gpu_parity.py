@@ -767,3 +767,52 @@ def test_pipelined_and_speculatively_sized_batches_identical(fc):
             for f in got.winner_paths:
                 assert np.array_equal(got.winner_paths[f][0], want[k].winner_paths[f][0])
                 assert np.array_equal(got.winner_paths[f][1], want[k].winner_paths[f][1])
+
+
+def test_omega_skip_row_pattern_vs_oracle(fc):
+    """Ω-type skip-row main work (opt-in, the reference has only the label, mlp3:312-320; build-defined, parity
+    unpinned): device vs oracle/ref_planner.omega_* — layout counts exact, points <= 1e-9 m, speeds, lengths, times,
+    violation counts; rectangles (axis-aligned chains), a sheared field, a heading axis, radii with bulb turns
+    (gap < 2R) and plain half circles; summary-only == paths mode; the default pattern is untouched."""
+    from oracle import batch as ob, ref_planner as rp
+    para = [(100, 50), (600, 120), (640, 330), (140, 260)]
+    small = [(0, 0), (100, 0), (100, 80), (0, 80)]
+    fields = [RECT, para, small]
+    veh = fc.VehicleParams()
+    cand = fc.make_candidates(3, radii=[5.0, 8.0, 11.0], start_corners=[0, 1, 2, 3])
+    res = fc.plan_batch(fields, veh, cand, outputs="paths", turn_model="omega")
+    u = fc.plan_batch(fields, veh, cand, coverage=False)
+    assert (res.summary["n_main"] == u.summary["n_main"]).all() and (res.summary["n_head"] == u.summary["n_head"]).all()
+    assert (res.summary["len_main"] != u.summary["len_main"]).all()            # another main path ...
+    assert res.summary["len_head"].tobytes() == u.summary["len_head"].tobytes()  # ... the same headland
+    for b in range(0, len(res.summary), 1):
+        o = ob.evaluate_candidate(fields[int(cand["field_id"][b])], rp.VehicleParams(), R=cand["R"][b],
+                                  start_corner=int(cand["start_corner"][b]), keep_paths=True, turn_model="omega",
+                                  coverage=(b % 5 == 0))
+        _summary_vs_oracle(res.summary[b], o, coverage=(b % 5 == 0))
+        p, s, n_main = res.path(b)
+        assert np.abs(p - o["path"]).max() <= TIGHT
+        assert np.abs(s - o["speeds"]).max() <= 1e-7
+        # every turn connects the two swath ends it lies between (first / last sample ON them)
+        m = p[:n_main].reshape(-1)[: (n_main // 22) * 44].reshape(-1, 22, 2)
+        assert np.abs(m[:, 2] - m[:, 1]).max() <= 1e-9
+        nxt = p[22:n_main:22]
+        assert np.abs(m[:len(nxt), 21] - nxt).max() <= 1e-9
+    summ = fc.plan_batch(fields, veh, cand, outputs="summary", turn_model="omega")
+    assert summ.summary.tobytes() == res.summary.tobytes()
+    # a heading axis (rotated swaths) in factored form
+    ax = fc.candidate_axes(2, headings=np.deg2rad([0.0, 17.0, 90.0, 133.0]), radii=[7.0])
+    hr = fc.plan_batch([para, RECT], veh, ax, outputs="paths", turn_model="omega")
+    ex = fc.expand_axes(ax)
+    for b in range(len(hr.summary)):
+        o = ob.evaluate_candidate([para, RECT][int(ex["field_id"][b])], rp.VehicleParams(), R=7.0,
+                                  heading=float(ex["heading"][b]), keep_paths=True, turn_model="omega", coverage=False)
+        _summary_vs_oracle(hr.summary[b], o, coverage=False)
+        assert np.abs(hr.path(b)[0] - o["path"]).max() <= TIGHT
+    # drop-in class
+    pl = fc.TwoLayerPathPlannerV37(fc.VehicleParams(), field_length=500, field_width=200, turn_model="omega")
+    r = pl.plan()
+    assert len(r["main_work"]["path"]) == 1256 and len(r["headland"]["path"]) == 435
+    # the turns respect the turning radius (the reference's U 'turns' are half circles of radius R that do not connect)
+    k = rp.curvatures(r["main_work"]["path"])
+    assert k.max() <= 1.0 / 8.0 * 1.01

@@ -287,3 +287,33 @@ def test_geos_faithful_buffer_vs_exact_round_buffer_quantified():
     for name, cells, worst, rel, band_diff in rows:
         print(f"N3 {name:12s} window {cells} lattice points: <= {worst} differ (GEOS fan vs exact round buffer); "
               f"coverage_rate bound {rel:.2e}; band lattice points that differ: {band_diff}")
+
+
+def test_omega_pattern_oracle_properties():
+    """The build-defined Ω (skip-row) pattern of the oracle (the reference has only the label, mlp3:312-320): every row
+    exactly once, consecutive rows at most s apart, the U pattern's sample counts and swath ends, turns that start and
+    end ON the swath ends with curvature <= 1/R (up to the sampling), equal arc-length spacing."""
+    for P in range(1, 40):
+        for s_ in (1, 2, 5, 7):
+            order = rp.omega_order(P, s_)
+            assert sorted(order) == list(range(P))
+            assert all(abs(a - b) <= s_ for a, b in zip(order, order[1:]))
+    assert rp.omega_skip(8.0, 3.2) == 5 and rp.omega_skip(1.0, 3.2) == 1 and rp.omega_skip(4.8, 3.2) == 3
+    for d, R in ((3.2, 8.0), (12.8, 8.0), (16.0, 8.0), (22.4, 8.0), (0.5, 5.0)):
+        u, v = rp.omega_turn_local(d, R)
+        pts = np.stack([u, v], axis=1)
+        assert np.abs(pts[0]).max() == 0.0 and np.abs(pts[-1] - (0.0, d)).max() < 1e-12
+        seg = np.linalg.norm(np.diff(pts, axis=0), axis=1)
+        assert seg.max() / seg.min() < 1.01
+        assert rp.curvatures(pts).max() <= 1.0 / max(R, d / 2) * 1.02
+    veh = rp.VehicleParams()
+    fo = rp.setup_field(veh, field_length=500, field_width=200, turn_model="omega")
+    fu = rp.setup_field(veh, field_length=500, field_width=200)
+    po, pu = rp.plan_complete_coverage(fo), rp.plan_complete_coverage(fu)
+    mo, mu = po["main_work"]["path"], pu["main_work"]["path"]
+    assert mo.shape == mu.shape == (1256, 2)
+    assert np.array_equal(po["headland"]["path"], pu["headland"]["path"])
+    ends_o = {tuple(np.round(p, 9)) for k in range(0, 1256, 22) for p in mo[k:k + 2]}
+    ends_u = {tuple(np.round(p, 9)) for k in range(0, 1256, 22) for p in mu[k:k + 2]}
+    assert ends_o == ends_u                                   # the same swaths, another order
+    assert rp.curvatures(mo).max() <= 1.0 / 8.0 * 1.01
