@@ -265,6 +265,12 @@ __device__ __forceinline__ double vlimit(double v0, double kappa, const fcpp_veh
 #define FCPP_PLAN_GEN_THREADS 128
 #endif
 constexpr int TG = FCPP_PLAN_GEN_THREADS;
+#ifndef FCPP_PLAN_GEN_MIN_CTAS
+// CTAs of 128 threads per SM the register allocation aims at.  Measured (tools/fused_ab.py, plan kernel of config
+// 2 / 5 / 3): 8 CTAs (64 registers, 308 B of spills) 0.207 / 0.624 / 4.50 ms, 7 (72 registers) 0.193 / 0.602 / 4.20,
+// 6 (80) 0.203 / 0.598 / 4.25, 5 (96) 0.220 / 0.641 / 4.36, 4 (120, no spills) 0.240 / 0.680 / 4.80.
+#define FCPP_PLAN_GEN_MIN_CTAS 7
+#endif
 static_assert(TG >= 128 && TG % 32 == 0, "the table set-up uses threads 0 .. 96 + 4 * FCPP_MAX_LOOPS - 1 in two rounds");
 
 // shared memory of the generated-plan kernel: fixed part (compile-time offsets) + obstacle tables + the staging of
@@ -1075,13 +1081,13 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
     }
 }
 
-__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_omega_kernel(const PlanArgs a)
+__global__ void __launch_bounds__(TG, FCPP_PLAN_GEN_MIN_CTAS) plan_gen_omega_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     plan_gen_body<CtaSync, true>(a, smem_raw, threadIdx.x, blockIdx.x, CtaSync());
 }
 
-__global__ void __launch_bounds__(TG, 1024 / TG) plan_gen_kernel(const PlanArgs a)
+__global__ void __launch_bounds__(TG, FCPP_PLAN_GEN_MIN_CTAS) plan_gen_kernel(const PlanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     plan_gen_body(a, smem_raw, threadIdx.x, blockIdx.x, CtaSync());
