@@ -1323,6 +1323,14 @@ struct CoverLaunch {
     int32_t *work = nullptr, *counters = nullptr;  // de-duplicated batches: the listed candidates (cover_work_kernel)
 };
 
+// few representatives expected (a heading search): persistent grid over the listed candidates.  (Measured: config 3
+// coverage 4.0 -> 2.8 ms per 737 280 candidates; batches where most candidates rasterise a part — configs 2 and 5 —
+// run 1.5-2.5 % slower that way, hence the hint.  Cover mode bits 6 / 7 force either.)
+static bool cover_use_work_list(const fcpp_handle *h, const fcpp_batch &b)
+{
+    return (b.cover_dedupe >= 2 || (h->cover_mode & 128)) && !(h->cover_mode & 64);
+}
+
 // sizes + (when the batch asks for it) the de-duplication kernels that precede the coverage kernel
 static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream_t st, CoverLaunch &L)
 {
@@ -1354,8 +1362,6 @@ static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream
         L.d_rep = (int32_t *)(L.hash + 2 * n);
         L.work = L.d_rep + 2 * n;
         L.counters = L.work + n;
-        e = cudaMemsetAsync(L.counters, 0, 2 * sizeof(int32_t), st);
-        if (e != cudaSuccess) return e;
         if (h->dedupe_cap != cap) {
             e = cudaMemsetAsync(h->d_dedupe, 0, (size_t)cap * 12, st);
             if (e != cudaSuccess) return e;
@@ -1364,8 +1370,15 @@ static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream
         const unsigned g = (unsigned)((n + 127) / 128);
         cover_key_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash);
         cover_rep_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash, L.d_rep);
-        cover_list_kernel<<<g, 128, 0, st>>>(n, L.d_rep, L.work, L.counters);
-        h->launches += 3;
+        h->launches += 2;
+        if (cover_use_work_list(h, b)) {
+            e = cudaMemsetAsync(L.counters, 0, 2 * sizeof(int32_t), st);
+            if (e != cudaSuccess) return e;
+            cover_list_kernel<<<g, 128, 0, st>>>(n, L.d_rep, L.work, L.counters);
+            h->launches++;
+        } else {
+            L.work = nullptr;
+        }
         e = cudaGetLastError();
     }
     return e;
@@ -1388,10 +1401,7 @@ cudaError_t fcpp_launch_cover(fcpp_handle *h, const fcpp_batch &b, const fcpp_ou
     CoverLaunch L;
     cudaError_t e = cover_prepare(h, b, st, L);
     if (e != cudaSuccess) return e;
-    if (L.work && (b.cover_dedupe >= 2 || (h->cover_mode & 128)) && !(h->cover_mode & 64)) {
-        // few representatives expected (a heading search): persistent grid over the listed candidates.  (Measured:
-        // config 3 coverage 4.0 -> ~3 ms per 737 280 candidates; batches where most candidates rasterise a part —
-        // configs 2 and 5 — run 1.5-2.5 % slower this way, hence the hint.  Cover mode bit 6 / 7 force either.)
+    if (L.work) {
         e = cudaFuncSetAttribute(cover_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes);
         if (e != cudaSuccess) return e;
         int64_t grid = (int64_t)FCPP_COVER_MINBLOCKS * h->sm_count;
