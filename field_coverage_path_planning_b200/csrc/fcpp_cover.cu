@@ -104,7 +104,11 @@ constexpr size_t OFF_ACT = OFF_APRE + sizeof(int) * (EBATCH + 16);   // uint16 [
 constexpr size_t OFF_ITEM = OFF_ACT + sizeof(uint16_t) * EBATCH;     // uint16 [ICAP]: active index holding an item's first pair
 constexpr size_t OFF_ENT = a16(OFF_ITEM + sizeof(uint16_t) * ICAP);  // Entry [pc]
 struct CoverDyn {
-    __device__ __forceinline__ Entry &ent(int e) const { return reinterpret_cast<Entry *>(cover_smem + OFF_ENT)[e]; }
+    __device__ __forceinline__ Entry &ent(int e) const
+    {
+        FCPP_ASSERT(e >= 0 && OFF_ENT + (size_t)(e + 1) * sizeof(Entry) <= fcpp_dynamic_smem_bytes());
+        return reinterpret_cast<Entry *>(cover_smem + OFF_ENT)[e];
+    }
     __device__ __forceinline__ int *apre() const { return reinterpret_cast<int *>(cover_smem + OFF_APRE); }
     __device__ __forceinline__ uint16_t *act() const { return reinterpret_cast<uint16_t *>(cover_smem + OFF_ACT); }
     __device__ __forceinline__ uint16_t *item_first() const { return reinterpret_cast<uint16_t *>(cover_smem + OFF_ITEM); }
@@ -216,6 +220,12 @@ __device__ __forceinline__ void quad_row_interval(const int2 *q, const double (*
 __device__ __forceinline__ void or_span(uint32_t *base, int ia, int ib)
 {
     const int w0 = ia >> 5, w1 = ib >> 5;
+#ifdef FCPP_BOUNDS_DEBUG
+    {
+        const uint32_t *tile = reinterpret_cast<const CoverFixed *>(cover_smem)->tile;
+        FCPP_ASSERT(ia >= 0 && ib >= ia && base + w0 >= tile && base + w1 < tile + TW);
+    }
+#endif
     const uint32_t m0 = 0xffffffffu << (ia & 31), m1 = 0xffffffffu >> (31 - (ib & 31));
     if (w0 == w1) {
         atomicOr(base + w0, m0 & m1);
@@ -426,12 +436,17 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
             if (rows[q]) {
                 const int ai = (int)((unsigned)inc[q] >> 21) - 1;
                 const int first = (int)((unsigned)inc[q] & 0x1fffffu) - rows[q];
+                FCPP_ASSERT(ai >= 0 && ai < EBATCH && first >= 0);
                 d.act()[ai] = (uint16_t)(q * T + tid);
                 d.apre()[ai] = first;
                 if (table)
-                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) d.item_first()[i] = (uint16_t)ai;
+                    for (int i = (first + 31) >> 5; i <= (first + rows[q] - 1) >> 5; ++i) {
+                        FCPP_ASSERT(i >= 0 && i < ICAP);
+                        d.item_first()[i] = (uint16_t)ai;
+                    }
             }
         }
+        FCPP_ASSERT(n_act >= 0 && n_act <= EBATCH);
         if (tid == 0) d.apre()[n_act] = n_pairs;
         __syncthreads();
         // items go to the warps round-robin (handing them out through a shared counter was measured
@@ -508,6 +523,8 @@ __device__ void raster_entries(CoverFixed &s, const CoverDyn &d, int e0, int n_e
 // of 4 are read too: callers keep them zero)
 __device__ __forceinline__ int count_words(const uint32_t *w, int n)
 {
+    FCPP_ASSERT(n >= 0 && w >= reinterpret_cast<const CoverFixed *>(cover_smem)->tile &&
+                w + ((n + 3) & ~3) <= reinterpret_cast<const CoverFixed *>(cover_smem)->tile + TW);
     int c = 0;
     const uint4 *v = reinterpret_cast<const uint4 *>(w);
     for (int i = threadIdx.x; i < (n + 3) >> 2; i += T) {
@@ -518,6 +535,8 @@ __device__ __forceinline__ int count_words(const uint32_t *w, int n)
 }
 __device__ __forceinline__ void zero_words(uint32_t *w, int n)  // rounds n up to a multiple of 4
 {
+    FCPP_ASSERT(n >= 0 && w >= reinterpret_cast<const CoverFixed *>(cover_smem)->tile &&
+                w + ((n + 3) & ~3) <= reinterpret_cast<const CoverFixed *>(cover_smem)->tile + TW);
     uint4 *v = reinterpret_cast<uint4 *>(w);
     for (int i = threadIdx.x; i < (n + 3) >> 2; i += T) v[i] = make_uint4(0u, 0u, 0u, 0u);
 }

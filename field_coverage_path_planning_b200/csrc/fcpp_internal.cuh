@@ -156,6 +156,22 @@ __device__ __forceinline__ bool cover_same(const CandRec &a, const CandRec &b, i
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
+// Bounds-checked debug build (make VARIANT=bounds DEFS=-DFCPP_BOUNDS_DEBUG): device asserts at the shared-memory
+// indexers of the hot kernels.  compute-sanitizer is closed on the GPU pool, so the parity tests are run once per
+// round through this build instead (a failed assert traps the kernel and surfaces as a CUDA error in the test).
+#ifdef FCPP_BOUNDS_DEBUG
+#include <assert.h>
+#define FCPP_ASSERT(c) assert(c)
+__device__ __forceinline__ uint32_t fcpp_dynamic_smem_bytes()
+{
+    uint32_t n;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(n));
+    return n;
+}
+#else
+#define FCPP_ASSERT(c) ((void)0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -462,6 +462,8 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         for (int k = tid; k <= n_obs_poly; k += T) s.obs_vs[k] = a.b.obs_vert_start[p0 + k] - base;
     }
     const int N = r.n_total, n_main = r.n_main;
+    FCPP_ASSERT(gen_smem_bytes(a.ncap, a.obs_cap_verts, a.obs_cap_polys) <= fcpp_dynamic_smem_bytes() + 0u ||
+                blockDim.x != TG /* fused kernel: four plans share one allocation, checked by the host */);
     const int n_skip = main_skip(n_main);  // regular chain points: i in [2, 2 + n_skip)
     const int NS = N - n_skip;             // staged points
     const int64_t off = a.out.offsets ? a.out.offsets[cand] : 0;
@@ -678,6 +680,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
             }
             const int pos = idx < 65536 ? atomicAdd(&f.n_mixed, 1) : MIXED_CAP;
             if (pos < MIXED_CAP) {
+                FCPP_ASSERT(pos >= 0 && idx >= 0 && idx < r.P);
                 f.mixed[pos] = (uint16_t)idx;
             } else {  // (a plan with more than MIXED_CAP unclassifiable passes, or more than 65 535 passes)
                 for (int j = lo; j < hi; ++j) {
@@ -765,6 +768,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         uint8_t c;
         int tag, gord;
         gen_point_tag<OMEGA>(r, f.tt, tm, W, i, x, y, c, tag, gord);
+        FCPP_ASSERT(q >= 0 && q < a.ncap && i >= 0 && i < N && gord < N_GENERIC && (gord >= 0 || (tag >= 0 && tag < N_SLOTS)));
         if (gp) gp[i] = make_double2(x, y);
         s.TAG[q] = (uint8_t)tag;
         if (gord >= 0) {
@@ -912,6 +916,7 @@ __device__ __forceinline__ void plan_gen_body(const PlanArgs &a, unsigned char *
         const double vl = vlimit(v0, kap, veh);
         const double vms = div36(vl);
         const int q = i < 2 ? i : i - n_skip;
+        FCPP_ASSERT(q >= 0 && q < NS && NS <= a.ncap && g < N_GENERIC);
         s.X[q] = ds2;
         s.Y[q] = kap;
         s.U[q] = vms * vms;
