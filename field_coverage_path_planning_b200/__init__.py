@@ -15,7 +15,9 @@ from .multi_field import (Connection, FieldData, MultiFieldPlannerV38, Optimized
 
 from .multi_vehicle import MultiVehiclePlanner, MultiVehicleRoute, VehicleRoute, kmeans_labels  # noqa: F401
 
-__all__ = ["MultiVehiclePlanner", "MultiVehicleRoute", "VehicleRoute", "kmeans_labels", "VehicleParams", "TwoLayerPathPlannerV37", "TwoLayerPathPlannerV35", "TwoLayerPathPlannerV36",
+from .tsp import TSPSolver, two_opt_batch  # noqa: F401
+
+__all__ = ["TSPSolver", "two_opt_batch", "MultiVehiclePlanner", "MultiVehicleRoute", "VehicleRoute", "kmeans_labels", "VehicleParams", "TwoLayerPathPlannerV37", "TwoLayerPathPlannerV35", "TwoLayerPathPlannerV36",
            "TwoLayerPlannerV35", "TwoLayerPlannerV36", "TwoLayerPlannerV37", "plan_batch", "prepare_batch",
            "make_candidates", "candidate_axes", "expand_axes", "BatchResult", "tour_lengths", "GeneticAlgorithmSolver", "GAConfig", "FcppError",
            "MultiFieldPlannerV38", "FieldData", "Connection", "OptimizedRoute", "distance_matrix",

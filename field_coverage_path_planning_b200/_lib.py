@@ -133,7 +133,7 @@ assert SUMMARY_DTYPE.itemsize == 176, SUMMARY_DTYPE.itemsize
 EXPORTS = [
     "fcpp_abi_version", "fcpp_create", "fcpp_destroy", "fcpp_last_error", "fcpp_set_trig_tables",
     "fcpp_layout", "fcpp_plan_batch", "fcpp_field_argmin", "fcpp_field_argmin_merge", "fcpp_field_argmin_exchange", "fcpp_winner_records", "fcpp_status_count", "fcpp_speed_verify", "fcpp_raster_window",
-    "fcpp_tour_lengths", "fcpp_distance_matrix", "fcpp_connection_matrix", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve", "fcpp_kmeans_lloyd",
+    "fcpp_tour_lengths", "fcpp_distance_matrix", "fcpp_connection_matrix", "fcpp_ga_init_population", "fcpp_ga_next_size", "fcpp_ga_generation", "fcpp_ga_solve", "fcpp_kmeans_lloyd", "fcpp_tsp_two_opt",
     "fcpp_launch_count", "fcpp_last_fused", "fcpp_last_max_points", "fcpp_last_max_head_points", "fcpp_last_total_points", "fcpp_set_profiling", "fcpp_kernel_times", "fcpp_set_cover_mode",
 ]
 
@@ -199,6 +199,8 @@ def load():
         L.fcpp_ga_solve.argtypes = [vp, C.POINTER(GAConfigC), vp, i32, vp, vp, vp, C.POINTER(GAResultC), vp]
         L.fcpp_kmeans_lloyd.restype = C.c_int
         L.fcpp_kmeans_lloyd.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32, dbl, vp, vp, vp]
+        L.fcpp_tsp_two_opt.restype = C.c_int
+        L.fcpp_tsp_two_opt.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp]
         L.fcpp_last_fused.restype = i32
         L.fcpp_last_fused.argtypes = [vp]
         L.fcpp_last_max_points.restype = i32

@@ -250,6 +250,135 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_lloyd_kernel(const KMeansAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-opt tour improvement — the `TSPSolver.solve(distance_matrix)` that multi_field_planner.py:176 and
+// multi_vehicle_planner.py:131 import from `multi_field_planner_v37`, a module the reference does not ship.
+// BUILD-DEFINED (no reference source; restated in oracle/tsp.py): nearest-neighbour tour from node 0 (first minimum),
+// then best-improvement 2-opt on the closed tour — every pair of tour edges (i, i+1), (j, j+1) is evaluated in
+// parallel, delta = (D[a][c] + D[b][d]) - (D[a][b] + D[c][d]); the move with the lowest delta below -1e-9 is applied
+// (ties: the lowest (i, j)) by reversing tour[i+1 .. j]; node 0 stays first.  D must be symmetric.
+// One CTA per problem, tour in shared memory, deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int TSP_THREADS = 256;
+constexpr double TSP_EPS = 1e-9;
+
+struct TspArgs {
+    const int64_t *mat_start;  // [P+1] offset of every problem's n x n matrix in D (doubles)
+    const double *D;
+    const int64_t *node_start; // [P+1] first node of every problem in tours
+    int32_t *tours;            // [sum n]
+    double *lengths;           // [P]
+    int32_t *iters;            // [P]
+    int max_iter;
+};
+
+// block-wide argmin of (value, index), ties to the lowest index; every thread gets the result
+__device__ __forceinline__ void block_argmin(double &v, long long &idx, double *sv, long long *si)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov < v || (ov == v && oi < idx)) {
+            v = ov;
+            idx = oi;
+        }
+    }
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        sv[w] = v;
+        si[w] = idx;
+    }
+    __syncthreads();
+    v = sv[0];
+    idx = si[0];
+#pragma unroll
+    for (int k = 1; k < TSP_THREADS / 32; ++k)
+        if (sv[k] < v || (sv[k] == v && si[k] < idx)) {
+            v = sv[k];
+            idx = si[k];
+        }
+}
+
+__global__ void __launch_bounds__(TSP_THREADS) two_opt_kernel(const TspArgs a)
+{
+    extern __shared__ int tsp_smem[];
+    __shared__ double sv[TSP_THREADS / 32];
+    __shared__ long long si[TSP_THREADS / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int n = (int)(a.node_start[p + 1] - a.node_start[p]);
+    const double *D = a.D + a.mat_start[p];
+    int32_t *out = a.tours + a.node_start[p];
+    int *tour = tsp_smem;       // [n]
+    int *used = tsp_smem + n;   // [n]
+    if (n <= 0) {
+        if (tid == 0) {
+            a.lengths[p] = 0.0;
+            a.iters[p] = 0;
+        }
+        return;
+    }
+    // nearest-neighbour tour from node 0
+    for (int k = tid; k < n; k += TSP_THREADS) used[k] = (k == 0);
+    if (tid == 0) tour[0] = 0;
+    __syncthreads();
+    for (int step = 1; step < n; ++step) {
+        const int cur = tour[step - 1];
+        double bv = INFINITY;
+        long long bi = 0x7fffffffffffffffll;
+        for (int k = tid; k < n; k += TSP_THREADS)
+            if (!used[k]) {
+                const double d = D[(int64_t)cur * n + k];
+                if (d < bv || (d == bv && k < bi)) {
+                    bv = d;
+                    bi = k;
+                }
+            }
+        block_argmin(bv, bi, sv, si);
+        if (tid == 0) {
+            tour[step] = (int)bi;
+            used[bi] = 1;
+        }
+        __syncthreads();
+    }
+    // best-improvement 2-opt
+    int it = 0;
+    const long long n_pairs = (long long)n * n;  // (i, j) as i * n + j, only 0 <= i < j <= n - 1 with j - i >= 2 count
+    for (; it < a.max_iter; ++it) {
+        double bv = INFINITY;
+        long long bi = 0x7fffffffffffffffll;
+        for (long long q = tid; q < n_pairs; q += TSP_THREADS) {
+            const int i = (int)(q / n), j = (int)(q - (long long)i * n);
+            if (j < i + 2 || (i == 0 && j == n - 1)) continue;  // adjacent edges (and the same pair seen cyclically)
+            const int ta = tour[i], tb = tour[i + 1], tc = tour[j], td = tour[j + 1 == n ? 0 : j + 1];
+            const double delta = (D[(int64_t)ta * n + tc] + D[(int64_t)tb * n + td]) -
+                                 (D[(int64_t)ta * n + tb] + D[(int64_t)tc * n + td]);
+            if (delta < bv || (delta == bv && q < bi)) {
+                bv = delta;
+                bi = q;
+            }
+        }
+        block_argmin(bv, bi, sv, si);
+        if (!(bv < -TSP_EPS)) break;
+        const int i = (int)(bi / n), j = (int)(bi - (long long)i * n);
+        __syncthreads();
+        for (int k = tid; k < (j - i) / 2; k += TSP_THREADS) {  // reverse tour[i+1 .. j]
+            const int x = tour[i + 1 + k];
+            tour[i + 1 + k] = tour[j - k];
+            tour[j - k] = x;
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < n; k += TSP_THREADS) out[k] = tour[k];
+    if (tid == 0) {
+        double len = 0.0;  // closed tour, left to right (ga:174-181)
+        for (int k = 0; k < n; ++k) len += D[(int64_t)tour[k] * n + tour[k + 1 == n ? 0 : k + 1]];
+        a.lengths[p] = len;
+        a.iters[p] = it;
+    }
+}
+
 }  // namespace
 
 extern "C" int fcpp_kmeans_lloyd(fcpp_handle *h, int32_t n_problems, const int64_t *d_pt_start, const double *d_xy,
@@ -275,5 +404,29 @@ extern "C" int fcpp_kmeans_lloyd(fcpp_handle *h, int32_t n_problems, const int64
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fcpp_cuda_fail(h, e, "fcpp_kmeans_lloyd");
+    return FCPP_OK;
+}
+
+extern "C" int fcpp_tsp_two_opt(fcpp_handle *h, int32_t n_problems, const int64_t *d_mat_start, const double *d_D,
+                                const int64_t *d_node_start, int32_t max_nodes, int32_t *d_tours, double *d_lengths,
+                                int32_t *d_iters, int32_t max_iter, void *stream)
+{
+    if (!h) return FCPP_ERR_INVALID;
+    if (n_problems < 0 || max_nodes < 0 || max_iter < 0) return fcpp_fail(h, FCPP_ERR_INVALID, "fcpp_tsp_two_opt: bad argument");
+    if (n_problems == 0) return FCPP_OK;
+    if (!d_mat_start || !d_D || !d_node_start || !d_tours || !d_lengths || !d_iters)
+        return fcpp_fail(h, FCPP_ERR_INVALID, "fcpp_tsp_two_opt: NULL pointer");
+    if (max_nodes > 16384) return fcpp_fail(h, FCPP_ERR_INVALID, "fcpp_tsp_two_opt: more than 16384 nodes per problem");
+    cudaSetDevice(h->device);
+    TspArgs a{d_mat_start, d_D, d_node_start, d_tours, d_lengths, d_iters, max_iter};
+    const size_t bytes = sizeof(int) * 2 * (size_t)(max_nodes > 0 ? max_nodes : 1);
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(two_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fcpp_cuda_fail(h, e, "fcpp_tsp_two_opt");
+    }
+    two_opt_kernel<<<(unsigned)n_problems, TSP_THREADS, bytes, (cudaStream_t)stream>>>(a);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fcpp_cuda_fail(h, e, "fcpp_tsp_two_opt");
     return FCPP_OK;
 }

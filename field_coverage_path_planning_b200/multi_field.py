@@ -13,10 +13,11 @@ records of mfp:29-61, :63-233, with the numeric steps on the GPU:
                length of every field from ``plan_batch`` (four start corners per field, per-field
                argmin) with ``work_distance="planned"``
 
-Not built: ``optimization_method="2opt"`` imports a module the reference
-does not ship (``multi_field_planner_v37``, mfp:176) and fails there with ModuleNotFoundError — the
-same error is raised here; ``optimize_multi_vehicle`` (KMeans split, multi_vehicle_planner.py) and the
-matplotlib visualisations are out of scope.
+``optimization_method="2opt"`` (the reference's choice for fewer than 50 fields, mfp:153-162) imports ``TSPSolver`` from
+``multi_field_planner_v37`` (mfp:176), a module the reference does not ship — there it fails with ModuleNotFoundError.
+Here the same import is attempted first (a caller's own module wins) and otherwise the build-defined device 2-opt of
+``tsp.py`` is used (no reference source, parity unpinned).  ``optimize_multi_vehicle`` hands over to
+``multi_vehicle.py`` (KMeans split).  The matplotlib visualisations are out of scope.
 """
 from __future__ import annotations
 
@@ -213,13 +214,15 @@ class MultiFieldPlannerV38:
             raise ValueError("多机协同请使用 optimize_multi_vehicle() 方法")
         distance_matrix_, node_ids = self._calculate_distance_matrix()
         if self.optimization_method == "2opt":
-            # the reference imports a module it does not ship (mfp:176); same failure here
-            raise ModuleNotFoundError("No module named 'multi_field_planner_v37'")
-        config = GAConfig(population_size=min(200, len(self.fields) * 4), max_generations=500,
-                          convergence_threshold=50)
-        solver = GeneticAlgorithmSolver(config, seed=self._seed, device=self._device)
-        optimal_route_indices, stats = solver.solve(distance_matrix_, verbose=self.verbose)
-        stats['method'] = 'genetic'
+            from .tsp import tsp_solver_class
+            optimal_route_indices = tsp_solver_class().solve(distance_matrix_)      # mfp:176-177
+            stats = {'method': '2opt'}
+        else:
+            config = GAConfig(population_size=min(200, len(self.fields) * 4), max_generations=500,
+                              convergence_threshold=50)
+            solver = GeneticAlgorithmSolver(config, seed=self._seed, device=self._device)
+            optimal_route_indices, stats = solver.solve(distance_matrix_, verbose=self.verbose)
+            stats['method'] = 'genetic'
         optimal_route_ids = [node_ids[i] for i in optimal_route_indices]
         field_sequence = [i for i in optimal_route_ids if i != "depot"]
         connections = [self._find_best_connection("depot", field_sequence[0])]

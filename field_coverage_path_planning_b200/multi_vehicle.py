@@ -12,8 +12,8 @@
 * workload balance (mvp:211-227): the reference computes the cluster areas and returns the clusters unchanged.
 * per-vehicle order (mvp:96-133): centroid distance matrix (``fcpp_distance_matrix``) + the device GA
   (``fcpp_ga_solve``) when ``use_genetic and len(cluster) > 20``; otherwise the reference imports ``TSPSolver`` from
-  ``multi_field_planner_v37``, a module that is not part of the reference tree — the same import is attempted
-  here, so the same ``ModuleNotFoundError`` surfaces unless the caller provides that module.
+  ``multi_field_planner_v37``, a module that is not part of the reference tree (ModuleNotFoundError there) — the same
+  import is attempted here and, when it fails, the build-defined device 2-opt of ``tsp.py`` is used.
 * statistics (mvp:139-183): transfer / work distance, work time at 5 and 15 km/h, load balance ratio.
 """
 from __future__ import annotations
@@ -170,8 +170,8 @@ class MultiVehiclePlanner:
                 seed = None if self._seed is None else self._seed + vehicle_id
                 optimal_route, _ = GeneticAlgorithmSolver(config, seed=seed, device=self._device).solve(D, verbose=False)
             else:
-                from multi_field_planner_v37 import TSPSolver   # not in the reference tree either (mvp:131)
-                optimal_route = TSPSolver.solve(D)
+                from .tsp import tsp_solver_class               # mvp:131 (a module the reference does not ship)
+                optimal_route = tsp_solver_class().solve(D)
             node_ids = ["depot"] + ids
             field_sequence = [node_ids[i] for i in optimal_route if node_ids[i] != "depot"]
             transfer = self._calculate_route_distance(optimal_route, D)

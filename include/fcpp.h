@@ -324,6 +324,18 @@ int fcpp_kmeans_lloyd(fcpp_handle *h, int32_t n_problems, const int64_t *d_pt_st
                       const int64_t *d_center_start, int32_t max_clusters, double *d_centers, int32_t *d_labels,
                       int32_t max_iter, double tol, int32_t *d_n_iter, double *d_inertia, void *stream);
 
+/* `TSPSolver.solve(distance_matrix)` — imported by multi_field_planner.py:176 and multi_vehicle_planner.py:131 from
+ * `multi_field_planner_v37`, a module the reference does not ship.  BUILD-DEFINED (no reference source): nearest-
+ * neighbour tour from node 0, then best-improvement 2-opt on the closed tour (delta = (D[a][c] + D[b][d]) -
+ * (D[a][b] + D[c][d]) for the tour edges (a, b), (c, d); the lowest delta < -1e-9 is applied, ties to the lowest
+ * edge pair; node 0 stays first) until no move improves or max_iter moves were made.  Batched: problem p owns the
+ * n_p x n_p symmetric FP64 matrix at d_D + d_mat_start[p] (n_p = d_node_start[p+1] - d_node_start[p] <= max_nodes
+ * <= 16384) and writes its tour to d_tours + d_node_start[p], the closed-tour length (left-to-right FP64 sum, as
+ * fcpp_tour_lengths) to d_lengths[p] and the number of moves to d_iters[p].  One CTA per problem, deterministic. */
+int fcpp_tsp_two_opt(fcpp_handle *h, int32_t n_problems, const int64_t *d_mat_start, const double *d_D,
+                     const int64_t *d_node_start, int32_t max_nodes, int32_t *d_tours, double *d_lengths,
+                     int32_t *d_iters, int32_t max_iter, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * GA evolution on the device ("ga" = genetic_algorithm_solver.py)
  * ------------------------------------------------------------------------------------------- */

@@ -143,9 +143,16 @@ def test_multi_field_planner_v38_drop_in(fc):
     rnd = np.mean([sum(z["D"][a, b] for a, b in zip(r, np.roll(r, -1)))
                    for r in (np.random.default_rng(s).permutation(13) for s in range(200))])
     assert tour < 0.75 * rnd
-    # reference error behaviour
-    with pytest.raises(ModuleNotFoundError):       # mfp:176 imports a module the reference does not ship
-        fc.MultiFieldPlannerV38(defs, (0, 0), fc.VehicleParams(), optimization_method="auto").optimize_sequence()
+    # "auto" picks 2-opt below 50 fields (mfp:153-162); the reference then imports a module it does not ship (mfp:176,
+    # ModuleNotFoundError there) — here the device 2-opt of tsp.py answers (build-defined, == oracle/tsp.py)
+    from oracle import tsp as otsp
+    p2 = fc.MultiFieldPlannerV38(defs, (0, 0), fc.VehicleParams(), optimization_method="auto")
+    assert p2.optimization_method == "2opt"
+    r2 = p2.optimize_sequence()
+    D2, ids2 = p2._calculate_distance_matrix()
+    want, want_len, _ = otsp.two_opt(D2)
+    assert r2.field_sequence == [ids2[i] for i in want if ids2[i] != "depot"]
+    assert r2.optimization_stats == {'method': '2opt'} and sorted(r2.field_sequence) == sorted(ids2[1:])
     with pytest.raises(ValueError):
         fc.MultiFieldPlannerV38(defs, (0, 0), fc.VehicleParams(), num_vehicles=2).optimize_sequence()
     import multi_field_planner
