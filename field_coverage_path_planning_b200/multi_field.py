@@ -134,28 +134,25 @@ class MultiFieldPlannerV38:
             self.optimization_method = self._select_optimization_method()
 
     def _prepare_fields(self, fields_definitions: List[dict]):
-        """mfp:105-151."""
-        for field_def in fields_definitions:
-            field_id = field_def['id']
-            vertices = field_def['vertices']
-            planner = TwoLayerPathPlannerV36(vehicle_params=self.vehicle_params, field_vertices=vertices,
+        """mfp:105-151: one planner per field (centroid, area) and, per vertex, the entry / exit point with the
+        bisector of the incoming and outgoing edge directions — all vertices of a field at once."""
+        for spec in fields_definitions:
+            planner = TwoLayerPathPlannerV36(vehicle_params=self.vehicle_params, field_vertices=spec['vertices'],
                                              device=self._device)
-            centroid = planner.field_polygon.centroid.coords[0]
-            area = planner.field_polygon.area
-            entry_points, exit_points = [], []
-            fv = planner.field_vertices
-            for i, vertex in enumerate(fv):
-                v_in = np.array(vertex) - np.array(fv[i - 1])
-                v_in = v_in / np.linalg.norm(v_in)
-                v_out = np.array(fv[(i + 1) % len(fv)]) - np.array(vertex)
-                v_out = v_out / np.linalg.norm(v_out)
-                v_avg = (v_in + v_out) / 2
-                v_avg = v_avg / np.linalg.norm(v_avg) if np.linalg.norm(v_avg) > 0.1 else v_in
-                entry_points.append((np.array(vertex), v_avg))
-                exit_points.append((np.array(vertex), v_avg))
-            self.fields[field_id] = FieldData(id=field_id, vertices=np.array(vertices), planner=planner,
-                                              centroid=centroid, area=area, entry_points=entry_points,
-                                              exit_points=exit_points)
+            P = np.asarray(planner.field_vertices, dtype=np.float64)            # [n, 2]
+            into = P - np.roll(P, 1, axis=0)                                     # edge arriving at vertex i
+            away = np.roll(P, -1, axis=0) - P                                    # edge leaving it
+            into /= np.hypot(into[:, 0], into[:, 1])[:, None]
+            away /= np.hypot(away[:, 0], away[:, 1])[:, None]
+            mid = (into + away) / 2
+            mlen = np.hypot(mid[:, 0], mid[:, 1])
+            keep = mlen > 0.1                                                    # a U-turn vertex keeps the incoming edge
+            heading = np.where(keep[:, None], mid / np.where(keep, mlen, 1.0)[:, None], into)
+            gates = [(P[i].copy(), heading[i].copy()) for i in range(len(P))]
+            poly = planner.field_polygon
+            self.fields[spec['id']] = FieldData(id=spec['id'], vertices=np.array(spec['vertices']), planner=planner,
+                                                centroid=poly.centroid.coords[0], area=poly.area,
+                                                entry_points=gates, exit_points=list(gates))
 
     def _select_optimization_method(self) -> str:
         """mfp:153-162."""
@@ -223,25 +220,25 @@ class MultiFieldPlannerV38:
             solver = GeneticAlgorithmSolver(config, seed=self._seed, device=self._device)
             optimal_route_indices, stats = solver.solve(distance_matrix_, verbose=self.verbose)
             stats['method'] = 'genetic'
-        optimal_route_ids = [node_ids[i] for i in optimal_route_indices]
-        field_sequence = [i for i in optimal_route_ids if i != "depot"]
-        connections = [self._find_best_connection("depot", field_sequence[0])]
-        for i in range(len(field_sequence) - 1):
-            connections.append(self._find_best_connection(field_sequence[i], field_sequence[i + 1]))
-        connections.append(self._find_best_connection(field_sequence[-1], "depot"))
-        total_transfer_distance = 0
-        for c in connections:
-            total_transfer_distance += c.distance
+        return self._route_of(optimal_route_indices, node_ids, stats)
+
+    def _route_of(self, order, node_ids, stats) -> OptimizedRoute:
+        """mfp:193-233: the fields in tour order, the best connection of every hop (depot -> first ... last -> depot:
+        look-ups into the connection tables) and the totals."""
+        sequence = [node_ids[k] for k in order if node_ids[k] != "depot"]
+        stops = ["depot"] + sequence + ["depot"]
+        hops = [self._find_best_connection(a, b) for a, b in zip(stops[:-1], stops[1:])]
+        transfer = 0
+        for hop in hops:                       # left to right, as the reference accumulates (mfp:199-210)
+            transfer += hop.distance
         if self.work_distance == "planned":
-            planned = self.planned_work_lengths()
-            stats['planned'] = planned
-            total_work_distance = sum(planned[f]['length'] for f in field_sequence)
+            stats['planned'] = planned = self.planned_work_lengths()
+            work = sum(planned[f]['length'] for f in sequence)
         else:
-            total_work_distance = sum(self.fields[f].area / self.vehicle_params.working_width for f in field_sequence)
-        return OptimizedRoute(field_sequence=field_sequence, connections=connections,
-                              total_transfer_distance=total_transfer_distance,
-                              total_work_distance=total_work_distance,
-                              total_distance=total_transfer_distance + total_work_distance,
+            width = self.vehicle_params.working_width
+            work = sum(self.fields[f].area / width for f in sequence)
+        return OptimizedRoute(field_sequence=sequence, connections=hops, total_transfer_distance=transfer,
+                              total_work_distance=work, total_distance=transfer + work,
                               optimization_method=self.optimization_method, optimization_stats=stats)
 
     def optimize_multi_vehicle(self):
