@@ -480,6 +480,14 @@ def main():
                 "traffic": nm.get("dram_bytes"), "peak_source": peak_src,
                 "kernel_ms": {"layout+scan": k_layout, "plan_kernel": k_plan, "cover_kernel": k_cover, "step": step_ms},
                 "algorithmic_bytes_per_launch": {"plan_kernel": bytes_plan, "cover_kernel": bytes_cover},
+                "per_kernel": {
+                    "plan_gen_kernel": {"ms": k_plan, "achieved": bytes_plan / (k_plan * 1e-3) / 1e9,
+                                        "frac": bytes_plan / (k_plan * 1e-3) / 1e9 / peak,
+                                        **{k: ncu_metrics("plan_gen_kernel", w.name).get(k) for k in ("issue_slot_frac", "fp64_pipe_frac")}},
+                    "cover_kernel": {"ms": k_cover, "achieved": bytes_cover / (k_cover * 1e-3) / 1e9,
+                                     "frac": bytes_cover / (k_cover * 1e-3) / 1e9 / peak,
+                                     **{k: (ncu_metrics("cover_kernel", w.name) or ncu_metrics("cover_work_kernel", w.name)).get(k)
+                                        for k in ("issue_slot_frac", "fp64_pipe_frac")}}},
                 "ncu_source": nm.get("source"),
                 "note": "both hot kernels are instruction-issue bound (FP64 + integer), not HBM bound: the occupancy grid "
                         "lives in shared memory and most of the band is counted in closed form, so `frac` (algorithmic "
