@@ -630,15 +630,28 @@ def _enqueue_fetch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, offse
         total_out = o_off + ((B + 1) * 8 if need_off else 0)
         pooled = _ResultPool.get(total_out)
         ho = pooled[0] if pooled is not None else _Staging.get(dev, db.slot).host_out(max(total_out, 256))
-        if nb_sum:
-            ho[:nb_sum].copy_(buffers.d_sum[:nb_sum], non_blocking=True)
-        if F:
-            ho[o_cost:o_cost + F * 8].view(torch.float64).copy_(buffers.d_cost[:F], non_blocking=True)
-            ho[o_best:o_best + F * 8].view(torch.int64).copy_(buffers.d_best[:F], non_blocking=True)
-        if need_off:
-            ho[o_off:o_off + (B + 1) * 8].view(torch.int64).copy_(buffers.d_off[:B + 1], non_blocking=True)
-        pf.event = torch.cuda.Event()
-        pf.event.record(torch.cuda.current_stream(dev))
+        # the copies run on a COPY stream behind an event of the launching stream: the next batch's kernels (already
+        # enqueued by a pipelining caller) must not wait for PCIe — at 737 280 candidates the 130 MB of summaries
+        # share the link with the 360 MB of the previous batch's winners' paths
+        # (small read-backs stay on the launching stream: the extra stream costs more than it hides.)  The device
+        # buffers stay referenced by the pending fetch / the result until the event has been waited for, so the
+        # allocator cannot hand them out while the copy runs.
+        main = torch.cuda.current_stream(dev)
+        cs = _copy_stream(dev) if total_out >= (8 << 20) else main
+        if cs is not main:
+            done = torch.cuda.Event()
+            done.record(main)
+            cs.wait_event(done)
+        with torch.cuda.stream(cs):
+            if nb_sum:
+                ho[:nb_sum].copy_(buffers.d_sum[:nb_sum], non_blocking=True)
+            if F:
+                ho[o_cost:o_cost + F * 8].view(torch.float64).copy_(buffers.d_cost[:F], non_blocking=True)
+                ho[o_best:o_best + F * 8].view(torch.int64).copy_(buffers.d_best[:F], non_blocking=True)
+            if need_off:
+                ho[o_off:o_off + (B + 1) * 8].view(torch.int64).copy_(buffers.d_off[:B + 1], non_blocking=True)
+            pf.event = torch.cuda.Event()
+            pf.event.record(cs)
     pf.db, pf.buffers, pf.outputs, pf.offsets, pf.cand_base = db, buffers, outputs, offsets, cand_base
     pf.pooled, pf.ho, pf.lay = pooled, ho, (nb_sum, need_off, o_cost, o_best, o_off)
     return pf
@@ -673,14 +686,26 @@ def _fetch_device_batch(db: DeviceBatch, buffers: "BatchBuffers", outputs: str, 
 
 
 _side_streams: Dict[int, "torch.cuda.Stream"] = {}
+_copy_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """The stream the result read-back of a batch runs on (see _enqueue_fetch)."""
+    st = _copy_streams.get(dev.index)
+    if st is None:
+        st = _copy_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    return st
 
 
 def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
     """A second stream per device for the winners' read-back of a finished batch: it must not queue behind the
-    kernels of the NEXT batch, which a pipelining caller has already launched on the main stream."""
+    kernels of the NEXT batch, which a pipelining caller has already launched on the main stream.  HIGH priority:
+    the small kernels of the winners' batch are dispatched ahead of the remaining CTAs of a 737 280-CTA grid of the
+    main stream — at default priority they waited until that grid had been dispatched completely (33 ms), the host
+    sat in result() meanwhile and the GPU idled 8 ms per step before the next submit (tools/pipeline_trace.py)."""
     st = _side_streams.get(dev.index)
     if st is None:
-        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
     return st
 
 
