@@ -296,6 +296,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    align_token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def align_start():
+        """Last part of the barrier in front of a timed region: a device-side barrier (one tiny all-reduce ENQUEUED
+        behind the host barrier + synchronize).  The ranks' hosts leave the host barrier up to a millisecond apart;
+        without it that skew lands in the first timed step's collective (rank 0 at N = 8: 2.09 ms for step 1, 1.07 ms
+        for every other step)."""
+        if world > 1:
+            dist.all_reduce(align_token)
+
     def max_over_ranks(x: float) -> float:
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
@@ -312,6 +322,7 @@ def main():
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
+    align_start()
     sampler.sm.clear()
     sampler.power.clear()
     sampler.reasons.clear()
@@ -385,6 +396,7 @@ def main():
         s2.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
+        align_start()
         s2.sm.clear()
         s2.power.clear()
         s2.reasons.clear()
