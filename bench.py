@@ -16,8 +16,10 @@ geofence validation -> coverage rasterisation -> per-field argmin (+ the cross-G
 value      candidates/s over EXACTLY K steps, inputs resident in HBM (CUDA events, max over ranks)
 sustained  the same step repeated for >= --sustain seconds (default 2 s) with no host synchronisation inside,
            SM clocks sampled under load — the burst of K steps may run at boost clocks a long job does not keep
-e2e        same metric through the public API plan_batch(host numpy) -> host numpy: host set-up, pinned H2D
-           copies, kernels, D2H of all summaries + the argmin + every field's WINNING path and speeds
+e2e        same metric through the public API plan_batch(host numpy fields + candidate axes, winners=True) -> host
+           numpy: host set-up, pinned H2D copies, kernels, D2H of all summaries + the argmin + every field's WINNING
+           path and speeds, every step.  e2e.value = the throughput form of the call (wait=False: batch k+1 is
+           submitted before the result of batch k is collected), e2e.serial_value = one call at a time
 argmin_ok  the (merged) per-field argmin of the timed steps equals the argmin of the whole job's candidates
            evaluated shard by shard on one GPU and merged in numpy (outside the timed region)
 roofline   the dominant kernel: issue-slot and FP64-pipe utilisation from the committed ncu capture of this
