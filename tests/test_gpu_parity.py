@@ -481,6 +481,18 @@ def test_edge_cases(fc):
         fc.plan_batch([RECT], fc.VehicleParams(), grid_h=0.0333)          # not an even multiple of 1e-4 m
     res = fc.plan_batch([RECT], fc.VehicleParams(), coverage=False)
     assert int(res.summary["cov_total"][0]) == 0 and int(res.summary["n_main"][0]) == 1256
+    # the same edge cases in factored form and through the asynchronous call: an empty range of the product, a
+    # one-candidate product, winners of an empty batch
+    ax = fc.candidate_axes(1, radii=[7.0, 8.0], start_corners=[0, 1])
+    for outputs in ("summary", "paths"):
+        e = fc.plan_batch([RECT], fc.VehicleParams(), dict(ax, range=(2, 2)), outputs=outputs, winners=True, wait=False).result()
+        assert len(e.summary) == 0 and int(e.best_cand[0]) == -1 and e.winner_paths == {}
+        one = fc.plan_batch([RECT], fc.VehicleParams(), dict(ax, range=(3, 4)), outputs=outputs, winners=True)
+        full = fc.plan_batch([RECT], fc.VehicleParams(), ax, outputs=outputs)
+        assert one.summary.tobytes() == full.summary[3:4].tobytes() and int(one.best_cand[0]) == 0
+        assert len(one.winner_paths[0][0]) == int(one.summary["n_main"][0] + one.summary["n_head"][0])
+    with pytest.raises(fc.FcppError):
+        fc.plan_batch([RECT], fc.VehicleParams(), ax, device="cpu")
 
 
 def test_clothoid_turn_model_vs_scipy_oracle(fc):
