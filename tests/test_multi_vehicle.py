@@ -46,6 +46,18 @@ def test_host_seeding_equals_oracle_seeding(gold):
         assert np.array_equal(a, b), key
 
 
+def test_host_seeding_equals_sklearn_kmeans_plusplus(gold):
+    """Where scikit-learn is installed (this image has it): the product's seeding == sklearn.cluster.kmeans_plusplus
+    with RandomState(42) on the centred data — what INTEGRATION.md's reference-side stub relies on."""
+    sk = pytest.importorskip("sklearn.cluster")
+    from field_coverage_path_planning_b200 import multi_vehicle as mv
+    z, meta = gold
+    for key in meta["scenarios"]:
+        X = z[key + "_pts"] - z[key + "_pts"].mean(axis=0)
+        _, idx = sk.kmeans_plusplus(X, _k(key), random_state=np.random.RandomState(42))
+        assert np.array_equal(idx, mv.kmeans_plusplus_seeds(X, _k(key), np.random.RandomState(42))), key
+
+
 def test_reference_module_names_and_default_path_error(gold):
     """`from multi_vehicle_planner import MultiVehiclePlanner, MultiVehicleRoute` (mfp:26); the reference's default
     path imports a module that is not in its tree (mvp:131) — recorded in the fixture, reproduced by the drop-in."""
