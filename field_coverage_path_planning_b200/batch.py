@@ -814,6 +814,15 @@ class PendingBatch:
         self.args = (want_curvature, cost, cand_base, copy_summary, winners, corner_bits)
         self._res = None
 
+    def __del__(self):
+        # an abandoned batch: its read-back may still be in flight into pooled pinned memory / out of buffers that
+        # the allocator is about to hand out again — wait for it before letting go
+        try:
+            if self._res is None and self.pf is not None:
+                self.pf.event.synchronize()
+        except Exception:
+            pass
+
     def result(self) -> "BatchResult":
         if self._res is not None:
             return self._res

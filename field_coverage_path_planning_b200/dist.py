@@ -180,6 +180,13 @@ class PendingShardedBatch:
         self.lo, self.hi, self.speculated = lo, hi, speculated
         self._res = None
 
+    def __del__(self):
+        try:        # an abandoned batch: wait for its read-back before the buffers go back to their pools
+            if self._res is None and self.pf is not None:
+                self.pf.event.synchronize()
+        except Exception:
+            pass
+
     def result(self):
         from .batch import _Hints, _finish_fetch, _side_stream, fetch_winner_paths
         if self._res is not None:
