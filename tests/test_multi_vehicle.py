@@ -58,6 +58,33 @@ def test_host_seeding_equals_sklearn_kmeans_plusplus(gold):
         assert np.array_equal(idx, mv.kmeans_plusplus_seeds(X, _k(key), np.random.RandomState(42))), key
 
 
+def test_oracle_kmeans_equals_sklearn_on_random_clouds():
+    """Beyond the 14 fixtures: where scikit-learn is installed, the numpy restatement gives the labels of
+    sklearn.cluster.KMeans(n_clusters=k, random_state=42).fit_predict on 60 seeded random clouds (2 .. 9 clusters,
+    5 .. 400 points, uniform / clustered / collinear)."""
+    sk = pytest.importorskip("sklearn.cluster")
+    import warnings
+    from oracle import kmeans
+    rng = np.random.default_rng(2026)
+    for trial in range(60):
+        n, k = int(rng.integers(5, 400)), int(rng.integers(2, 10))
+        k = min(k, n)
+        kind = trial % 3
+        if kind == 0:
+            X = rng.uniform(0, 5000, (n, 2))
+        elif kind == 1:
+            c = rng.uniform(0, 6000, (4, 2))
+            X = c[rng.integers(0, 4, n)] + rng.normal(0, 200, (n, 2))
+        else:
+            t = rng.uniform(0, 8000, n)
+            X = np.stack([t, -0.7 * t + rng.normal(0, 3, n)], axis=1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = sk.KMeans(n_clusters=k, random_state=42).fit_predict(X)
+        got, _, _ = kmeans.kmeans_labels(X, k)
+        assert np.array_equal(got, want), (trial, n, k, int((got != want).sum()))
+
+
 def test_reference_module_names_and_default_path_error(gold):
     """`from multi_vehicle_planner import MultiVehiclePlanner, MultiVehicleRoute` (mfp:26); the reference's default
     path imports a module that is not in its tree (mvp:131) — recorded in the fixture, reproduced by the drop-in."""
@@ -93,6 +120,35 @@ def test_device_lloyd_reproduces_the_reference_labels(gold):
     batch = mv.kmeans_batch([z[k + "_pts"] for k in keys], [_k(k) for k in keys])
     for key, (labels, _, _, _) in zip(keys, batch):
         assert np.array_equal(labels, z[key + "_labels"]), key
+
+
+@pytest.mark.gpu
+def test_device_lloyd_equals_oracle_on_random_clouds_in_one_launch():
+    """60 seeded random clouds (the set test_oracle_kmeans_equals_sklearn_on_random_clouds pins to scikit-learn) as ONE
+    batched launch, one CTA per cloud: labels and iteration counts of the numpy oracle, centres <= 1e-8."""
+    from oracle import kmeans
+    from field_coverage_path_planning_b200 import multi_vehicle as mv
+    rng = np.random.default_rng(2026)
+    clouds, ks = [], []
+    for trial in range(60):
+        n, k = int(rng.integers(5, 400)), int(rng.integers(2, 10))
+        k = min(k, n)
+        kind = trial % 3
+        if kind == 0:
+            X = rng.uniform(0, 5000, (n, 2))
+        elif kind == 1:
+            c = rng.uniform(0, 6000, (4, 2))
+            X = c[rng.integers(0, 4, n)] + rng.normal(0, 200, (n, 2))
+        else:
+            t = rng.uniform(0, 8000, n)
+            X = np.stack([t, -0.7 * t + rng.normal(0, 3, n)], axis=1)
+        clouds.append(X)
+        ks.append(k)
+    got = mv.kmeans_batch(clouds, ks)
+    for X, k, (labels, centres, it, _) in zip(clouds, ks, got):
+        ol, oc, oit = kmeans.kmeans_labels(X, k)
+        assert np.array_equal(labels, ol) and it == oit
+        np.testing.assert_allclose(centres, oc, rtol=0, atol=1e-8)
 
 
 @pytest.mark.gpu
