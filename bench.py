@@ -221,6 +221,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and args.impl == "b200":
+        raise SystemExit("bench.py --gpus N (N > 1) must be launched with one process per GPU:\n  python -m torch.distributed.run "
+                         "--nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
     n_gpus = max(args.gpus, world)
     w = wl.WORKLOADS[args.workload](n_gpus)
     config = make_config(w, n_gpus)
