@@ -1350,6 +1350,8 @@ static bool cover_use_work_list(const fcpp_handle *h, const fcpp_batch &b)
     return (b.cover_dedupe >= 2 || (h->cover_mode & 128)) && !(h->cover_mode & 64);
 }
 
+static int dedupe_threads(const fcpp_handle *h, int64_t n) { return n <= 2 * 32 * (int64_t)h->sm_count ? 32 : 128; }
+
 // sizes + (when the batch asks for it) the de-duplication kernels that precede the coverage kernel
 static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream_t st, CoverLaunch &L)
 {
@@ -1386,14 +1388,16 @@ static cudaError_t cover_prepare(fcpp_handle *h, const fcpp_batch &b, cudaStream
             if (e != cudaSuccess) return e;
             h->dedupe_cap = cap;
         }
-        const unsigned g = (unsigned)((n + 127) / 128);
-        cover_key_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash);
-        cover_rep_kernel<<<g, 128, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash, L.d_rep);
+        // (one thread per candidate, latency bound: small batches use 32-thread CTAs to reach more SMs)
+        const int th = dedupe_threads(h, n);
+        const unsigned g = (unsigned)((n + th - 1) / th);
+        cover_key_kernel<<<g, th, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash);
+        cover_rep_kernel<<<g, th, 0, st>>>(h->d_rec, n, L.keys, L.vals, cap - 1, L.hash, L.d_rep);
         h->launches += 2;
         if (cover_use_work_list(h, b)) {
             e = cudaMemsetAsync(L.counters, 0, 2 * sizeof(int32_t), st);
             if (e != cudaSuccess) return e;
-            cover_list_kernel<<<g, 128, 0, st>>>(n, L.d_rep, L.work, L.counters);
+            cover_list_kernel<<<g, th, 0, st>>>(n, L.d_rep, L.work, L.counters);
             h->launches++;
         } else {
             L.work = nullptr;
@@ -1409,7 +1413,8 @@ static cudaError_t cover_finish(fcpp_handle *h, const fcpp_batch &b, const fcpp_
 {
     if (!L.d_rep) return cudaSuccess;
     const int64_t n = b.n_cand;
-    cover_copy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(o.summary, n, L.d_rep, L.keys, L.vals, L.hash);
+    const int th = dedupe_threads(h, n);
+    cover_copy_kernel<<<(unsigned)((n + th - 1) / th), th, 0, st>>>(o.summary, n, L.d_rep, L.keys, L.vals, L.hash);
     h->launches++;
     return cudaGetLastError();
 }
